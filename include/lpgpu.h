@@ -1,0 +1,125 @@
+/* include/lpgpu.h -- C ABI of the B200 Landau-Poisson hot path (liblpgpu.so).
+ *
+ * The reference (ClarkPennie/landau-poisson-solver) has no plugin/FFI interface: the seam is the
+ * set of free functions its main() calls inside the time loop (LP_ompi.cpp:662-813).  Each entry
+ * point below names the reference call it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions kept from the reference: the caller owns every host array; `U` is the single
+ * source of truth between phases, host layout AoS U[6*k+l] with k = i*Nv^3 + j1*Nv^2 + j2*Nv + j3
+ * (advection_1.cpp:75-80); spectral arrays are C-order N^3 with interleaved (re,im) complex
+ * (fftw_complex); calls are synchronous at the boundary unless stated; one caller thread per
+ * context.  Where the reference returns void and exits on error, these return 0 on success and
+ * a non-zero LPGPU_E* code otherwise (lpgpu_last_error() gives the text).
+ *
+ * There is no CPU fallback: every compute entry point fails with LPGPU_ENODEV when no CUDA
+ * device is usable.
+ */
+#ifndef LPGPU_H
+#define LPGPU_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPGPU_OK 0
+#define LPGPU_EINVAL 1   /* bad argument / unsupported option (e.g. gamma != -3) */
+#define LPGPU_ENODEV 2   /* no usable CUDA device */
+#define LPGPU_ECUDA 3    /* CUDA runtime error */
+#define LPGPU_ENOMEM 4
+
+typedef struct lpgpu_ctx lpgpu_ctx;
+
+/* Mirrors the scalars the reference reads from LPsolver-input.txt (InputParsing.cpp:291-470)
+ * plus the shard this context owns.  x_begin/x_count select the contiguous block of spatial
+ * cells held by this GPU (the reference's chunk_Nx split, LP_ompi.cpp:208-220, :673);
+ * single GPU: x_begin = 0, x_count = Nx.  Homogeneous: Nx is ignored, one cell. */
+typedef struct lpgpu_params {
+  int Nx, Nv, N;
+  double Lv, Lx, nu, dt;
+  int gamma;        /* only -3 (Landau/Coulomb) is implemented */
+  int homogeneous;  /* reference flag Homogeneous */
+  int x_begin, x_count;
+  int device;       /* CUDA device ordinal */
+  int computeq_variant; /* 0 = default (fastest validated), 1 = simple reference kernel */
+} lpgpu_params;
+
+const char *lpgpu_last_error(void);
+int lpgpu_device_count(void);
+
+/* Replaces the start-up calls createCCtAndPivot() and generate_conv_weights() (LP_ompi.cpp:375,
+ * :424; conservationRoutines.cpp:159-216; collisionRoutines_1.cpp:220-237) and the allocation
+ * of the collision/advection work arrays (LP_ompi.cpp:227-348). */
+int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out);
+int lpgpu_finalize(lpgpu_ctx *c);
+/* Run all work of this context on the given cudaStream_t (passed as void*); NULL = default. */
+int lpgpu_set_stream(lpgpu_ctx *c, void *cuda_stream);
+int lpgpu_synchronize(lpgpu_ctx *c);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long lpgpu_launch_count(const lpgpu_ctx *c);
+
+/* ---- state transfer: replaces MPI_Bcast(U) at LP_ompi.cpp:658 and :813 ------------------- */
+/* U_host: this shard only, x_count*Nv^3*6 doubles, reference AoS layout. */
+int lpgpu_upload_U(lpgpu_ctx *c, const double *U_host);
+int lpgpu_download_U(lpgpu_ctx *c, double *U_host);
+
+/* ---- whole phases ----------------------------------------------------------------------- */
+/* RK3(U), LP_ompi.cpp:666 / advection_1.cpp:412-576.  Single-shard contexts only
+ * (x_count == Nx); sharded runs drive the three calls below once per stage. */
+int lpgpu_advect_rk3(lpgpu_ctx *c);
+/* setInit_spectral + for every local cell ComputeQ, conserveMoments, RK4 + the scatter of the 5
+ * updated coefficients into U: LP_ompi.cpp:671-754. */
+int lpgpu_collide_step(lpgpu_ctx *c);
+/* nsteps passes of the while(t<nT) body without diagnostics (single shard). */
+int lpgpu_step(lpgpu_ctx *c, int nsteps);
+
+/* ---- sharded advection: one exchange per SSP-RK3 stage (stage = 0,1,2) ------------------- */
+/* Device addresses (in this context's memory) for the exchange of stage `stage`:
+ *   ms_local  : 2*x_count doubles written by lpgpu_advect_reduce: (m_i, s_i) per local cell
+ *   ms_all    : 2*Nx doubles the caller must fill (all-gather of every shard's ms_local)
+ *   send_left / send_right : first / last owned x-plane of the stage input (6*Nv^3 doubles each)
+ *   recv_left / recv_right : halo planes to fill from the left / right neighbour's
+ *                            send_right / send_left (periodic in x, advection_1.cpp:297,306)  */
+typedef struct lpgpu_exchange {
+  double *ms_local, *ms_all;
+  double *send_left, *send_right, *recv_left, *recv_right;
+  long long plane_doubles;
+} lpgpu_exchange;
+int lpgpu_advect_exchange_info(lpgpu_ctx *c, int stage, lpgpu_exchange *out);
+/* per-cell density sums of the stage input (asynchronous on the context's stream) */
+int lpgpu_advect_reduce(lpgpu_ctx *c, int stage);
+/* after the caller's all-gather + halo exchange: field integrals, DG right-hand side and the
+ * SSP combination of this stage (asynchronous on the context's stream) */
+int lpgpu_advect_apply(lpgpu_ctx *c, int stage);
+
+/* ---- fine-grained entry points (host buffers, B cells per call) -------------------------- */
+/* void setInit_spectral(double *U, double **f)            SetInit_1.h:48 ; f: x_count*N^3 */
+int lpgpu_setInit_spectral(lpgpu_ctx *c, double *f_host);
+/* void fft3D(fftw_complex *in, fftw_complex *out)         collisionRoutines_1.cpp:285 */
+int lpgpu_fft3D(lpgpu_ctx *c, const double *in, double *out, int B);
+/* void FS(fftw_complex *in, fftw_complex *out)            collisionRoutines_1.cpp:363 (real part in out[.][0], imag set to 0) */
+int lpgpu_FS(lpgpu_ctx *c, const double *in, double *out, int B);
+/* void ComputeQ(double *f, fftw_complex *qHat, double **conv_weights)   collisionRoutines_1.h:72 */
+int lpgpu_ComputeQ(lpgpu_ctx *c, const double *f, double *qHat, int B);
+/* void conserveMoments(fftw_complex *qHat, ...)           conservationRoutines.h:28 */
+int lpgpu_conserveMoments(lpgpu_ctx *c, double *qHat, int B);
+/* ComputeQ + conserveMoments with everything resident on the device: evaluates the B cells
+ * currently sampled by lpgpu_sample_device() -- the unit of the "collision-cell evals/s" metric. */
+int lpgpu_sample_device(lpgpu_ctx *c);
+int lpgpu_eval_device(lpgpu_ctx *c, int B);
+/* read back stage spectra of the last lpgpu_collide_step: which = 0..3 (qHat, Q1_fft..Q3_fft) */
+int lpgpu_get_stage_spectrum(lpgpu_ctx *c, int which, double *out /* x_count*N^3*2 */);
+/* field integrals of the current U (single shard): out = ce, cp[Nx], intE[Nx], intE1[Nx], intE2[Nx]
+ * -- computePhi_x_0, computeC_rho, Int_E, Int_E1st, Int_E2nd (advection_1.cpp:419-429) */
+int lpgpu_field(lpgpu_ctx *c, double *out);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+/* Partial sums over this shard: out5 = mass, P1, P2, P3, KiE (computeMass/Momentum/KiE,
+ * MomentCalculations.cpp:23-131); sum over shards for the global value.  ms_local_host (may be
+ * NULL) receives the 2*x_count (m_i, s_i) pairs needed by lpgpu_eleE_from_ms. */
+int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host);
+/* computeEleE (MomentCalculations.cpp:201-230) from the gathered per-cell sums; host-only. */
+int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms_all, double *EleE);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,269 @@
+// Advection-path kernels (sm_100a): per-cell density sums, the 1-D Poisson field integrals, the
+// DG upwind right-hand side with the SSP-RK3 stage combination, the periodic x halo, and the
+// per-step moments.  Reference: advection_1.cpp, FieldCalculations.cpp, MomentCalculations.cpp
+// under /root/reference/source.
+//
+// State layout: plane-major  U[(p*6 + c)*sv + j],  p = local x cell + 1 (planes 0 and ncell+1 are
+// the x halos), c = DG coefficient 0..5, j = j1*Nv^2 + j2*Nv + j3.  Every access below is
+// unit-stride in j across a warp; an x-plane is one contiguous 6*sv block, so a halo is one copy.
+#include "lpgpu_internal.h"
+
+#define LP_LAUNCHED(c)                                  \
+  do {                                                  \
+    (c)->launches++;                                    \
+    LP_CUDA(cudaGetLastError());                        \
+  } while (0)
+
+// fixed-order block sum of NV values per thread (deterministic run to run)
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* NV*32 */)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  #pragma unroll
+  for (int m = 0; m < NV; m++) {
+    double x = v[m];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) smem[m * 32 + wid] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    #pragma unroll
+    for (int m = 0; m < NV; m++) { double x = 0.; for (int w = 0; w < nw; w++) x += smem[m * 32 + w]; v[m] = x; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// m_i = scalev * sum_j (U0 + U5/4),  s_i = scalev * sum_j U1  -- the only quantities the nested
+// loops of computePhi_x_0_Normal / computeC_rho / Int_E* (FieldCalculations.cpp:223-243, 60-73,
+// 356-409) depend on.
+__global__ void __launch_bounds__(256) k_field_reduce(const double *__restrict__ planes, double *__restrict__ ms, int sv, double scalev)
+{
+  __shared__ double red[2 * 32];
+  const long long cell = blockIdx.x;
+  const double *u = planes + ((cell + 1) * 6) * (long long)sv;
+  double v[2] = {0., 0.};
+  for (int j = threadIdx.x; j < sv; j += blockDim.x) {
+    v[0] += u[j] + u[5LL * sv + j] / 4.;
+    v[1] += u[1LL * sv + j];
+  }
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0) { ms[2 * cell] = v[0] * scalev; ms[2 * cell + 1] = v[1] * scalev; }
+}
+int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes)
+{
+  k_field_reduce<<<c->ncell, 256, 0, c->stream>>>(planes, c->d_ms_local, c->sv, c->tab.scalev);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// Closed forms of ce = computePhi_x_0, cp = computeC_rho, intE = Int_E, intE1 = Int_E1st,
+// intE2 = Int_E2nd (advection_1.cpp:419-429) from the gathered (m_q, s_q), q = 0..Nx-1.  The scan is
+// Nx long (<= a few hundred) and sequential on purpose: ce is a catastrophic cancellation
+// (Lx/2 - O(Lx/2)), so every GPU evaluates it in the same fixed order.
+__global__ void k_field_scan(const double *__restrict__ ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
+                             double dx, double Lx)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double P = 0., acc = 0.;
+  for (int q = 0; q < Nx; q++) { const double m = ms_all[2 * q], s = ms_all[2 * q + 1]; acc += P + 0.5 * m - s / 12.; P += m; }
+  const double ce = 0.5 * Lx - acc * dx * dx / Lx;
+  fld[0] = ce;
+  P = 0.;
+  for (int q = 0; q < Nx; q++) {
+    const double m = ms_all[2 * q], s = ms_all[2 * q + 1];
+    if (q >= x_begin && q < x_begin + x_count) {
+      const double xi = (q + 0.5) * dx, xl = ((q - 0.5) + 0.5) * dx, c2 = s * dx / 2., cp = dx * P;
+      double *o = fld + 1 + 4 * (q - x_begin);
+      o[0] = cp;
+      o[1] = -ce * dx - (P + 0.5 * m - s / 12.) * dx * dx + xi * dx;
+      o[2] = (1 - m) * dx * dx / 12.;
+      o[3] = (-cp - ce + (m * xl + 0.25 * c2)) * dx / 12. + (1 - m) * dx * xi / 12. - c2 * dx / 80.;
+    }
+    P += m;
+  }
+}
+int lp_launch_field_scan(lpgpu_ctx *c)
+{
+  const double dx = c->p.Lx / c->p.Nx;
+  k_field_scan<<<1, 32, 0, c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One SSP-RK3 stage (advection_1.cpp:436-455 / 488-507 / 538-557): per DG cell
+//   tp_l = I1 - I2 - I3 + I5   (I1,I2: :72-103; I3_Normal: :284-321; I5: :323-390)
+//   H = M^-1 tp / (dx scalev)  (:449-452)
+//   stage 0: U1 = U + dt H(U);  stage 1: U2 = 3/4 U + 1/4 U1 + 1/4 dt H(U1);
+//   stage 2: U  = 1/3 U + 2/3 U2 + 2/3 dt H(U2)
+struct DgParams {
+  int Nv, sv, ncell;
+  double dv, dx, dt, scalev, Lv;
+};
+template <int STAGE>
+__global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin, const double *__restrict__ U0,
+                                                  double *__restrict__ Uout, const double *__restrict__ fld, DgParams P)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)P.ncell * P.sv) return;
+  const int sv = P.sv, Nv = P.Nv, NN = Nv * Nv;
+  const long long cell = t / sv; const int j = (int)(t % sv), j1 = j / NN;
+  const double dv = P.dv, dv2 = dv * dv, dv3 = dv2 * dv;
+  const double c1 = -P.Lv + (j1 + 0.5) * dv;
+  const double *f4 = fld + 1 + 4 * cell;
+  const double E = f4[1], E1 = f4[2], E2 = f4[3];
+  const long long own = ((cell + 1) * 6) * (long long)sv + j;
+  double u[6];
+  #pragma unroll
+  for (int c = 0; c < 6; c++) u[c] = Uin[own + (long long)c * sv];
+  double tp[6] = {0., 0., 0., 0., 0., 0.};
+  // I1: only the phi_x test function sees the v1 f volume term
+  tp[1] += dv3 * (c1 * u[0] + dv * u[2] / 12. + u[5] * c1 / 4.);
+  // I2: E f volume term (Int_fE, FieldCalculations.cpp:126-135)
+  tp[2] -= ((u[0] + u[5] / 4.) * E + u[1] * E1) * P.scalev / dv;
+  tp[5] -= u[2] * dv2 * E / 6.;
+  // I3: x faces, upwind on the sign of the v1 cell index
+  {
+    double R[6], L[6], ur, ul;
+    if (j1 < Nv / 2) {
+      const long long nb = own + 6LL * sv;    // plane p+1 (right neighbour; halo when p = ncell)
+      #pragma unroll
+      for (int c = 0; c < 6; c++) { R[c] = Uin[nb + (long long)c * sv]; L[c] = u[c]; }
+      ur = -R[1]; ul = -L[1];
+    } else {
+      const long long nb = own - 6LL * sv;    // plane p-1
+      #pragma unroll
+      for (int c = 0; c < 6; c++) { L[c] = Uin[nb + (long long)c * sv]; R[c] = u[c]; }
+      ur = R[1]; ul = L[1];
+    }
+    tp[0] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 + (R[2] - L[2]) * dv / 12. + (R[5] - L[5]) * c1 / 4.);
+    tp[1] -= 0.5 * dv3 * ((R[0] + 0.5 * ur + L[0] + 0.5 * ul) * c1 + (R[2] + L[2]) * dv / 12. + (R[5] + L[5]) * c1 / 4.);
+    tp[2] -= dv2 * (((R[0] - L[0]) * dv2 + (ur - ul) * 0.5 * dv2 + (R[2] - L[2]) * dv * c1) / 12. + (R[5] - L[5]) * dv2 * 19. / 720.);
+    tp[3] -= (R[3] - L[3]) * c1 * dv3 / 12.;
+    tp[4] -= (R[4] - L[4]) * c1 * dv3 / 12.;
+    tp[5] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 / 4. + (R[2] - L[2]) * dv * 19. / 720. + (R[5] - L[5]) * c1 * 19. / 240.);
+  }
+  // I5: v1 faces, upwind on the sign of the cell-integrated field; no flux through |v1| = Lv
+  {
+    double R[6], L[6], ur, ul;
+    if (E > 0) {
+      #pragma unroll
+      for (int c = 0; c < 6; c++) L[c] = u[c];
+      ul = -L[2];
+      if (j1 + 1 < Nv) {
+        #pragma unroll
+        for (int c = 0; c < 6; c++) R[c] = Uin[own + NN + (long long)c * sv];
+        ur = -R[2];
+      } else {
+        #pragma unroll
+        for (int c = 0; c < 6; c++) R[c] = 0.;
+        ur = 0.;
+      }
+    } else {
+      #pragma unroll
+      for (int c = 0; c < 6; c++) R[c] = u[c];
+      ur = R[2];
+      if (j1 > 0) {
+        #pragma unroll
+        for (int c = 0; c < 6; c++) L[c] = Uin[own - NN + (long long)c * sv];
+        ul = L[2];
+      } else {
+        #pragma unroll
+        for (int c = 0; c < 6; c++) L[c] = 0.;
+        ul = 0.;
+      }
+    }
+    const double gR = R[0] + 0.5 * ur + R[5] * 5. / 12., gL = L[0] + 0.5 * ul + L[5] * 5. / 12.;
+    tp[0] += dv2 * (gR - gL) * E + dv2 * (R[1] - L[1]) * E1;
+    tp[1] += dv2 * ((gR - gL) * E1 + (R[1] - L[1]) * E2);
+    tp[2] += 0.5 * (dv2 * (gR + gL) * E + dv2 * (R[1] + L[1]) * E1);
+    tp[3] += (R[3] - L[3]) * E * dv2 / 12.;
+    tp[4] += (R[4] - L[4]) * E * dv2 / 12.;
+    tp[5] += dv2 * (((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * 5. / 12. + (R[5] - L[5]) * 133. / 720.) * E + (R[1] - L[1]) * E1 * 5. / 12.);
+  }
+  const double dxs = P.dx * P.scalev;
+  double H[6];
+  H[0] = (19 * tp[0] / 4. - 15 * tp[5]) / dxs;
+  H[5] = (60 * tp[5] - 15 * tp[0]) / dxs;
+  #pragma unroll
+  for (int l = 1; l < 5; l++) H[l] = tp[l] * 12. / dxs;
+  #pragma unroll
+  for (int c = 0; c < 6; c++) {
+    const long long o = own + (long long)c * sv;
+    double r;
+    if (STAGE == 0) r = u[c] + P.dt * H[c];
+    else if (STAGE == 1) r = 0.75 * U0[o] + 0.25 * u[c] + 0.25 * P.dt * H[c];
+    else r = U0[o] / 3. + u[c] * 2. / 3. + P.dt * H[c] * 2. / 3.;
+    Uout[o] = r;
+  }
+}
+int lp_launch_dg_stage(lpgpu_ctx *c, int stage)
+{
+  DgParams P;
+  P.Nv = c->p.Nv; P.sv = c->sv; P.ncell = c->ncell; P.dv = c->tab.dv; P.dx = c->p.Lx / c->p.Nx; P.dt = c->p.dt;
+  P.scalev = c->tab.scalev; P.Lv = c->p.Lv;
+  const long long n = (long long)c->ncell * c->sv;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  // buffers: stage 0 reads U -> writes U1; stage 1 reads U1 (+U) -> U2; stage 2 reads U2 (+U) -> U
+  if (stage == 0) k_dg_stage<0><<<grid, 256, 0, c->stream>>>(c->d_U[0], c->d_U[0], c->d_U[1], c->d_fld, P);
+  else if (stage == 1) k_dg_stage<1><<<grid, 256, 0, c->stream>>>(c->d_U[1], c->d_U[0], c->d_U[2], c->d_fld, P);
+  else if (stage == 2) k_dg_stage<2><<<grid, 256, 0, c->stream>>>(c->d_U[2], c->d_U[0], c->d_U[0], c->d_fld, P);
+  else { lp_set_error("lp_launch_dg_stage: stage must be 0, 1 or 2"); return LPGPU_EINVAL; }
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// periodic halo when one context owns all of x (advection_1.cpp:297, :306)
+int lp_launch_local_halo(lpgpu_ctx *c, double *planes)
+{
+  const size_t plane = (size_t)6 * c->sv;
+  LP_CUDA(cudaMemcpyAsync(planes, planes + plane * c->ncell, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  LP_CUDA(cudaMemcpyAsync(planes + plane * (c->ncell + 1), planes + plane, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// computeMass / computeMomentum / computeKiE (MomentCalculations.cpp:23-131) partial sums over the
+// local cells: one block per cell, then one block folds the per-cell partials in cell order.
+__global__ void __launch_bounds__(256) k_moments_cell(const double *__restrict__ planes, double *__restrict__ part, int Nv, int sv,
+                                                      double dv, double Lv)
+{
+  __shared__ double red[5 * 32];
+  const long long cell = blockIdx.x;
+  const double *u = planes + ((cell + 1) * 6) * (long long)sv;
+  double v[5] = {0., 0., 0., 0., 0.};
+  for (int j = threadIdx.x; j < sv; j += blockDim.x) {
+    const int j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
+    const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv, c3 = -Lv + (j3 + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
+    const double U0 = u[j], U2 = u[2LL * sv + j], U3 = u[3LL * sv + j], U4 = u[4LL * sv + j], U5 = u[5LL * sv + j];
+    v[0] += U0 + U5 / 4.;
+    v[1] += c1 * dv * U0 + U2 * dv * dv / 12. + U5 * c1 * dv / 4.;
+    v[2] += c2 * dv * U0 + U3 * dv * dv / 12. + U5 * c2 * dv / 4.;
+    v[3] += c3 * dv * U0 + U4 * dv * dv / 12. + U5 * c3 * dv / 4.;
+    v[4] += U0 * (r2 + dv * dv / 4.) * dv + (c1 * U2 + c2 * U3 + c3 * U4) * dv * dv / 6. + U5 * (dv * dv * dv * 19. / 240. + r2 * dv / 4.);
+  }
+  block_sum<5>(v, red);
+  if (threadIdx.x == 0)
+    for (int m = 0; m < 5; m++) part[5 * cell + m] = v[m];
+}
+__global__ void k_moments_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double xs, double dv, double scalev)
+{
+  if (threadIdx.x != 0) return;
+  double v[5] = {0., 0., 0., 0., 0.};
+  for (int c = 0; c < ncell; c++)
+    for (int m = 0; m < 5; m++) v[m] += part[5 * c + m];
+  out[0] = v[0] * xs * scalev;
+  out[1] = v[1] * xs * dv * dv; out[2] = v[2] * xs * dv * dv; out[3] = v[3] * xs * dv * dv;
+  out[4] = 0.5 * v[4] * xs * dv * dv;
+}
+int lp_launch_moments(lpgpu_ctx *c, const double *planes)
+{
+  // d_B is free outside the projection: use its head for the per-cell partials
+  double *part = c->d_B;
+  k_moments_cell<<<c->ncell, 256, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv);
+  LP_LAUNCHED(c);
+  const double xs = c->p.homogeneous ? 1. : c->p.Lx / c->p.Nx;
+  k_moments_fold<<<1, 32, 0, c->stream>>>(part, c->d_mom, c->ncell, xs, c->tab.dv, c->tab.scalev);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}

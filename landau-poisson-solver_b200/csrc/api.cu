@@ -1,0 +1,393 @@
+// extern "C" boundary of liblpgpu.so (declared in include/lpgpu.h).  Host orchestration only:
+// every numerical operation is a kernel in collision.cu / computeq.cu / advection.cu.
+#include "lpgpu_internal.h"
+#include <cmath>
+#include <cstring>
+#include <new>
+
+static thread_local std::string g_err;
+void lp_set_error(const std::string &s) { g_err = s; }
+
+#define LP_TRY(expr)            \
+  do {                          \
+    int rc_ = (expr);           \
+    if (rc_ != LPGPU_OK) return rc_; \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(T **p, size_t count)
+{
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+  if (e != cudaSuccess) { lp_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return LPGPU_ENOMEM; }
+  return LPGPU_OK;
+}
+template <typename T>
+static int dev_upload(T **p, const std::vector<T> &h)
+{
+  LP_TRY(dev_alloc(p, h.size()));
+  LP_CUDA(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return LPGPU_OK;
+}
+
+extern "C" {
+
+const char *lpgpu_last_error(void) { return g_err.c_str(); }
+
+int lpgpu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
+{
+  if (!p || !out) { lp_set_error("lpgpu_init: null argument"); return LPGPU_EINVAL; }
+  *out = nullptr;
+  if (p->gamma != -3) { lp_set_error("lpgpu_init: only gamma = -3 (Landau) is implemented"); return LPGPU_EINVAL; }
+  if (p->N < 2 || p->N > 32 || (p->N & 1)) { lp_set_error("lpgpu_init: N must be even and in [2, 32]"); return LPGPU_EINVAL; }
+  if (p->Nv < 2 || p->Nv > 64 || (p->Nv & 1)) { lp_set_error("lpgpu_init: Nv must be even and in [2, 64]"); return LPGPU_EINVAL; }
+  if (!(p->Lv > 0) || !(p->dt > 0) || p->nu < 0) { lp_set_error("lpgpu_init: need Lv > 0, dt > 0, nu >= 0"); return LPGPU_EINVAL; }
+  if (!p->homogeneous) {
+    if (p->Nx < 1 || !(p->Lx > 0)) { lp_set_error("lpgpu_init: need Nx >= 1 and Lx > 0"); return LPGPU_EINVAL; }
+    if (p->x_begin < 0 || p->x_count < 1 || p->x_begin + p->x_count > p->Nx) { lp_set_error("lpgpu_init: bad shard [x_begin, x_begin + x_count)"); return LPGPU_EINVAL; }
+  }
+  const int ndev = lpgpu_device_count();
+  if (ndev <= 0) { lp_set_error("lpgpu_init: no CUDA device (this library has no CPU path)"); return LPGPU_ENODEV; }
+  if (p->device < 0 || p->device >= ndev) { lp_set_error("lpgpu_init: bad device ordinal"); return LPGPU_EINVAL; }
+  LP_CUDA(cudaSetDevice(p->device));
+
+  lpgpu_ctx *c = new (std::nothrow) lpgpu_ctx();
+  if (!c) return LPGPU_ENOMEM;
+  c->p = *p;
+  if (p->homogeneous) { c->p.Nx = 1; c->p.x_begin = 0; c->p.x_count = 1; if (!(c->p.Lx > 0)) c->p.Lx = 1.; }
+  c->N3 = p->N * p->N * p->N;
+  c->sv = p->Nv * p->Nv * p->Nv;
+  c->ncell = c->p.x_count;
+  c->stream = 0;
+  c->launches = 0;
+  lp_build_tables(c->p, c->tab);
+
+  const LpTables &t = c->tab;
+  int rc = LPGPU_OK;
+#define A_(x) if (rc == LPGPU_OK) rc = (x)
+  A_(dev_upload(&c->d_eta, t.eta));
+  A_(dev_upload(&c->d_G, t.G));
+  A_(dev_upload(&c->d_C5, t.C5));
+  { std::vector<double> cct(t.CCt, t.CCt + 25); A_(dev_upload(&c->d_CCt, cct)); }
+  A_(dev_upload(&c->d_Ffwd, t.Ffwd));
+  A_(dev_upload(&c->d_Finv, t.Finv));
+  A_(dev_upload(&c->d_T, t.T));
+  A_(dev_upload(&c->d_M, t.M));
+  A_(dev_upload(&c->d_S, t.S));
+  A_(dev_upload(&c->d_node_xi, t.node_xi));
+  A_(dev_upload(&c->d_vc, t.vc));
+  A_(dev_upload(&c->d_node_cell, t.node_cell));
+  const size_t plane = (size_t)6 * c->sv, nst = plane * (c->ncell + 2);
+  for (int s = 0; s < 3; s++) {
+    A_(dev_alloc(&c->d_U[s], nst));
+    if (rc == LPGPU_OK && cudaMemset(c->d_U[s], 0, nst * sizeof(double)) != cudaSuccess) rc = LPGPU_ECUDA;
+  }
+  A_(dev_alloc(&c->d_aos, plane * c->ncell));
+  A_(dev_alloc(&c->d_ms_local, (size_t)2 * c->ncell));
+  A_(dev_alloc(&c->d_ms_all, (size_t)2 * c->p.Nx));
+  A_(dev_alloc(&c->d_fld, (size_t)1 + 4 * c->ncell));
+  A_(dev_alloc(&c->d_mom, (size_t)5));
+  c->cap_cells = c->ncell;
+  const size_t n3 = (size_t)c->N3 * c->cap_cells;
+  A_(dev_alloc(&c->d_f, n3));
+  A_(dev_alloc(&c->d_f1, n3));
+  A_(dev_alloc(&c->d_Qv, n3));
+  A_(dev_alloc(&c->d_fhat, 2 * n3));
+  A_(dev_alloc(&c->d_tmp, 2 * n3));
+  for (int s = 0; s < 4; s++) A_(dev_alloc(&c->d_q[s], 2 * n3));
+  A_(dev_alloc(&c->d_lam, (size_t)5 * c->cap_cells));
+  A_(dev_alloc(&c->d_B, (size_t)2 * c->cap_cells * p->N * 4 * p->Nv * p->Nv));
+#undef A_
+  if (rc != LPGPU_OK) { lpgpu_finalize(c); return rc; }
+  *out = c;
+  return LPGPU_OK;
+}
+
+int lpgpu_finalize(lpgpu_ctx *c)
+{
+  if (!c) return LPGPU_OK;
+  cudaSetDevice(c->p.device);
+  cudaDeviceSynchronize();
+  double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Ffwd, c->d_Finv, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
+                    c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
+                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B};
+  for (double *q : ptrs) if (q) cudaFree(q);
+  if (c->d_node_cell) cudaFree(c->d_node_cell);
+  delete c;
+  return LPGPU_OK;
+}
+
+int lpgpu_set_stream(lpgpu_ctx *c, void *s) { if (!c) return LPGPU_EINVAL; c->stream = (cudaStream_t)s; return LPGPU_OK; }
+int lpgpu_synchronize(lpgpu_ctx *c) { if (!c) return LPGPU_EINVAL; LP_CUDA(cudaSetDevice(c->p.device)); LP_CUDA(cudaStreamSynchronize(c->stream)); return LPGPU_OK; }
+long long lpgpu_launch_count(const lpgpu_ctx *c) { return c ? c->launches : 0; }
+
+#define LP_ENTER(c)                                                        \
+  if (!(c)) { lp_set_error("null context"); return LPGPU_EINVAL; }        \
+  LP_CUDA(cudaSetDevice((c)->p.device))
+
+int lpgpu_upload_U(lpgpu_ctx *c, const double *U)
+{
+  LP_ENTER(c);
+  if (!U) { lp_set_error("lpgpu_upload_U: null U"); return LPGPU_EINVAL; }
+  const size_t n = (size_t)6 * c->sv * c->ncell;
+  LP_CUDA(cudaMemcpyAsync(c->d_aos, U, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LP_TRY(lp_launch_aos_to_planes(c, c->d_aos, c->d_U[0]));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+int lpgpu_download_U(lpgpu_ctx *c, double *U)
+{
+  LP_ENTER(c);
+  if (!U) { lp_set_error("lpgpu_download_U: null U"); return LPGPU_EINVAL; }
+  const size_t n = (size_t)6 * c->sv * c->ncell;
+  LP_TRY(lp_launch_planes_to_aos(c, c->d_U[0], c->d_aos));
+  LP_CUDA(cudaMemcpyAsync(U, c->d_aos, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+// ---- advection ------------------------------------------------------------------------------
+static int check_stage(lpgpu_ctx *c, int stage)
+{
+  if (c->p.homogeneous) { lp_set_error("advection is not defined for a homogeneous context"); return LPGPU_EINVAL; }
+  if (stage < 0 || stage > 2) { lp_set_error("stage must be 0, 1 or 2"); return LPGPU_EINVAL; }
+  return LPGPU_OK;
+}
+int lpgpu_advect_exchange_info(lpgpu_ctx *c, int stage, lpgpu_exchange *out)
+{
+  LP_ENTER(c);
+  LP_TRY(check_stage(c, stage));
+  if (!out) return LPGPU_EINVAL;
+  const size_t plane = (size_t)6 * c->sv;
+  double *in = c->d_U[stage];
+  out->ms_local = c->d_ms_local; out->ms_all = c->d_ms_all;
+  out->send_left = in + plane; out->send_right = in + plane * c->ncell;
+  out->recv_left = in; out->recv_right = in + plane * (c->ncell + 1);
+  out->plane_doubles = (long long)plane;
+  return LPGPU_OK;
+}
+int lpgpu_advect_reduce(lpgpu_ctx *c, int stage)
+{
+  LP_ENTER(c);
+  LP_TRY(check_stage(c, stage));
+  return lp_launch_field_reduce(c, c->d_U[stage]);
+}
+int lpgpu_advect_apply(lpgpu_ctx *c, int stage)
+{
+  LP_ENTER(c);
+  LP_TRY(check_stage(c, stage));
+  LP_TRY(lp_launch_field_scan(c));
+  return lp_launch_dg_stage(c, stage);
+}
+static int advect_rk3_async(lpgpu_ctx *c)
+{
+  if (c->ncell != c->p.Nx) { lp_set_error("lpgpu_advect_rk3: context is a shard; drive the per-stage calls instead"); return LPGPU_EINVAL; }
+  for (int s = 0; s < 3; s++) {
+    LP_TRY(lp_launch_local_halo(c, c->d_U[s]));
+    LP_TRY(lp_launch_field_reduce(c, c->d_U[s]));
+    LP_CUDA(cudaMemcpyAsync(c->d_ms_all, c->d_ms_local, (size_t)2 * c->ncell * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    LP_TRY(lp_launch_field_scan(c));
+    LP_TRY(lp_launch_dg_stage(c, s));
+  }
+  return LPGPU_OK;
+}
+int lpgpu_advect_rk3(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  LP_TRY(check_stage(c, 0));
+  LP_TRY(advect_rk3_async(c));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+// ---- collision ------------------------------------------------------------------------------
+static int eval_async(lpgpu_ctx *c, const double *f, double *q, int B)
+{
+  LP_TRY(lp_launch_fft3d(c, f, true, c->d_fhat, B));
+  LP_TRY(lp_launch_computeQ(c, c->d_fhat, q, B));
+  return lp_launch_conserve(c, q, B);
+}
+static int collide_async(lpgpu_ctx *c)
+{
+  const int B = c->ncell;
+  LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, B));
+  LP_TRY(eval_async(c, c->d_f, c->d_q[0], B));
+  for (int s = 1; s <= 3; s++) {
+    LP_TRY(lp_launch_fs(c, c->d_q[s - 1], s, nullptr, B));
+    LP_TRY(eval_async(c, c->d_f1, c->d_q[s], B));
+  }
+  return lp_launch_project(c, c->d_U[0], B);
+}
+int lpgpu_collide_step(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  if (!(c->p.nu > 0.)) return LPGPU_OK;    // nu = 0: collisionless (LP_ompi.cpp:669)
+  LP_TRY(collide_async(c));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+int lpgpu_step(lpgpu_ctx *c, int nsteps)
+{
+  LP_ENTER(c);
+  for (int s = 0; s < nsteps; s++) {
+    if (!c->p.homogeneous) LP_TRY(advect_rk3_async(c));
+    if (c->p.nu > 0.) LP_TRY(collide_async(c));
+  }
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+int lpgpu_sample_device(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  return lp_launch_sample(c, c->d_U[0], c->d_f, c->ncell);
+}
+int lpgpu_eval_device(lpgpu_ctx *c, int B)
+{
+  LP_ENTER(c);
+  if (B < 1 || (size_t)B > c->cap_cells) { lp_set_error("lpgpu_eval_device: B out of range"); return LPGPU_EINVAL; }
+  return eval_async(c, c->d_f, c->d_q[0], B);
+}
+
+// ---- fine-grained, host buffers: chunks of cap_cells cells ---------------------------------------
+int lpgpu_setInit_spectral(lpgpu_ctx *c, double *f_host)
+{
+  LP_ENTER(c);
+  LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, c->ncell));
+  LP_CUDA(cudaMemcpyAsync(f_host, c->d_f, (size_t)c->ncell * c->N3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+} // extern "C"
+template <typename F>
+static int chunked(lpgpu_ctx *c, int B, F body)
+{
+  if (B < 1) { lp_set_error("B must be >= 1"); return LPGPU_EINVAL; }
+  for (int b0 = 0; b0 < B; b0 += (int)c->cap_cells) {
+    const int nb = (B - b0 < (int)c->cap_cells) ? B - b0 : (int)c->cap_cells;
+    LP_TRY(body(b0, nb));
+    LP_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return LPGPU_OK;
+}
+extern "C" {
+int lpgpu_fft3D(lpgpu_ctx *c, const double *in, double *out, int B)
+{
+  LP_ENTER(c);
+  const size_t cz = (size_t)2 * c->N3;
+  return chunked(c, B, [&](int b0, int nb) -> int {
+    LP_CUDA(cudaMemcpyAsync(c->d_q[1], in + cz * b0, cz * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LP_TRY(lp_launch_fft3d(c, c->d_q[1], false, c->d_fhat, nb));
+    LP_CUDA(cudaMemcpyAsync(out + cz * b0, c->d_fhat, cz * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return LPGPU_OK;
+  });
+}
+int lpgpu_FS(lpgpu_ctx *c, const double *in, double *out, int B)
+{
+  LP_ENTER(c);
+  const size_t cz = (size_t)2 * c->N3;
+  return chunked(c, B, [&](int b0, int nb) -> int {
+    LP_CUDA(cudaMemcpyAsync(c->d_q[1], in + cz * b0, cz * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LP_TRY(lp_launch_fs(c, c->d_q[1], 0, c->d_fhat, nb));
+    LP_CUDA(cudaMemcpyAsync(out + cz * b0, c->d_fhat, cz * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return LPGPU_OK;
+  });
+}
+int lpgpu_ComputeQ(lpgpu_ctx *c, const double *f, double *qHat, int B)
+{
+  LP_ENTER(c);
+  const size_t rz = (size_t)c->N3, cz = 2 * rz;
+  return chunked(c, B, [&](int b0, int nb) -> int {
+    LP_CUDA(cudaMemcpyAsync(c->d_f1, f + rz * b0, rz * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LP_TRY(lp_launch_fft3d(c, c->d_f1, true, c->d_fhat, nb));
+    LP_TRY(lp_launch_computeQ(c, c->d_fhat, c->d_q[1], nb));
+    LP_CUDA(cudaMemcpyAsync(qHat + cz * b0, c->d_q[1], cz * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return LPGPU_OK;
+  });
+}
+int lpgpu_conserveMoments(lpgpu_ctx *c, double *qHat, int B)
+{
+  LP_ENTER(c);
+  const size_t cz = (size_t)2 * c->N3;
+  return chunked(c, B, [&](int b0, int nb) -> int {
+    LP_CUDA(cudaMemcpyAsync(c->d_q[1], qHat + cz * b0, cz * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LP_TRY(lp_launch_conserve(c, c->d_q[1], nb));
+    LP_CUDA(cudaMemcpyAsync(qHat + cz * b0, c->d_q[1], cz * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return LPGPU_OK;
+  });
+}
+int lpgpu_get_stage_spectrum(lpgpu_ctx *c, int which, double *out)
+{
+  LP_ENTER(c);
+  if (which < 0 || which > 3 || !out) { lp_set_error("lpgpu_get_stage_spectrum: bad argument"); return LPGPU_EINVAL; }
+  LP_CUDA(cudaMemcpyAsync(out, c->d_q[which], (size_t)2 * c->N3 * c->ncell * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+int lpgpu_field(lpgpu_ctx *c, double *out)
+{
+  LP_ENTER(c);
+  LP_TRY(check_stage(c, 0));
+  if (c->ncell != c->p.Nx) { lp_set_error("lpgpu_field: single-shard contexts only"); return LPGPU_EINVAL; }
+  LP_TRY(lp_launch_field_reduce(c, c->d_U[0]));
+  LP_CUDA(cudaMemcpyAsync(c->d_ms_all, c->d_ms_local, (size_t)2 * c->ncell * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  LP_TRY(lp_launch_field_scan(c));
+  std::vector<double> h((size_t)1 + 4 * c->ncell);
+  LP_CUDA(cudaMemcpyAsync(h.data(), c->d_fld, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  const int Nx = c->p.Nx;
+  out[0] = h[0];
+  for (int i = 0; i < Nx; i++)
+    for (int a = 0; a < 4; a++) out[1 + a * Nx + i] = h[1 + 4 * i + a];
+  return LPGPU_OK;
+}
+
+// ---- diagnostics ----------------------------------------------------------------------------
+int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host)
+{
+  LP_ENTER(c);
+  if (!out5) return LPGPU_EINVAL;
+  LP_TRY(lp_launch_moments(c, c->d_U[0]));
+  LP_CUDA(cudaMemcpyAsync(out5, c->d_mom, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (ms_local_host && !c->p.homogeneous) {
+    LP_TRY(lp_launch_field_reduce(c, c->d_U[0]));
+    LP_CUDA(cudaMemcpyAsync(ms_local_host, c->d_ms_local, (size_t)2 * c->ncell * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+// computeEleE (MomentCalculations.cpp:201-230) written in terms of the per-cell sums
+// m_i = scalev sum (U0 + U5/4), s_i = scalev sum U1.  Pure host arithmetic on 2*Nx numbers.
+int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms, double *EleE)
+{
+  if (!p || !ms || !EleE || p->Nx < 1) return LPGPU_EINVAL;
+  const int Nx = p->Nx;
+  const double Lx = p->Lx, dx = Lx / Nx;
+  double P = 0., acc = 0.;
+  for (int q = 0; q < Nx; q++) { acc += P + 0.5 * ms[2 * q] - ms[2 * q + 1] / 12.; P += ms[2 * q]; }
+  const double ce = 0.5 * Lx - acc * dx * dx / Lx;
+  double t4 = 0., t5 = 0., t6 = 0.;
+  P = 0.;
+  for (int i = 0; i < Nx; i++) {
+    const double m = ms[2 * i], s = ms[2 * i + 1];
+    const double cp = dx * P, cc = dx * dx * (0.5 * m - s / 12.);
+    const double xi = (i + 0.5) * dx, xl = i * dx, xr = (i + 1.0) * dx, s2 = s * dx / 2.;
+    t4 += dx * cp + cc;
+    t5 += dx * xi * cp + (m * ((xr * xr * xr - xl * xl * xl) / 3. - xl * xi * dx) - s * dx * dx * xi / 12.);
+    t6 += cp * cp * dx + 2 * cp * cc + (m * m * dx * dx * dx / 3. + s2 * s2 * dx / 30. - m * s2 * dx * dx / 6.);
+    P += m;
+  }
+  *EleE = 0.5 * (ce * ce * Lx + Lx * Lx * Lx / 3. - ce * Lx * Lx + 2 * ce * t4 - 2 * t5 + t6);
+  return LPGPU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,399 @@
+// Collision-path kernels (sm_100a): DG -> spectral sampling, shifted 3-D transforms, the
+// weighted spectral convolution ComputeQ, the conservation projection, the RK stage updates and
+// the Fourier -> DG projection.  Reference lines are cited per kernel; paths are relative to
+// /root/reference/source.
+#include "lpgpu_internal.h"
+
+#define LP_LAUNCHED(c)                                  \
+  do {                                                  \
+    (c)->launches++;                                    \
+    LP_CUDA(cudaGetLastError());                        \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// complex helpers (double2 = (re, im))
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{ return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void cfma(double2 &acc, double2 a, double2 b)
+{
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout changes between the reference's AoS U[6k+l] and the device's plane-major
+// U[(p*6 + c)*sv + j] (p = local x cell + 1; planes 0 and ncell+1 are x halos)
+__global__ void k_aos_to_planes(const double *__restrict__ aos, double *__restrict__ planes, long long n, int sv)
+{
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  long long cell = t / sv; int j = (int)(t % sv);
+  const double *s = aos + 6 * t;
+  double *d = planes + ((cell + 1) * 6) * (long long)sv + j;
+  #pragma unroll
+  for (int c = 0; c < 6; c++) d[(long long)c * sv] = s[c];
+}
+__global__ void k_planes_to_aos(const double *__restrict__ planes, double *__restrict__ aos, long long n, int sv)
+{
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  long long cell = t / sv; int j = (int)(t % sv);
+  const double *s = planes + ((cell + 1) * 6) * (long long)sv + j;
+  double *d = aos + 6 * t;
+  #pragma unroll
+  for (int c = 0; c < 6; c++) d[c] = s[(long long)c * sv];
+}
+int lp_launch_aos_to_planes(lpgpu_ctx *c, const double *aos, double *planes)
+{
+  long long n = (long long)c->ncell * c->sv;
+  k_aos_to_planes<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(aos, planes, n, c->sv);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+int lp_launch_planes_to_aos(lpgpu_ctx *c, const double *planes, double *aos)
+{
+  long long n = (long long)c->ncell * c->sv;
+  k_planes_to_aos<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(planes, aos, n, c->sv);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// setInit_spectral (SetInit_1.cpp:396-436): evaluate the DG polynomial at the N^3 spectral nodes
+__global__ void k_sample(const double *__restrict__ planes, double *__restrict__ f, const int *__restrict__ node_cell,
+                         const double *__restrict__ node_xi, int N, int Nv, int sv, long long total)
+{
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int N3 = N * N * N;
+  long long cell = t / N3; int q = (int)(t % N3);
+  int n = q % N, m = (q / N) % N, l = q / (N * N);
+  int j = (node_cell[l] * Nv + node_cell[m]) * Nv + node_cell[n];
+  double x1 = node_xi[l], x2 = node_xi[m], x3 = node_xi[n];
+  const double *u = planes + ((cell + 1) * 6) * (long long)sv + j;
+  f[t] = u[0] + u[2LL * sv] * x1 + u[3LL * sv] * x2 + u[4LL * sv] * x3 + u[5LL * sv] * (x1 * x1 + x2 * x2 + x3 * x3);
+}
+int lp_launch_sample(lpgpu_ctx *c, const double *planes, double *f, int ncell)
+{
+  long long total = (long long)ncell * c->N3;
+  k_sample<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(planes, f, c->d_node_cell, c->d_node_xi, c->p.N, c->p.Nv, c->sv, total);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shifted transforms.  fft3D (collisionRoutines_1.cpp:285-319) and FS (:363-398) are separable:
+// per dimension  fhat(eta_k) = sum_j Ffwd[k][j] f(v_j)  and  Q(v_j) = sum_k Finv[j][k] Qhat(eta_k)
+// with the N x N complex matrices built in tables.cpp (pre-phase * DFT * post-phase folded).
+// N <= 32, so each 1-D transform is a dense N-point sum out of shared memory; the two kernels
+// below cover axes (1,2) of one x-slab and axis 0 of one y-slab.
+//
+// EPI: 0 complex out; 1..3 = FS real part + RK stage update (RK4_Inhomo/RK4_Homo,
+// collisionRoutines_1.cpp:910-941 / 1094-1123); 4 = FS real part stored as (re, 0).
+struct FsEpilogue {
+  double scaleL, scale3, dt, nu;
+  const double *f;   // stage-0 samples
+  double *Qv;        // first-stage Q (written in mode 1, read in 2,3)
+  double *f1;        // stage input for the next ComputeQ
+};
+
+template <bool IN_REAL, int EPI>
+__global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, double *__restrict__ out,
+                                                 const double2 *__restrict__ Fm, int N, FsEpilogue ep)
+{
+  extern __shared__ double2 sm2[];
+  const int P = N + 1;
+  double2 *X = sm2, *Y = X + N * P, *F = Y + N * P;
+  const long long slab = blockIdx.x;                 // cell*N + i
+  const int tid = threadIdx.x, r = tid / N, cc = tid % N;
+  const long long g = slab * N * N + tid;
+  if (IN_REAL) X[r * P + cc] = make_double2(in[g], 0.);
+  else X[r * P + cc] = reinterpret_cast<const double2 *>(in)[g];
+  F[r * P + cc] = Fm[tid];
+  __syncthreads();
+  double2 acc = make_double2(0., 0.);
+  for (int j = 0; j < N; j++) cfma(acc, F[cc * P + j], X[r * P + j]);   // axis 2
+  Y[r * P + cc] = acc;
+  __syncthreads();
+  acc = make_double2(0., 0.);
+  for (int j = 0; j < N; j++) cfma(acc, F[r * P + j], Y[j * P + cc]);   // axis 1
+  if (EPI == 0) {
+    reinterpret_cast<double2 *>(out)[g] = acc;
+  } else {
+    const double Q = acc.x / ep.scaleL / ep.scale3;
+    if (EPI == 4) reinterpret_cast<double2 *>(out)[g] = make_double2(Q, 0.);
+    if (EPI == 1) { ep.Qv[g] = Q; ep.f1[g] = ep.f[g] + ep.dt * Q * ep.nu; }
+    if (EPI == 2) ep.f1[g] = ep.f[g] + 0.5 * ep.dt * ep.Qv[g] * ep.nu + 0.5 * ep.dt * Q * ep.nu;
+    if (EPI == 3) ep.f1[g] = ep.f[g] + 0.5 * ep.Qv[g] * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
+  }
+}
+
+// axis 0: block = (cell, j); slab X[i][k] = in[cell][i][j][k]
+__global__ void __launch_bounds__(1024) k_dft_i(const double2 *__restrict__ in, double2 *__restrict__ out,
+                                                const double2 *__restrict__ Fm, int N)
+{
+  extern __shared__ double2 sm2[];
+  const int P = N + 1;
+  double2 *X = sm2, *F = X + N * P;
+  const long long cell = blockIdx.x / N; const int j = blockIdx.x % N;
+  const int tid = threadIdx.x, i = tid / N, k = tid % N;
+  const long long g = ((cell * N + i) * N + j) * N + k;
+  X[i * P + k] = in[g];
+  F[i * P + k] = Fm[tid];
+  __syncthreads();
+  double2 acc = make_double2(0., 0.);
+  for (int a = 0; a < N; a++) cfma(acc, F[i * P + a], X[a * P + k]);
+  out[g] = acc;
+}
+
+static size_t dft_smem(int N, int arrays) { return (size_t)arrays * N * (N + 1) * sizeof(double2); }
+
+template <bool IN_REAL, int EPI>
+static int launch_jk(lpgpu_ctx *c, const double *in, double *out, const double *Fm, int B, FsEpilogue ep)
+{
+  const int N = c->p.N;
+  const size_t smem = dft_smem(N, 3);
+  LP_CUDA(cudaFuncSetAttribute(k_dft_jk<IN_REAL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dft_jk<IN_REAL, EPI><<<B * N, N * N, smem, c->stream>>>(in, out, reinterpret_cast<const double2 *>(Fm), N, ep);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *Fm, int B)
+{
+  const int N = c->p.N;
+  const size_t smem = dft_smem(N, 2);
+  LP_CUDA(cudaFuncSetAttribute(k_dft_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dft_i<<<B * N, N * N, smem, c->stream>>>(reinterpret_cast<const double2 *>(in), reinterpret_cast<double2 *>(out),
+                                              reinterpret_cast<const double2 *>(Fm), N);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, int B)
+{
+  FsEpilogue ep = {};
+  int rc = in_real ? launch_jk<true, 0>(c, in, c->d_tmp, c->d_Ffwd, B, ep) : launch_jk<false, 0>(c, in, c->d_tmp, c->d_Ffwd, B, ep);
+  if (rc) return rc;
+  return launch_i(c, c->d_tmp, out, c->d_Ffwd, B);
+}
+
+int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B)
+{
+  FsEpilogue ep;
+  ep.scaleL = c->tab.scaleL; ep.scale3 = c->tab.scale3;
+  ep.dt = c->p.dt; ep.nu = c->p.nu; ep.f = c->d_f; ep.Qv = c->d_Qv; ep.f1 = c->d_f1;
+  int rc = launch_i(c, q, c->d_tmp, c->d_Finv, B);
+  if (rc) return rc;
+  switch (mode) {
+    case 0: return launch_jk<false, 4>(c, c->d_tmp, out_complex, c->d_Finv, B, ep);
+    case 1: return launch_jk<false, 1>(c, c->d_tmp, nullptr, c->d_Finv, B, ep);
+    case 2: return launch_jk<false, 2>(c, c->d_tmp, nullptr, c->d_Finv, B, ep);
+    case 3: return launch_jk<false, 3>(c, c->d_tmp, nullptr, c->d_Finv, B, ep);
+  }
+  lp_set_error("lp_launch_fs: bad mode");
+  return LPGPU_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ComputeQ (collisionRoutines_1.cpp:691-774):
+//   Qhat[xi] = sum_{omega in win(xi)} h_eta^3 wt(omega) gHat3(xi, omega) fhat[omega] fhat[xi + N/2 - omega]
+// Variant 1 ("simple"): one thread per xi, weight rebuilt per pair from the 7 folded symbols.
+// Kept as the on-device cross-check for the tiled kernel.
+__device__ __forceinline__ void lp_window(int N, int i, int &s, int &e)
+{
+  if (i < N / 2) { s = 0; e = i + N / 2 + 1; } else { s = i - N / 2 + 1; e = N; }
+}
+__global__ void __launch_bounds__(128) k_computeQ_simple(const double2 *__restrict__ fhat, double2 *__restrict__ q,
+                                                         const double *__restrict__ G, const double *__restrict__ eta,
+                                                         int N, long long total)
+{
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int N3 = N * N * N, H = N / 2;
+  const long long cell = t / N3; const int xi = (int)(t % N3);
+  const int k = xi % N, j = (xi / N) % N, i = xi / (N * N);
+  const double2 *fh = fhat + cell * N3;
+  int si, ei, sj, ej, sk, ek;
+  lp_window(N, i, si, ei); lp_window(N, j, sj, ej); lp_window(N, k, sk, ek);
+  double t0 = 0., t1 = 0.;
+  for (int l = si; l < ei; l++) {
+    const int x = i + H - l; const double e1 = eta[i] - eta[l];
+    for (int m = sj; m < ej; m++) {
+      const int y = j + H - m; const double e2 = eta[j] - eta[m];
+      for (int n = sk; n < ek; n++) {
+        const int z = k + H - n; const double e3 = eta[k] - eta[n];
+        const int w = n + N * (m + N * l);
+        const double *g = G + 7LL * w;
+        const double W = g[0] - (g[1] * e1 * e1 + g[2] * e2 * e2 + g[3] * e3 * e3 + g[4] * e1 * e2 + g[5] * e1 * e3 + g[6] * e2 * e3);
+        const double2 a = fh[w], b = fh[z + N * (y + N * x)];
+        t0 += W * (a.x * b.x - a.y * b.y);
+        t1 += W * (a.x * b.y + a.y * b.x);
+      }
+    }
+  }
+  q[t] = make_double2(t0, t1);
+}
+
+int lp_launch_computeQ_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B);   // computeq.cu
+
+int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B)
+{
+  if (c->p.computeq_variant != 1) {
+    int rc = lp_launch_computeQ_tiled(c, fhat, q, B);
+    if (rc != -1) return rc;   // -1: size not covered by the tiled kernel -> simple kernel
+  }
+  long long total = (long long)B * c->N3;
+  k_computeQ_simple<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(
+      reinterpret_cast<const double2 *>(fhat), reinterpret_cast<double2 *>(q), c->d_G, c->d_eta, c->p.N, total);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conserveAllMoments_Normal + solveWithCCt (conservationRoutines.cpp:131-156, 32-58).
+// One block per cell: five dot products (fixed-order tree reduction), lambda = CCt^-1-applied,
+// rank-5 correction.
+__global__ void __launch_bounds__(512) k_conserve(double2 *__restrict__ q, const double *__restrict__ C5,
+                                                  const double *__restrict__ CCt, int N3)
+{
+  __shared__ double red[5][16];
+  __shared__ double lam[5];
+  double2 *qc = q + (long long)blockIdx.x * N3;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  double s[5] = {0., 0., 0., 0., 0.};
+  for (int idx = tid; idx < N3; idx += blockDim.x) {
+    const double2 v = qc[idx];
+    s[0] += v.x * C5[idx];
+    s[1] += v.y * C5[N3 + idx];
+    s[2] += v.y * C5[2 * N3 + idx];
+    s[3] += v.y * C5[3 * N3 + idx];
+    s[4] += v.x * C5[4 * N3 + idx];
+  }
+  #pragma unroll
+  for (int m = 0; m < 5; m++) {
+    double v = s[m];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[m][wid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot[5];
+    for (int m = 0; m < 5; m++) { double v = 0.; for (int w = 0; w < nw; w++) v += red[m][w]; tot[m] = v; }
+    for (int a = 0; a < 5; a++) { double v = 0.; for (int b = 0; b < 5; b++) v += CCt[b + a * 5] * tot[b]; lam[a] = v; }
+  }
+  __syncthreads();
+  const double b0 = lam[0], b1 = lam[1], b2 = lam[2], b3 = lam[3], b4 = lam[4];
+  for (int idx = tid; idx < N3; idx += blockDim.x) {
+    double2 v = qc[idx];
+    v.x -= (C5[idx] * b0 + C5[4 * N3 + idx] * b4);
+    v.y -= (C5[N3 + idx] * b1 + C5[2 * N3 + idx] * b2 + C5[3 * N3 + idx] * b3);
+    qc[idx] = v;
+  }
+}
+int lp_launch_conserve(lpgpu_ctx *c, double *q, int B)
+{
+  k_conserve<<<B, 512, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->N3);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fourier -> DG projection: the kt loop of RK4_Inhomo / RK4_Homo (collisionRoutines_1.cpp:946-984,
+// 1128-1166).  IntModes (:408-562) factorises per dimension into T, M, S (tables.cpp), so
+//   tp_l[j1,j2,j3] = Re sum_{k1,k2,k3} IntM_l(k,j) Qc[k],   Qc = nu (q0/2 + (q1+q2+q3)/6)
+// is three chained 1-D contractions.  k_project_slab contracts k3 then k2 for one k1 slab;
+// k_project_final contracts k1 and applies the DG update in place on U (LP_ompi.cpp:727-753 scatter folded).
+__global__ void __launch_bounds__(1024) k_project_slab(const double2 *__restrict__ q0, const double2 *__restrict__ q1,
+                                                       const double2 *__restrict__ q2, const double2 *__restrict__ q3,
+                                                       double2 *__restrict__ Bbuf, const double2 *__restrict__ tT,
+                                                       const double2 *__restrict__ tM, const double2 *__restrict__ tS,
+                                                       int N, int Nv, double nu)
+{
+  extern __shared__ double2 sm2[];
+  const int P = N + 1, PV = Nv + 1;
+  double2 *Xs = sm2;                 // [N][P]
+  double2 *As = Xs + N * P;          // [3][N][PV]
+  const long long slab = blockIdx.x; // cell*N + k1
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < N * N; t += nt) {
+    const long long g = slab * N * N + t;
+    const double2 a = q0[g], b = q1[g], c = q2[g], d = q3[g];
+    Xs[(t / N) * P + (t % N)] = make_double2(nu * (0.5 * a.x + (b.x + c.x + d.x) / 6.), nu * (0.5 * a.y + (b.y + c.y + d.y) / 6.));
+  }
+  __syncthreads();
+  for (int t = tid; t < N * Nv; t += nt) {
+    const int k2 = t / Nv, j3 = t % Nv;
+    double2 aT = make_double2(0., 0.), aM = aT, aS = aT;
+    for (int k3 = 0; k3 < N; k3++) {
+      const double2 x = Xs[k2 * P + k3];
+      cfma(aT, tT[k3 * Nv + j3], x); cfma(aM, tM[k3 * Nv + j3], x); cfma(aS, tS[k3 * Nv + j3], x);
+    }
+    As[(0 * N + k2) * PV + j3] = aT; As[(1 * N + k2) * PV + j3] = aM; As[(2 * N + k2) * PV + j3] = aS;
+  }
+  __syncthreads();
+  const int Pq = Nv * Nv;
+  for (int t = tid; t < Pq; t += nt) {
+    const int j2 = t / Nv, j3 = t % Nv;
+    double2 bTT = make_double2(0., 0.), bMT = bTT, bTM = bTT, bS = bTT;
+    for (int k2 = 0; k2 < N; k2++) {
+      const double2 T2 = tT[k2 * Nv + j2], M2 = tM[k2 * Nv + j2], S2 = tS[k2 * Nv + j2];
+      const double2 at = As[(0 * N + k2) * PV + j3], am = As[(1 * N + k2) * PV + j3], as = As[(2 * N + k2) * PV + j3];
+      cfma(bTT, T2, at); cfma(bMT, M2, at); cfma(bTM, T2, am); cfma(bS, S2, at); cfma(bS, T2, as);
+    }
+    double2 *o = Bbuf + slab * 4 * Pq + t;
+    o[0] = bTT; o[Pq] = bMT; o[2 * Pq] = bTM; o[3 * Pq] = bS;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_project_final(const double2 *__restrict__ Bbuf, double *__restrict__ planes,
+                                                       const double2 *__restrict__ tT, const double2 *__restrict__ tM,
+                                                       const double2 *__restrict__ tS, int N, int Nv, int sv, double dt,
+                                                       double scalev, double scaleL, double scale3)
+{
+  const int Pq = Nv * Nv;
+  const long long cell = blockIdx.y; const int j1 = blockIdx.z;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Pq) return;
+  double tp0 = 0., tp2 = 0., tp3 = 0., tp4 = 0., tp5 = 0.;
+  for (int k1 = 0; k1 < N; k1++) {
+    const double2 T1 = tT[k1 * Nv + j1], M1 = tM[k1 * Nv + j1], S1 = tS[k1 * Nv + j1];
+    const double2 *b = Bbuf + (cell * N + k1) * 4 * Pq + p;
+    const double2 btt = b[0], bmt = b[Pq], btm = b[2 * Pq], bs = b[3 * Pq];
+    tp0 += T1.x * btt.x - T1.y * btt.y;
+    tp2 += M1.x * btt.x - M1.y * btt.y;
+    tp3 += T1.x * bmt.x - T1.y * bmt.y;
+    tp4 += T1.x * btm.x - T1.y * btm.y;
+    tp5 += S1.x * btt.x - S1.y * btt.y + T1.x * bs.x - T1.y * bs.y;
+  }
+  double *u = planes + ((cell + 1) * 6) * (long long)sv + (long long)j1 * Pq + p;
+  const double U0 = u[0], U2 = u[2LL * sv], U3 = u[3LL * sv], U4 = u[4LL * sv], U5 = u[5LL * sv];
+  const double t0 = U0 + U5 / 4. + dt * tp0 / scalev / scaleL / scale3;
+  const double t2 = U2 + dt * tp2 * 12. / scalev / scaleL / scale3;
+  const double t3 = U3 + dt * tp3 * 12. / scalev / scaleL / scale3;
+  const double t4 = U4 + dt * tp4 * 12. / scalev / scaleL / scale3;
+  const double t5 = U0 / 4. + U5 * 19. / 240. + dt * tp5 / scalev / scaleL / scale3;
+  u[0] = 19 * t0 / 4. - 15 * t5;
+  u[5LL * sv] = 60 * t5 - 15 * t0;
+  u[2LL * sv] = t2; u[3LL * sv] = t3; u[4LL * sv] = t4;      // U[6k+1] is not touched by collisions
+}
+
+int lp_launch_project(lpgpu_ctx *c, double *planes, int B)
+{
+  const int N = c->p.N, Nv = c->p.Nv;
+  const size_t smem = ((size_t)N * (N + 1) + (size_t)3 * N * (Nv + 1)) * sizeof(double2);
+  int threads = N * Nv > Nv * Nv ? N * Nv : Nv * Nv;
+  if (threads > 1024) threads = 1024;
+  LP_CUDA(cudaFuncSetAttribute(k_project_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const double2 *T = reinterpret_cast<const double2 *>(c->d_T), *M = reinterpret_cast<const double2 *>(c->d_M),
+                *S = reinterpret_cast<const double2 *>(c->d_S);
+  k_project_slab<<<B * N, threads, smem, c->stream>>>(
+      reinterpret_cast<const double2 *>(c->d_q[0]), reinterpret_cast<const double2 *>(c->d_q[1]),
+      reinterpret_cast<const double2 *>(c->d_q[2]), reinterpret_cast<const double2 *>(c->d_q[3]),
+      reinterpret_cast<double2 *>(c->d_B), T, M, S, N, Nv, c->p.nu);
+  LP_LAUNCHED(c);
+  dim3 grid((Nv * Nv + 255) / 256, B, Nv);
+  k_project_final<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(c->d_B), planes, T, M, S, N, Nv, c->sv,
+                                               c->p.dt, c->tab.scalev, c->tab.scaleL, c->tab.scale3);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}

@@ -1,0 +1,74 @@
+// Internal declarations shared by the CUDA translation units of liblpgpu.so.
+#pragma once
+#include "../../include/lpgpu.h"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+// Host-side tables that depend only on (N, Nv, Lv): built once in lpgpu_init.
+struct LpTables {
+  int N, Nv;
+  double Lv, dv, scalev, scaleL, scale3, L_eta, h_v, h_eta;
+  std::vector<double> v, eta, wt;          // N
+  std::vector<double> G;                   // 7*N^3  folded kernel symbols, [w*7 + t]
+  std::vector<double> C5;                  // 5*N^3  conservation rows, [q*5 + m] (interleaved)
+  double CCt[25];                          // (C C^T)^-1
+  std::vector<double> Ffwd, Finv;          // N*N complex: forward / inverse 1-D transform matrices
+  std::vector<double> T, M, S;             // N*Nv complex: 1-D IntModes factors [k*Nv + j]
+  std::vector<int> node_cell;              // N
+  std::vector<double> node_xi;             // N
+  std::vector<double> vc;                  // Nv  cell centres Gridv(j)
+};
+void lp_build_tables(const lpgpu_params &p, LpTables &t);
+
+struct lpgpu_ctx {
+  lpgpu_params p;
+  LpTables tab;
+  int N3, sv, ncell;       // N^3, Nv^3, local cells (x_count or 1)
+  cudaStream_t stream;
+  long long launches;
+  // ---- device tables
+  double *d_eta, *d_G, *d_C5, *d_CCt, *d_Ffwd, *d_Finv, *d_T, *d_M, *d_S, *d_node_xi, *d_vc;
+  int *d_node_cell;
+  // ---- DG state, plane-major: buf[((p*6 + c)*sv + j)], p = 0..ncell+1 (planes 0 and ncell+1 are x halos)
+  double *d_U[3];
+  double *d_aos;           // staging for AoS <-> plane-major (ncell*sv*6)
+  // ---- field
+  double *d_ms_local, *d_ms_all, *d_fld;   // 2*ncell, 2*Nx, 1 + 4*ncell (ce | cp,iE,iE1,iE2 interleaved by 4)
+  double *d_mom;           // 5 partial moments
+  // ---- collision work arrays (ncell cells each)
+  double *d_f, *d_f1, *d_Qv;               // real N^3
+  double *d_fhat, *d_tmp;                  // complex N^3
+  double *d_q[4];                          // complex N^3: qHat, Q1_fft..Q3_fft
+  double *d_lam;                           // 5 per cell
+  double *d_B;                             // projection intermediate: ncell*N*4*Nv^2 complex
+  size_t cap_cells;        // capacity (in cells) of the collision work arrays
+};
+
+// error plumbing
+void lp_set_error(const std::string &s);
+#define LP_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      lp_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                     \
+      return LPGPU_ECUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+// ---- kernel launchers (collision.cu) -- all asynchronous on c->stream
+int lp_launch_aos_to_planes(lpgpu_ctx *c, const double *aos, double *planes);
+int lp_launch_planes_to_aos(lpgpu_ctx *c, const double *planes, double *aos);
+int lp_launch_sample(lpgpu_ctx *c, const double *planes, double *f, int ncell);
+int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, int B);
+// FS + RK-stage epilogue.  mode 0: plain (writes complex out, imag 0); 1..3: stage updates of f1
+int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B);
+int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B);
+int lp_launch_conserve(lpgpu_ctx *c, double *q, int B);
+int lp_launch_project(lpgpu_ctx *c, double *planes, int B);
+// ---- advection.cu
+int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes);
+int lp_launch_field_scan(lpgpu_ctx *c);
+int lp_launch_dg_stage(lpgpu_ctx *c, int stage);
+int lp_launch_local_halo(lpgpu_ctx *c, double *planes);
+int lp_launch_moments(lpgpu_ctx *c, const double *planes);

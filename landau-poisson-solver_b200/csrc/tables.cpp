@@ -1,0 +1,182 @@
+// Host-side construction of every table the device kernels consume.  All of them depend only
+// on (N, Nv, Lv) and are built once per context, replacing the reference's start-up work:
+//   grids v/eta/wtN              LP_ompi.cpp:359-373, SetInit_1.cpp:19-27
+//   Landau kernel symbols        collisionRoutines_1.cpp:18-36, 98-161 (gHat3, gamma = -3)
+//   conservation rows + CCt^-1   conservationRoutines.cpp:159-216
+//   IntModes 1-D factors         collisionRoutines_1.cpp:408-562
+//   node -> DG cell map          SetInit_1.cpp:399-408
+//
+// The reference tabulates gHat3 for all N^6 (xi, omega) pairs (8*N^6 bytes, 8.6 GB at N = 32).
+// gHat3 is  A(omega) - sum_ab S_ab(omega) (xi-omega)_a (xi-omega)_b,  so only the 7 omega-only
+// factors are stored (7*N^3 doubles, folded with the quadrature factor h_eta^3 wt_l wt_m wt_n
+// that ComputeQ applies per pair, collisionRoutines_1.cpp:758-761); the kernels rebuild the
+// weight from them.
+#include "lpgpu_internal.h"
+#include <cmath>
+
+namespace {
+
+struct Cx { double re, im; };
+
+// symbols of the Landau collision kernel (Coulomb, gamma = -3) on the ball of radius R
+double sym_s1(double R, double k1, double k2, double k3)
+{
+  if (k1 == 0. && k2 == 0. && k3 == 0.) return std::sqrt(1. / (2 * M_PI)) * R * R;
+  const double r2 = k1 * k1 + k2 * k2 + k3 * k3;
+  return std::sqrt(2.0 / M_PI) * (1 - std::cos(R * std::sqrt(r2))) / r2;
+}
+double sym_s233(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3);
+  if (r == 0.) return std::sqrt(1. / (2. * M_PI)) * R * R / 3.;
+  const double Rr = R * r, s = std::sin(Rr), c = std::cos(Rr);
+  return std::sqrt(2. / M_PI) * ((k1 * k1 + k2 * k2) * (Rr - s) / Rr - k3 * k3 * (Rr + Rr * c - 2. * s) / Rr) / std::pow(r, 4.);
+}
+double sym_s213(double R, double k1, double k2, double k3)
+{
+  if (k1 == 0. || k3 == 0.) return 0.;
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r;
+  return -std::sqrt(2 / M_PI) * k1 * k3 * (2. * Rr + Rr * std::cos(Rr) - 3. * std::sin(Rr)) / (R * std::pow(r, 5.));
+}
+double sinc1(double x) { return x == 0.0 ? 1.0 : std::sin(x) / x; }
+
+// in-place inverse of a small dense matrix (partial pivoting); replaces dgetrf_/dgetri_
+void invert_in_place(double *a, int n)
+{
+  std::vector<double> inv(n * n, 0.);
+  for (int i = 0; i < n; i++) inv[i * n + i] = 1.;
+  for (int col = 0; col < n; col++) {
+    int piv = col;
+    for (int r = col + 1; r < n; r++)
+      if (std::fabs(a[r * n + col]) > std::fabs(a[piv * n + col])) piv = r;
+    if (piv != col)
+      for (int j = 0; j < n; j++) { std::swap(a[col * n + j], a[piv * n + j]); std::swap(inv[col * n + j], inv[piv * n + j]); }
+    const double d = a[col * n + col];
+    for (int j = 0; j < n; j++) { a[col * n + j] /= d; inv[col * n + j] /= d; }
+    for (int r = 0; r < n; r++) {
+      if (r == col) continue;
+      const double f = a[r * n + col];
+      for (int j = 0; j < n; j++) { a[r * n + j] -= f * a[col * n + j]; inv[r * n + j] -= f * inv[col * n + j]; }
+    }
+  }
+  for (int i = 0; i < n * n; i++) a[i] = inv[i];
+}
+
+} // namespace
+
+void lp_build_tables(const lpgpu_params &p, LpTables &t)
+{
+  const int N = p.N, Nv = p.Nv, N3 = N * N * N;
+  t.N = N; t.Nv = Nv; t.Lv = p.Lv;
+  t.dv = 2. * p.Lv / Nv;
+  t.scalev = t.dv * t.dv * t.dv;
+  t.scaleL = 8 * p.Lv * p.Lv * p.Lv;
+  t.scale3 = std::pow(1.0 / std::sqrt(2.0 * M_PI), 3.0);
+  t.L_eta = 0.5 * (double)(N - 1) * M_PI / p.Lv;   // N-1 here ...
+  t.h_v = 2.0 * p.Lv / (double)(N - 1);
+  t.h_eta = 2.0 * t.L_eta / (double)N;             // ... but N here: reference quirk, kept
+  t.v.resize(N); t.eta.resize(N); t.wt.resize(N);
+  for (int i = 0; i < N; i++) {
+    t.eta[i] = -t.L_eta + (double)i * t.h_eta;
+    t.v[i] = -p.Lv + (double)i * t.h_v;
+    t.wt[i] = (i == 0 || i == N - 1) ? 0.5 : 1.0;
+  }
+
+  // ---- folded kernel symbols G[w][0..6] = h_eta^3 wt^3 * {A, S11, S22, S33, 2 S12, 2 S13, 2 S23}
+  t.G.assign((size_t)7 * N3, 0.);
+  const double R = p.Lv, pref = t.h_eta * t.h_eta * t.h_eta;
+  for (int l = 0; l < N; l++)
+    for (int m = 0; m < N; m++)
+      for (int n = 0; n < N; n++) {
+        const double k1 = t.eta[l], k2 = t.eta[m], k3 = t.eta[n];
+        const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3);
+        const double s1 = sym_s1(R, k1, k2, k3);
+        const double S11 = s1 - sym_s233(R, k2, k3, k1), S22 = s1 - sym_s233(R, k1, k3, k2), S33 = s1 - sym_s233(R, k1, k2, k3);
+        const double S12 = -sym_s213(R, k1, k3, k2), S13 = -sym_s213(R, k1, k2, k3), S23 = -sym_s213(R, k2, k1, k3);
+        const double A = (r == 0.) ? 0. : std::sqrt(8. / M_PI) * (R * r - std::sin(R * r)) / (R * r);
+        const double w = pref * t.wt[l] * t.wt[m] * t.wt[n];
+        double *g = &t.G[(size_t)7 * (n + N * (m + N * l))];
+        g[0] = w * A; g[1] = w * S11; g[2] = w * S22; g[3] = w * S33;
+        g[4] = w * 2. * S12; g[5] = w * 2. * S13; g[6] = w * 2. * S23;
+      }
+
+  // ---- conservation rows, planar [m*N^3 + q]: m = 0 mass (real), 1..3 momentum (imag), 4 energy (real)
+  t.C5.assign((size_t)5 * N3, 0.);
+  const double L = p.Lv;
+  for (int q = 0; q < N3; q++) {
+    const int k = q % N, j = (q / N) % N, i = q / (N * N);
+    const double e[3] = {t.eta[i], t.eta[j], t.eta[k]};
+    double sc[3], a[3];
+    for (int d = 0; d < 3; d++) {
+      sc[d] = sinc1(L * e[d]);
+      a[d] = (e[d] != 0) ? ((e[d] * e[d] * L * L - 2) * std::sin(e[d] * L) + 2 * e[d] * L * std::cos(e[d] * L)) / (e[d] * e[d] * e[d] * L)
+                         : L * L / 3.;
+    }
+    t.C5[0 * (size_t)N3 + q] = sc[0] * sc[1] * sc[2];
+    t.C5[4 * (size_t)N3 + q] = 0.5 * (a[0] * sc[1] * sc[2] + a[1] * sc[0] * sc[2] + a[2] * sc[0] * sc[1]);
+    const int o1[3] = {1, 0, 0}, o2[3] = {2, 2, 1};
+    for (int d = 0; d < 3; d++)
+      t.C5[(size_t)(1 + d) * N3 + q] = (e[d] != 0) ? -sc[o1[d]] * sc[o2[d]] * (sinc1(e[d] * L) - std::cos(e[d] * L)) / e[d] : 0.;
+  }
+  for (int i = 0; i < 5; i++)
+    for (int j = 0; j < 5; j++) {
+      const bool ri = (i == 0 || i == 4), rj = (j == 0 || j == 4);
+      double s = 0.;
+      if (ri == rj)
+        for (int q = 0; q < N3; q++) s += t.C5[(size_t)i * N3 + q] * t.C5[(size_t)j * N3 + q];
+      t.CCt[i * 5 + j] = s;
+    }
+  invert_in_place(t.CCt, 5);
+
+  // ---- 1-D transform matrices.  fft3D == (2 pi)^(-1/2) h_v wt_j exp(-i v_j eta_k) per dimension,
+  // FS == exp(+i v_j eta_k) per dimension (pre-phase * DFT twiddle * post-phase of
+  // collisionRoutines_1.cpp:291-317 and :370-396, with the twiddle index reduced mod N).
+  t.Ffwd.resize((size_t)2 * N * N); t.Finv.resize((size_t)2 * N * N);
+  const long double s1d = 1.0L / sqrtl(2.0L * M_PIl) * (long double)t.h_v;
+  for (int k = 0; k < N; k++)
+    for (int j = 0; j < N; j++) {
+      const long double tw = 2.0L * M_PIl * (long double)((j * k) % N) / (long double)N;
+      const long double af = (long double)j * (long double)t.L_eta * (long double)t.h_v - tw + (long double)p.Lv * (long double)t.eta[k];
+      t.Ffwd[2 * ((size_t)k * N + j)] = (double)(s1d * (long double)t.wt[j] * cosl(af));
+      t.Ffwd[2 * ((size_t)k * N + j) + 1] = (double)(s1d * (long double)t.wt[j] * sinl(af));
+      // inverse: row = velocity node j, column = Fourier node k
+      const long double ai = -(long double)k * (long double)p.Lv * (long double)t.h_eta + tw - (long double)t.L_eta * (long double)t.v[j];
+      t.Finv[2 * ((size_t)j * N + k)] = (double)cosl(ai);
+      t.Finv[2 * ((size_t)j * N + k) + 1] = (double)sinl(ai);
+    }
+
+  // ---- IntModes 1-D factors: T = int_cell e^{i eta v}, M = int e^{i eta v}(v-c)/dv, S = int e^{i eta v}((v-c)/dv)^2
+  t.T.resize((size_t)2 * N * Nv); t.M.resize((size_t)2 * N * Nv); t.S.resize((size_t)2 * N * Nv);
+  t.vc.resize(Nv);
+  const double dv = t.dv;
+  for (int j = 0; j < Nv; j++) t.vc[j] = -p.Lv + (j + 0.5) * dv;
+  for (int k = 0; k < N; k++)
+    for (int j = 0; j < Nv; j++) {
+      const double e = t.eta[k], c0 = t.vc[j], vl = -p.Lv + ((j - 0.5) + 0.5) * dv, vr = -p.Lv + ((j + 0.5) + 0.5) * dv;
+      Cx T, Mm, S;
+      if (e != 0.) {
+        const double sr = std::sin(e * vr), sl = std::sin(e * vl), cr = std::cos(e * vr), cl = std::cos(e * vl);
+        T.re = (sr - sl) / e;
+        T.im = (cl - cr) / e;
+        const double a_re = (vr * sr - vl * sl) / e + (cr - cl) / e / e;
+        const double a_im = (sr - sl) / e / e + (vl * cl - vr * cr) / e;
+        Mm.re = (a_re - c0 * T.re) / dv;
+        Mm.im = (a_im - c0 * T.im) / dv;
+        S.re = ((vr * vr * sr - vl * vl * sl - 2 * a_im) / e - 2 * c0 * a_re + c0 * c0 * T.re) / dv / dv;
+        S.im = ((vl * vl * cl - vr * vr * cr + 2 * a_re) / e - 2 * c0 * a_im + c0 * c0 * T.im) / dv / dv;
+      } else {
+        T.re = dv; T.im = 0.; Mm.re = 0.; Mm.im = 0.; S.re = dv / 12.; S.im = 0.;
+      }
+      const size_t o = 2 * ((size_t)k * Nv + j);
+      t.T[o] = T.re; t.T[o + 1] = T.im; t.M[o] = Mm.re; t.M[o + 1] = Mm.im; t.S[o] = S.re; t.S[o + 1] = S.im;
+    }
+
+  // ---- spectral node -> DG cell: identical expression to the reference, evaluated on the host
+  t.node_cell.resize(N); t.node_xi.resize(N);
+  for (int l = 0; l < N; l++) {
+    int j = (int)((l * t.h_v) / dv);
+    if (j == Nv) j = Nv - 1;
+    t.node_cell[l] = j;
+    t.node_xi[l] = (t.v[l] - t.vc[j]) / dv;
+  }
+}

@@ -1,0 +1,229 @@
+"""ctypes binding of include/lpgpu.h.  No torch types cross this boundary: host arrays are numpy
+(float64, C-contiguous), device buffers are raw addresses.  There is no CPU fallback: if
+liblpgpu.so is missing or no CUDA device is usable, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path():
+    return os.path.join(_HERE, "liblpgpu.so")
+
+
+class LPGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """struct lpgpu_params (include/lpgpu.h)."""
+    _fields_ = [("Nx", C.c_int), ("Nv", C.c_int), ("N", C.c_int),
+                ("Lv", C.c_double), ("Lx", C.c_double), ("nu", C.c_double), ("dt", C.c_double),
+                ("gamma", C.c_int), ("homogeneous", C.c_int),
+                ("x_begin", C.c_int), ("x_count", C.c_int), ("device", C.c_int),
+                ("computeq_variant", C.c_int)]
+
+
+class Exchange(C.Structure):
+    """struct lpgpu_exchange (include/lpgpu.h)."""
+    _fields_ = [("ms_local", C.c_void_p), ("ms_all", C.c_void_p),
+                ("send_left", C.c_void_p), ("send_right", C.c_void_p),
+                ("recv_left", C.c_void_p), ("recv_right", C.c_void_p),
+                ("plane_doubles", C.c_longlong)]
+
+
+# every symbol include/lpgpu.h declares (tests check the library exports exactly these)
+EXPORTS = [
+    "lpgpu_last_error", "lpgpu_device_count", "lpgpu_init", "lpgpu_finalize", "lpgpu_set_stream",
+    "lpgpu_synchronize", "lpgpu_launch_count", "lpgpu_upload_U", "lpgpu_download_U",
+    "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_step", "lpgpu_advect_exchange_info",
+    "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
+    "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
+    "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen liblpgpu.so (needs libcudart, not a GPU) and declare signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise LPGpuError("liblpgpu.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "or `make -C landau-poisson-solver_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(path)
+    L.lpgpu_last_error.restype = C.c_char_p
+    L.lpgpu_launch_count.restype = C.c_longlong
+    L.lpgpu_launch_count.argtypes = [C.c_void_p]
+    L.lpgpu_init.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+    for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_sample_device"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.lpgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+    for name in ("lpgpu_step", "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_eval_device"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+    L.lpgpu_advect_exchange_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(Exchange)]
+    for name in ("lpgpu_fft3D", "lpgpu_FS", "lpgpu_ComputeQ"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.lpgpu_conserveMoments.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.lpgpu_get_stage_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.lpgpu_moments_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lpgpu_eleE_from_ms.argtypes = [C.POINTER(Params), C.c_void_p, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class LPGpu:
+    """One context = one GPU's shard of spatial cells.  Method names follow the reference's
+    function names (RK3 -> advect_rk3, ComputeQ, conserveMoments, FS, fft3D, setInit_spectral)."""
+
+    def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, gamma=-3, x_begin=0, x_count=None,
+                 device=0, computeq_variant=0):
+        self.L = load_library()
+        if x_count is None:
+            x_count = 1 if homogeneous else Nx
+        self.params = Params(Nx, Nv, N, Lv, Lx, nu, dt, gamma, int(bool(homogeneous)), x_begin, x_count, device,
+                             computeq_variant)
+        self.Nx, self.Nv, self.N = Nx, Nv, N
+        self.homogeneous = bool(homogeneous)
+        self.ncell = 1 if homogeneous else x_count
+        self.N3, self.sv = N ** 3, Nv ** 3
+        self.h = C.c_void_p()
+        self._check(self.L.lpgpu_init(C.byref(self.params), C.byref(self.h)))
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise LPGpuError("lpgpu error %d: %s" % (rc, (self.L.lpgpu_last_error() or b"").decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lpgpu_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.L.lpgpu_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def synchronize(self):
+        self._check(self.L.lpgpu_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.lpgpu_launch_count(self.h))
+
+    # -- state
+    def upload_U(self, U):
+        U = _f64(U)
+        assert U.size == self.ncell * self.sv * 6, "U must hold this shard: x_count*Nv^3*6 doubles"
+        self._check(self.L.lpgpu_upload_U(self.h, _ptr(U)))
+
+    def download_U(self, out=None):
+        U = np.empty(self.ncell * self.sv * 6) if out is None else out
+        self._check(self.L.lpgpu_download_U(self.h, _ptr(U)))
+        return U
+
+    # -- phases
+    def advect_rk3(self):
+        self._check(self.L.lpgpu_advect_rk3(self.h))
+
+    def collide_step(self):
+        self._check(self.L.lpgpu_collide_step(self.h))
+
+    def step(self, nsteps=1):
+        self._check(self.L.lpgpu_step(self.h, int(nsteps)))
+
+    def exchange_info(self, stage):
+        ex = Exchange()
+        self._check(self.L.lpgpu_advect_exchange_info(self.h, int(stage), C.byref(ex)))
+        return ex
+
+    def advect_reduce(self, stage):
+        self._check(self.L.lpgpu_advect_reduce(self.h, int(stage)))
+
+    def advect_apply(self, stage):
+        self._check(self.L.lpgpu_advect_apply(self.h, int(stage)))
+
+    # -- fine-grained (host buffers)
+    def setInit_spectral(self):
+        f = np.empty((self.ncell, self.N3))
+        self._check(self.L.lpgpu_setInit_spectral(self.h, _ptr(f)))
+        return f
+
+    def _batched(self, fn, x, in_w, out_w):
+        x = _f64(x)
+        B = x.size // (self.N3 * in_w)
+        assert B * self.N3 * in_w == x.size and B >= 1
+        out = np.empty((B, self.N3, out_w))
+        self._check(fn(self.h, _ptr(x), _ptr(out), B))
+        return out
+
+    def fft3D(self, x):
+        return self._batched(self.L.lpgpu_fft3D, x, 2, 2)
+
+    def FS(self, x):
+        return self._batched(self.L.lpgpu_FS, x, 2, 2)
+
+    def ComputeQ(self, f):
+        return self._batched(self.L.lpgpu_ComputeQ, f, 1, 2)
+
+    def conserveMoments(self, q):
+        q = _f64(q).copy()
+        B = q.size // (2 * self.N3)
+        self._check(self.L.lpgpu_conserveMoments(self.h, _ptr(q), B))
+        return q.reshape(B, self.N3, 2)
+
+    def sample_device(self):
+        self._check(self.L.lpgpu_sample_device(self.h))
+
+    def eval_device(self, B=None):
+        self._check(self.L.lpgpu_eval_device(self.h, int(self.ncell if B is None else B)))
+
+    def stage_spectrum(self, which):
+        out = np.empty((self.ncell, self.N3, 2))
+        self._check(self.L.lpgpu_get_stage_spectrum(self.h, int(which), _ptr(out)))
+        return out
+
+    def field(self):
+        out = np.empty(1 + 4 * self.Nx)
+        self._check(self.L.lpgpu_field(self.h, _ptr(out)))
+        return out
+
+    # -- diagnostics
+    def moments_partial(self):
+        out = np.empty(5)
+        ms = np.zeros(2 * self.ncell)
+        self._check(self.L.lpgpu_moments_partial(self.h, _ptr(out), _ptr(ms)))
+        return out, ms
+
+    def eleE_from_ms(self, ms_all):
+        ms_all = _f64(ms_all)
+        assert ms_all.size == 2 * self.Nx
+        v = C.c_double()
+        self._check(self.L.lpgpu_eleE_from_ms(C.byref(self.params), _ptr(ms_all), C.byref(v)))
+        return v.value
+
+    def moments(self):
+        """mass, P1, P2, P3, KiE, EleE for a single-shard context."""
+        m5, ms = self.moments_partial()
+        ele = 0.0 if self.homogeneous else self.eleE_from_ms(ms)
+        return np.concatenate([m5, [ele]])

@@ -1,0 +1,297 @@
+"""GPU parity tests: every entry point of the C ABI (include/lpgpu.h) against the CPU oracle on
+the same inputs.  All arithmetic is FP64; tolerances are stated per test (they bound summation
+reordering, FMA contraction and libm-vs-table differences, i.e. a few hundred ulps of the
+largest element).  The oracle itself is pinned to the unmodified reference in test_oracle.py."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle.oracle import PortOracle
+
+pytestmark = pytest.mark.gpu
+
+TEST0 = dict(Nx=16, Nv=16, N=8, Lv=5.25, Lx=4 * np.pi, nu=0.05, dt=0.01)   # tests/LPsolver-input-test0.txt
+SMALL = dict(Nx=6, Nv=8, N=8, Lv=5.25, Lx=4 * np.pi, nu=0.05, dt=0.01)
+TOL_SPEC = 1e-12   # spectral arrays, relative to max|.|  
+TOL_U = 1e-12      # DG coefficients, relative to max|U|
+TOL_DU = 1e-9      # one-step UPDATE (U_new - U_old), relative to its own max
+
+
+def _perturbed(ora, seed=0):
+    """Landau-damping data with every coefficient (incl. U1) made non-trivial."""
+    U = ora.SetInit_LD(0.2, 0.5)
+    rng = np.random.default_rng(seed)
+    return U * (1 + 0.05 * rng.standard_normal(U.shape)) + 1e-4 * rng.standard_normal(U.shape)
+
+
+@pytest.fixture(scope="module")
+def small(pkg):
+    ora = PortOracle(**SMALL)
+    g = pkg.LPGpu(**SMALL)
+    yield ora, g
+    g.close()
+
+
+def test_upload_download_roundtrip(small):
+    ora, g = small
+    U = _perturbed(ora)
+    g.upload_U(U)
+    assert np.array_equal(g.download_U(), U)        # layout change only: bit exact
+
+
+def test_setInit_spectral(small):
+    ora, g = small
+    U = _perturbed(ora)
+    g.upload_U(U)
+    assert relerr(g.setInit_spectral(), ora.setInit_spectral(U)) < 1e-14
+
+
+@pytest.mark.parametrize("N", [8, 16, 24, 32])
+def test_fft3D_and_FS(pkg, N):
+    cfg = dict(TEST0, N=N, Nv=16)
+    ora = PortOracle(homogeneous=True, **cfg)
+    g = pkg.LPGpu(homogeneous=True, **cfg)
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((N ** 3, 2))
+    assert relerr(g.fft3D(x)[0], ora.fft3D(x)) < TOL_SPEC
+    fs = g.FS(x)[0]
+    want = ora.FS(x)
+    assert relerr(fs[:, 0], want[:, 0]) < TOL_SPEC    # callers keep the real part only
+    g.close()
+
+
+@pytest.mark.parametrize("N,variant", [(8, 0), (8, 1), (16, 0), (16, 1)])
+def test_ComputeQ_and_conserve(pkg, N, variant):
+    cfg = dict(TEST0, N=N, Nv=16)
+    ora = PortOracle(homogeneous=True, **cfg)
+    g = pkg.LPGpu(homogeneous=True, computeq_variant=variant, **cfg)
+    f = ora.setInit_spectral(ora.SetInit_4H_Homo())[0]
+    f = f * (1 + 0.1 * np.sin(np.arange(f.size)))          # break the symmetry: complex, non-trivial qHat
+    q_want = ora.ComputeQ(f)
+    q = g.ComputeQ(f)[0]
+    assert relerr(q, q_want) < TOL_SPEC
+    qc = g.conserveMoments(q_want)[0]
+    qc_want = ora.conserveMoments(q_want)
+    assert relerr(qc, qc_want) < TOL_SPEC
+    # property: the five conserved moments of the corrected spectrum vanish
+    C5, _ = ora.conservation()
+    lam = [qc[:, 0] @ C5[0], qc[:, 1] @ C5[1], qc[:, 1] @ C5[2], qc[:, 1] @ C5[3], qc[:, 0] @ C5[4]]
+    assert max(abs(v) for v in lam) < 1e-12 * np.abs(q_want).max() * np.abs(C5).max() * f.size
+    g.close()
+
+
+def test_ComputeQ_batch_of_cells(small):
+    ora, g = small
+    U = _perturbed(ora, 3)
+    f = ora.setInit_spectral(U)
+    q = g.ComputeQ(f)
+    for cell in range(ora.ncell):
+        assert relerr(q[cell], ora.ComputeQ(f[cell])) < TOL_SPEC
+
+
+def test_collide_step_homogeneous_test4(pkg):
+    """tests/LPsolver-input-test4.txt: Homogeneous FourHump, Nv16 N8, five steps."""
+    ora = PortOracle(homogeneous=True, **TEST0)
+    g = pkg.LPGpu(homogeneous=True, **TEST0)
+    U0 = ora.SetInit_4H_Homo()
+    g.upload_U(U0)
+    g.collide_step()
+    U1 = g.download_U()
+    want = ora.collide_step(U0)
+    assert relerr(U1, want) < TOL_U
+    assert relerr(U1 - U0, want - U0) < TOL_DU
+    f = ora.setInit_spectral(U0)[0]
+    q0 = ora.conserveMoments(ora.ComputeQ(f))
+    _, q123 = ora.RK4(f, 0, q0, U0)
+    assert relerr(g.stage_spectrum(0)[0], q0) < TOL_SPEC
+    for s in range(3):
+        assert relerr(g.stage_spectrum(s + 1)[0], q123[s]) < 1e-11
+    # four more steps -> row 6 of Moments_Test4.dc: mass 1, KiE 0.6006 (%11.8g), |momentum| <= 1e-10
+    g.step(4)
+    m = g.moments()
+    assert abs(m[0] - 1.0) <= 2e-6 and np.all(np.abs(m[1:4]) <= 1e-10) and abs(m[4] - 0.6006) <= 5e-5
+    Uo = U0
+    for _ in range(5):
+        Uo = ora.step(Uo)
+    mo = ora.moments(Uo)
+    assert abs(m[0] - mo[0]) <= 1e-10 * abs(mo[0]) and abs(m[4] - mo[4]) <= 1e-10 * abs(mo[4])
+    g.close()
+
+
+def test_field_integrals(small):
+    ora, g = small
+    U = _perturbed(ora, 1)
+    g.upload_U(U)
+    got, want = g.field(), ora.field(U)
+    Nx = SMALL["Nx"]
+    # ce is a catastrophic cancellation: absolute tolerance scaled by Lx/2
+    assert abs(got[0] - want[0]) < 1e-11 * SMALL["Lx"]
+    for a in range(4):
+        sl = slice(1 + a * Nx, 1 + (a + 1) * Nx)
+        assert np.max(np.abs(got[sl] - want[sl])) < 1e-11 * max(np.max(np.abs(want[sl])), 1.0)
+
+
+def test_RK3(small):
+    ora, g = small
+    U = _perturbed(ora, 2)
+    g.upload_U(U)
+    g.advect_rk3()
+    got, want = g.download_U(), ora.RK3(U)
+    assert relerr(got, want) < TOL_U
+    assert relerr(got - U, want - U) < TOL_DU
+
+
+def test_full_step_small(small):
+    ora, g = small
+    U = ora.SetInit_LD(0.2, 0.5)
+    g.upload_U(U)
+    g.step(2)
+    want = ora.step(ora.step(U))
+    got = g.download_U()
+    assert relerr(got, want) < TOL_U
+    assert relerr(got - U, want - U) < TOL_DU
+    mg, mo = g.moments(), ora.moments(want)
+    for i in (0, 4, 5):                                   # mass, KiE, EleE: 1e-10 relative
+        assert abs(mg[i] - mo[i]) <= 1e-10 * abs(mo[i])
+    assert np.all(np.abs(mg[1:4] - mo[1:4]) <= 1e-10)     # momentum: absolute, as moment_differ.sh does
+
+
+def test_two_stream_step(pkg):
+    cfg = dict(Nx=8, Nv=8, N=8, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
+    ora = PortOracle(**cfg)
+    g = pkg.LPGpu(**cfg)
+    U = ora.SetInit_LD(0.5, 2 * np.pi / 4., twostream=True)
+    g.upload_U(U)
+    g.step(1)
+    want = ora.step(U)
+    got = g.download_U()
+    assert relerr(got, want) < TOL_U and relerr(got - U, want - U) < TOL_DU
+    g.close()
+
+
+def test_golden_test0_moments(pkg):
+    """tests/LPsolver-input-test0.txt, 5 steps; row 6 of tests/Moments_Test0.dc with the thresholds
+    of tests/moment_differ.sh:9-13 (mass 2e-6, momentum 1e-10 absolute, total energy +3e-5/-1e-10...)."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_moments.json")))["Moments_Test0.dc"][5]
+    ora = PortOracle(**TEST0)
+    g = pkg.LPGpu(**TEST0)
+    g.upload_U(ora.SetInit_LD(0.2, 0.5))
+    g.step(5)
+    m = g.moments()
+    g.close()
+    assert abs(m[0] - gold[0]) <= 2e-6
+    assert np.all(np.abs(m[1:4] - np.array(gold[1:4])) <= 1e-10)
+    tot = m[4] + m[5]
+    assert tot - gold[8] <= 3e-5 and gold[8] - tot <= 5e-8      # golden has 8 significant digits
+    assert abs(m[4] - gold[4]) <= 5e-7 and abs(m[5] - gold[5]) <= 5e-8
+
+
+@pytest.mark.parametrize("N", [16, 24, 32])
+def test_ComputeQ_checksums_full_size(pkg, N):
+    """Known-answer checksums of the reference at the headline sizes (measured
+    with the unmodified reference): FourHump homogeneous IC, one ComputeQ + conserveMoments."""
+    known = {16: (0.0098730589658264766, -1.4055046834745595e-4),
+             24: (0.091858551020261747, -6.0915531569819021e-5),
+             32: (7.8363114577120031e-5, -6.7737121404026841e-9)}[N]
+    cfg = dict(TEST0, N=N, Nv=N)
+    ora = PortOracle(homogeneous=True, **cfg)
+    f = ora.setInit_spectral(ora.SetInit_4H_Homo())[0]
+    g = pkg.LPGpu(homogeneous=True, **cfg)
+    q = g.conserveMoments(g.ComputeQ(f)[0])[0]
+    g.close()
+    g1 = pkg.LPGpu(homogeneous=True, computeq_variant=1, **cfg)
+    q1 = g1.conserveMoments(g1.ComputeQ(f)[0])[0]
+    g1.close()
+    assert relerr(q, q1) < TOL_SPEC                           # tiled kernel vs simple kernel on device
+    s = float(np.sum(q[:, 0] ** 2))
+    mid = q[(N // 2) * (N * N + N + 1), 0]
+    assert abs(s - known[0]) <= 1e-9 * known[0]
+    assert abs(mid - known[1]) <= 1e-7 * abs(known[1])
+    assert float(np.sum(q[:, 1] ** 2)) < 1e-20               # symmetric IC -> real spectrum
+
+
+def test_sharded_advection_matches_single(pkg):
+    """Two contexts on one GPU, each owning half of x, exchanging halos and (m_i,s_i) by hand:
+    the sharded stage API must reproduce the single-context RK3 exactly."""
+    import ctypes as C
+    cfg = dict(SMALL)
+    ora = PortOracle(**cfg)
+    U = _perturbed(ora, 5)
+    sv6 = 6 * cfg["Nv"] ** 3
+    half = cfg["Nx"] // 2
+    single = pkg.LPGpu(**cfg)
+    single.upload_U(U)
+    single.advect_rk3()
+    want = single.download_U()
+    single.close()
+    shards = [pkg.LPGpu(x_begin=r * half, x_count=half, **cfg) for r in range(2)]
+    for r, s in enumerate(shards):
+        s.upload_U(U[r * half * sv6:(r + 1) * half * sv6])
+    cudart = C.CDLL("libcudart.so")
+    cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    D2D = 3
+
+    def copy(dst, src, n):
+        assert cudart.cudaMemcpy(dst, src, n * 8, D2D) == 0
+
+    for stage in range(3):
+        ex = [s.exchange_info(stage) for s in shards]
+        for s in shards:
+            s.advect_reduce(stage)
+            s.synchronize()
+        for r in range(2):
+            for o in range(2):      # all-gather of (m_i, s_i)
+                copy(ex[r].ms_all + o * 2 * half * 8, ex[o].ms_local, 2 * half)
+            left, right = (r - 1) % 2, (r + 1) % 2
+            copy(ex[r].recv_left, ex[left].send_right, ex[r].plane_doubles)
+            copy(ex[r].recv_right, ex[right].send_left, ex[r].plane_doubles)
+        for s in shards:
+            s.advect_apply(stage)
+            s.synchronize()
+    got = np.concatenate([s.download_U() for s in shards])
+    for s in shards:
+        s.close()
+    assert np.array_equal(got, want)
+
+
+def test_against_committed_reference_vectors(pkg):
+    """CUDA path vs tests/golden/ref_vectors.npz (outputs of the unmodified reference, generated by
+    tests/golden/make_golden.py); nothing under /root/reference or oracle/ is touched here."""
+    import json, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    g = pkg.LPGpu(**cfg)
+    U0 = z["U0"]
+    g.upload_U(U0)
+    assert relerr(g.setInit_spectral(), z["f"]) < 1e-14
+    assert relerr(g.fft3D(z["x"])[0], z["fft3D"]) < TOL_SPEC
+    assert relerr(g.FS(z["x"])[0][:, 0], z["FS"][:, 0]) < TOL_SPEC
+    f1 = z["f"][1] * (1 + 0.1 * np.sin(np.arange(z["f"][1].size)))
+    assert relerr(g.ComputeQ(f1)[0], z["qHat"]) < TOL_SPEC
+    assert relerr(g.conserveMoments(z["qHat"])[0], z["qHat_conserved"]) < TOL_SPEC
+    Nx = cfg["Nx"]
+    fld = g.field()
+    assert abs(fld[0] - z["field"][0]) < 1e-11 * cfg["Lx"]
+    assert np.max(np.abs(fld[1:] - z["field"][1:])) < 1e-11 * max(1.0, np.max(np.abs(z["field"][1:])))
+    assert relerr(g.moments(), z["moments"]) < 1e-12
+    g.collide_step()
+    got = g.download_U()
+    assert relerr(got, z["U_collide"]) < TOL_U and relerr(got - U0, z["U_collide"] - U0) < TOL_DU
+    assert relerr(g.stage_spectrum(3)[Nx - 1], z["stage_spectra"][2]) < 1e-11   # Q3_fft of the last cell
+    g.upload_U(U0)
+    g.advect_rk3()
+    got = g.download_U()
+    assert relerr(got, z["U_RK3"]) < TOL_U and relerr(got - U0, z["U_RK3"] - U0) < TOL_DU
+    g.upload_U(U0)
+    g.step(1)
+    got = g.download_U()
+    assert relerr(got, z["U_step"]) < TOL_U and relerr(got - U0, z["U_step"] - U0) < TOL_DU
+    g.close()
+    gh = pkg.LPGpu(homogeneous=True, **cfg)
+    gh.upload_U(z["Uh0"])
+    gh.collide_step()
+    got = gh.download_U()
+    assert relerr(got, z["Uh_collide"]) < TOL_U and relerr(got - z["Uh0"], z["Uh_collide"] - z["Uh0"]) < TOL_DU
+    assert relerr(gh.moments()[:5], z["moments_h"][:5]) < 1e-10 or np.allclose(gh.moments()[:5], z["moments_h"][:5], rtol=1e-10, atol=1e-12)
+    gh.close()

@@ -1,0 +1,113 @@
+"""CPU tests (no GPU): the oracle is pinned to the reference.
+
+1. the C restatement (oracle/lp_oracle.c) against the committed golden vectors, which are outputs
+   of the unmodified reference (tests/golden/make_golden.py), and against the reference's own
+   golden moment files tests/Moments_Test0.dc / Moments_Test4.dc with moment_differ.sh's gates;
+2. where oracle/_ref/libref.so exists (the reference compiled behind shims), element-wise against
+   the live reference on further inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle.oracle import PortOracle, RefOracle, have_ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TEST0 = dict(Nx=16, Nv=16, N=8, Lv=5.25, Lx=4 * np.pi, nu=0.05, dt=0.01)
+
+
+@pytest.fixture(scope="module")
+def vec():
+    z = np.load(os.path.join(GOLD, "ref_vectors.npz"))
+    return z, json.loads(str(z["cfg"]))
+
+
+def test_port_matches_reference_vectors(vec):
+    z, cfg = vec
+    P = PortOracle(**cfg)
+    U0 = z["U0"]
+    assert relerr(P.setInit_spectral(U0), z["f"]) < 1e-15
+    assert relerr(P.fft3D(z["x"]), z["fft3D"]) < 1e-14
+    assert relerr(P.FS(z["x"]), z["FS"]) < 1e-14
+    f1 = z["f"][1] * (1 + 0.1 * np.sin(np.arange(z["f"][1].size)))
+    assert relerr(P.ComputeQ(f1), z["qHat"]) < 1e-14
+    assert relerr(P.conserveMoments(z["qHat"]), z["qHat_conserved"]) < 1e-13
+    assert np.max(np.abs(P.field(U0) - z["field"])) < 1e-12 * cfg["Lx"]
+    assert relerr(P.moments(U0), z["moments"]) < 1e-13
+    for name, got in (("U_collide", P.collide_step(U0)), ("U_RK3", P.RK3(U0)), ("U_step", P.step(U0))):
+        assert relerr(got, z[name]) < 1e-13, name
+        assert relerr(got - U0, z[name] - U0) < 1e-10, name
+    Ph = PortOracle(homogeneous=True, **cfg)
+    assert relerr(Ph.SetInit_4H_Homo(), z["Uh0"]) < 1e-15
+    got = Ph.collide_step(z["Uh0"])
+    assert relerr(got - z["Uh0"], z["Uh_collide"] - z["Uh0"]) < 1e-10
+
+
+def test_separable_projection_equals_literal_IntModes(vec):
+    z, cfg = vec
+    P = PortOracle(**cfg)
+    a = P.collide_step(z["U0"])
+    P.set_direct_intmodes(1)
+    b = P.collide_step(z["U0"])
+    assert relerr(a - z["U0"], b - z["U0"]) < 1e-11
+
+
+def _gate(row, gold):
+    """tests/moment_differ.sh:9-13, row 6: mass 2e-6, momenta 1e-10 (absolute), total energy."""
+    assert abs(row[0] - gold[0]) <= 2e-6
+    for d in (1, 2, 3):
+        assert abs(row[d] - gold[d]) <= 1e-10
+    tot_col = len(gold) - 1
+    assert row[tot_col] - gold[tot_col] <= 3e-5 and gold[tot_col] - row[tot_col] <= 5e-8
+
+
+def test_port_reproduces_Moments_Test0():
+    gold = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test0.dc"]
+    P = PortOracle(**TEST0)
+    U = P.SetInit_LD(0.2, 0.5)
+    for step in range(6):
+        m = P.moments(U)
+        row = [m[0], m[1], m[2], m[3], m[4], m[5], np.sqrt(m[5]), np.log(np.sqrt(m[5])), m[4] + m[5]]
+        for col in (0, 4, 5, 6, 7, 8):                      # every printed digit of every row
+            assert abs(row[col] - gold[step][col]) <= 6e-8 * max(1.0, abs(gold[step][col])), (step, col)
+        if step == 5:
+            _gate(row, gold[5])
+        U = P.step(U)
+
+
+def test_port_reproduces_Moments_Test4():
+    gold = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test4.dc"]
+    P = PortOracle(homogeneous=True, **TEST0)
+    U = P.SetInit_4H_Homo()
+    for _ in range(5):
+        U = P.step(U)
+    m = P.moments(U)
+    _gate([m[0], m[1], m[2], m[3], 0., 0., 0., m[4]], gold[5])
+    assert abs(m[4] - gold[5][7]) <= 5e-8
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libref.so not built (needs /root/reference)")
+def test_port_matches_live_reference():
+    cfg = dict(Nx=4, Nv=8, N=8, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
+    P, R = PortOracle(**cfg), RefOracle(**cfg)
+    for a, b in zip(P.grids(), R.grids()):
+        assert np.array_equal(a, b)
+    Cp, CCp = P.conservation()
+    Cr, CCr = R.conservation()
+    assert relerr(Cp, Cr) < 1e-15 and relerr(CCp, CCr) < 1e-13
+    for xi in (0, 77, 292, 511):
+        assert relerr(P.weight_row(xi), R.weight_row(xi)) < 1e-15
+    for idx in [(0, 1, 2, 3, 4, 5), (4, 4, 4, 0, 0, 0), (7, 3, 4, 7, 7, 1)]:
+        assert relerr(P.IntModes(*idx), R.IntModes(*idx)) < 1e-15
+    assert relerr(P.SetInit_LD(0.5, np.pi / 2, True), R.SetInit_LD(0.5, np.pi / 2, True)) < 1e-15
+    assert relerr(P.SetInit_4H(), R.SetInit_4H()) < 1e-15
+    U = R.SetInit_LD(0.5, np.pi / 2, True)
+    rng = np.random.default_rng(7)
+    U = U * (1 + 0.1 * rng.standard_normal(U.shape)) + 1e-3 * rng.standard_normal(U.shape)
+    assert np.max(np.abs(P.field(U) - R.field(U))) < 1e-12 * max(1.0, np.max(np.abs(R.field(U))))
+    assert relerr(P.moments(U), R.moments(U)) < 1e-13
+    a, b = P.step(U), R.step(U)
+    assert relerr(a, b) < 1e-13 and relerr(a - U, b - U) < 1e-10
