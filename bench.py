@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Landau-Poisson hot path on B200 (one JSON line on rank 0).
+
+Metric (BASELINE.json): collision-cell evaluations/s, one evaluation = ComputeQ + conserveMoments
+on one spatial cell; the solver does 4 per cell per timestep (LP_ompi.cpp:700-702,
+collisionRoutines_1.cpp:919,931,943).  A "step" is one full timestep (SSP-RK3 advection + RK4
+collision of every local cell); value = 4 * Nx * steps / time, timesteps/s is reported beside it.
+
+Workload: BASELINE config "two-stream, Nx=256, Nv=32^3 on 8 GPUs" cut to its per-GPU shard: 32
+x-cells per GPU, Nv = N = 32 (weak scaling: Nx = 32 * n_gpus).  BASELINE's single-cell homogeneous
+config cannot be sharded for the 1->8 sweep; it is measured too (N=1 only) and reported under
+"homogeneous_1cell".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun ... bench.py --gpus N ...        (one rank per GPU, NCCL)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CELLS_PER_GPU = 32
+NV = 32
+NSPEC = 32
+PHYS = dict(Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)     # [TwoStream] section of the reference input deck
+A_AMP, K_WAVE = 0.5, 2 * np.pi / 4.
+METRIC, UNIT = "collision_cell_evals_per_s", "evals/s"
+
+
+def pairs_per_eval(N):
+    return (3 * N * N / 4.) ** 3
+
+
+def flop_per_eval(N):
+    return 10. * pairs_per_eval(N)                  # algorithmic: 6 complex-mul + 4 scale-accumulate per pair
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0., set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_eval_rate(reps, warm):
+    """ComputeQ + conserveMoments of the reference's own CPU code (oracle/_ref when it was built
+    from /root/reference, else the C restatement) on this box's host cores: evals/s on one cell."""
+    from oracle.oracle import PortOracle, RefOracle, have_ref
+    cfg = dict(Nx=1, Nv=NV, N=NSPEC, homogeneous=True, **PHYS)
+    kind, t_init = "port", time.time()
+    ora = None
+    if have_ref():
+        try:
+            avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+            if avail_gb > 8 * NSPEC ** 6 / 2 ** 30 + 4:
+                ora = RefOracle(**cfg)              # builds the reference's 8*N^6-byte weight table
+                kind = "reference"
+        except Exception:
+            ora = None
+    if ora is None:
+        ora = PortOracle(**cfg)
+    t_init = time.time() - t_init
+    from lpsolver_b200 import solver
+    f = (PortOracle(**cfg).setInit_spectral(solver.set_init_4h_homo(NV, PHYS["Lv"])))[0]
+    for _ in range(warm):
+        ora.conserveMoments(ora.ComputeQ(f))
+    t = time.time()
+    for _ in range(reps):
+        ora.conserveMoments(ora.ComputeQ(f))
+    dt = (time.time() - t) / reps
+    return dict(value=1. / dt, unit=UNIT, cores=int(ora.num_threads), kind=kind,
+                sample="%d x (ComputeQ + conserveMoments) on 1 cell, N=%d, OpenMP on %d threads; init %.0f s excluded" % (reps, NSPEC, ora.num_threads, t_init)), dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the metric's unit, timed on the host."""
+    if rank != 0:
+        return
+    base, dt = cpu_eval_rate(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "two-stream Landau-Poisson step, %d x-cells per GPU, Nv=%d, N=%d" % (CELLS_PER_GPU, NV, NSPEC),
+                       "sample": "each step = one ComputeQ + conserveMoments on one cell (the metric's unit)"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    from lpsolver_b200 import solver
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, "--gpus must equal the number of launched ranks"
+
+    Nx = CELLS_PER_GPU * world
+    s = solver.ShardedSolver(Nx, NV, NSPEC, homogeneous=False, rank=rank, world=world, device=local, dist=dist, **PHYS)
+    g = s.g
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    U0 = solver.set_init_ld(Nx, NV, PHYS["Lv"], PHYS["Lx"], A_AMP, K_WAVE, True, s.x_begin, s.x_count)
+    host = torch.from_numpy(U0).pin_memory()
+    host_np = host.numpy()
+    back = torch.empty_like(host).pin_memory()
+    back_np = back.numpy()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    s.upload(host_np)
+    for _ in range(args.warmup):
+        s.step(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    g.profile_computeQ(True)
+    l0 = g.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        s.step(1)
+    e1.record()
+    barrier()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = sum_over_ranks(g.launch_count - l0)
+    cq_ms, cq_n = g.profile_read()
+    g.profile_computeQ(False)
+    clocks = sampler.finish()
+    value = 4. * Nx * args.steps / t_dev
+
+    # ---- end to end: host buffers in, host buffers out, every step --------------------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.upload(host_np)          # H2D from pinned memory (the reference's MPI_Bcast(U), LP_ompi.cpp:658)
+        s.step(1)
+        s.download(back_np)        # D2H (the reference's gather for diagnostics/output, LP_ompi.cpp:813-849)
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": 4. * Nx * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 8 * world),
+           "d2h_bytes_per_step": int(back.numel() * 8 * world), "steps": e2e_steps, "timesteps_per_s": e2e_steps / t_e2e}
+
+    # ---- roofline of the dominant kernel (ComputeQ, FP64-pipe bound) ----------------------------
+    roof = None
+    if cq_n > 0:
+        avg_s = cq_ms * 1e-3 / cq_n
+        achieved = flop_per_eval(NSPEC) * s.x_count / avg_s / 1e12
+        peak = pkg.lpgpu.fp64_peak_tflops(local)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "computeq_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roof = {"bound": "fp64", "kernel": "k_computeQ_tiled", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic, "avg_launch_ms": avg_s * 1e3, "launches": cq_n,
+                "share_of_step": cq_ms * 1e-3 / t_dev,
+                "peak_source": "DFMA micro-benchmark run live on this GPU (lpgpu_fp64_peak); MEASURED_PEAKS.json holds only HBM and bf16 peaks; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
+                "algorithmic_flop_per_launch": flop_per_eval(NSPEC) * s.x_count}
+
+    line = None
+    if rank == 0:
+        ws_mb = (3 * (s.x_count + 2) * 6 * NV ** 3 * 8 + s.x_count * NSPEC ** 3 * 8 * (3 + 2 * 6) + s.x_count * NSPEC * 4 * NV * NV * 16) / 2 ** 20
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "two-stream Landau-Poisson timestep (SSP-RK3 DG advection + RK4 spectral Landau collision), %d x-cells per GPU, Nv=%d, N=%d (BASELINE config Nx=256,Nv=32^3 on 8 GPUs, per-GPU shard)" % (CELLS_PER_GPU, NV, NSPEC),
+                           "Nx": Nx, "Nv": NV, "N": NSPEC, "evals_per_step": 4 * Nx, "parallelism": "x-cells sharded over %d GPU(s)" % world,
+                           "l2": "per-GPU working set %.0f MB > 126 MB L2; no flush between steps" % ws_mb},
+                "timesteps_per_s": args.steps / t_dev, "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+
+    # ---- BASELINE's single-cell homogeneous config, and the CPU baseline (N=1 only) --------------
+    if world == 1:
+        s.close()
+        h = solver.ShardedSolver(1, NV, NSPEC, homogeneous=True, device=local, **PHYS)
+        h.g.set_stream(torch.cuda.current_stream().cuda_stream)
+        h.upload(solver.set_init_4h_homo(NV, PHYS["Lv"]))
+        for _ in range(3):
+            h.step(1)
+        torch.cuda.synchronize()
+        e0.record()
+        nh = 20
+        for _ in range(nh):
+            h.step(1)
+        e1.record()
+        torch.cuda.synchronize()
+        th = e0.elapsed_time(e1) * 1e-3
+        line["homogeneous_1cell"] = {"workload": "space-homogeneous collision-only relaxation, 1 cell, Nv=N=32 (FourHump IC)",
+                                     "value": 4 * nh / th, "unit": UNIT, "timesteps_per_s": nh / th, "steps": nh}
+        h.close()
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"], _ = cpu_eval_rate(2, 1)
+            except Exception as e:                          # the oracle is a checker; never let it break the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+    else:
+        s.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

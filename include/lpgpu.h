@@ -111,6 +111,14 @@ int lpgpu_get_stage_spectrum(lpgpu_ctx *c, int which, double *out /* x_count*N^3
  * -- computePhi_x_0, computeC_rho, Int_E, Int_E1st, Int_E2nd (advection_1.cpp:419-429) */
 int lpgpu_field(lpgpu_ctx *c, double *out);
 
+/* ---- measurement helpers (bench.py) -------------------------------------------------------- */
+/* Bracket every ComputeQ kernel launch with CUDA events on the context's stream; read returns the
+ * summed device time and the number of launches since enable (synchronises the stream). */
+int lpgpu_profile_computeQ(lpgpu_ctx *c, int enable);
+int lpgpu_profile_read(lpgpu_ctx *c, double *total_ms, long long *launches);
+/* DFMA micro-benchmark: sustained FP64 FMA rate of `device` in TFLOP/s (roofline denominator). */
+int lpgpu_fp64_peak(int device, double *tflops);
+
 /* ---- diagnostics ------------------------------------------------------------------------ */
 /* Partial sums over this shard: out5 = mass, P1, P2, P3, KiE (computeMass/Momentum/KiE,
  * MomentCalculations.cpp:23-131); sum over shards for the global value.  ms_local_host (may be

@@ -84,6 +84,9 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_upload(&c->d_S, t.S));
   A_(dev_upload(&c->d_node_xi, t.node_xi));
   A_(dev_upload(&c->d_vc, t.vc));
+  A_(dev_upload(&c->d_Etab, t.Etab));
+  c->cap_part = 16;
+  A_(dev_alloc(&c->d_qpart, (size_t)2 * c->N3 * c->cap_part));
   A_(dev_upload(&c->d_node_cell, t.node_cell));
   const size_t plane = (size_t)6 * c->sv, nst = plane * (c->ncell + 2);
   for (int s = 0; s < 3; s++) {
@@ -118,9 +121,10 @@ int lpgpu_finalize(lpgpu_ctx *c)
   cudaDeviceSynchronize();
   double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Ffwd, c->d_Finv, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
-                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B};
+                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart};
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
+  for (auto &e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return LPGPU_OK;
 }
@@ -266,6 +270,7 @@ int lpgpu_setInit_spectral(lpgpu_ctx *c, double *f_host)
   LP_CUDA(cudaStreamSynchronize(c->stream));
   return LPGPU_OK;
 }
+
 } // extern "C"
 template <typename F>
 static int chunked(lpgpu_ctx *c, int B, F body)
@@ -350,6 +355,33 @@ int lpgpu_field(lpgpu_ctx *c, double *out)
   return LPGPU_OK;
 }
 
+// ---- measurement helpers ------------------------------------------------------------------------
+int lpgpu_profile_computeQ(lpgpu_ctx *c, int enable)
+{
+  LP_ENTER(c);
+  if (enable && c->prof_ev.empty()) {
+    c->prof_ev.resize(8192);
+    for (auto &e : c->prof_ev) LP_CUDA(cudaEventCreate(&e));
+  }
+  c->prof_on = enable != 0;
+  c->prof_used = 0;
+  return LPGPU_OK;
+}
+int lpgpu_profile_read(lpgpu_ctx *c, double *total_ms, long long *launches)
+{
+  LP_ENTER(c);
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  double tot = 0.;
+  for (size_t k = 0; k + 1 < c->prof_used; k += 2) {
+    float ms = 0.f;
+    LP_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[k], c->prof_ev[k + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (long long)(c->prof_used / 2);
+  return LPGPU_OK;
+}
+
 // ---- diagnostics ----------------------------------------------------------------------------
 int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host)
 {
@@ -390,4 +422,43 @@ int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms, double *EleE)
   return LPGPU_OK;
 }
 
+
+// FP64 FMA throughput of the device (the roofline denominator of ComputeQ): 8 independent DFMA
+// chains per thread, enough threads to fill every SM.
 } // extern "C"
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 1.2345) out[0] = x0;
+}
+extern "C" int lpgpu_fp64_peak(int device, double *tflops)
+{
+  if (!tflops) return LPGPU_EINVAL;
+  if (lpgpu_device_count() <= 0) { lp_set_error("lpgpu_fp64_peak: no CUDA device"); return LPGPU_ENODEV; }
+  LP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LP_CUDA(cudaGetDeviceProperties(&prop, device));
+  double *d = nullptr;
+  LP_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  LP_CUDA(cudaEventCreate(&e0)); LP_CUDA(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double best = 0.;
+  for (int rep = 0; rep < 4; rep++) {
+    LP_CUDA(cudaEventRecord(e0, 0));
+    k_dfma_peak<<<blocks, 256>>>(d, iters, 0.999999, 1e-7);
+    LP_CUDA(cudaEventRecord(e1, 0));
+    LP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return LPGPU_OK;
+}

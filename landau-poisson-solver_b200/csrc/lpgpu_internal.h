@@ -5,6 +5,8 @@
 #include <string>
 #include <vector>
 
+#define LP_ETAB_PAD 8
+
 // Host-side tables that depend only on (N, Nv, Lv): built once in lpgpu_init.
 struct LpTables {
   int N, Nv;
@@ -18,6 +20,7 @@ struct LpTables {
   std::vector<int> node_cell;              // N
   std::vector<double> node_xi;             // N
   std::vector<double> vc;                  // Nv  cell centres Gridv(j)
+  std::vector<double> Etab;                // N + 2*LP_ETAB_PAD: eta[z] - eta[N/2] for z = -PAD .. N+PAD-1
 };
 void lp_build_tables(const lpgpu_params &p, LpTables &t);
 
@@ -28,6 +31,8 @@ struct lpgpu_ctx {
   cudaStream_t stream;
   long long launches;
   // ---- device tables
+  double *d_Etab, *d_qpart;
+  size_t cap_part;         // capacity of d_qpart in spectra (cells x l-splits)
   double *d_eta, *d_G, *d_C5, *d_CCt, *d_Ffwd, *d_Finv, *d_T, *d_M, *d_S, *d_node_xi, *d_vc;
   int *d_node_cell;
   // ---- DG state, plane-major: buf[((p*6 + c)*sv + j)], p = 0..ncell+1 (planes 0 and ncell+1 are x halos)
@@ -43,6 +48,10 @@ struct lpgpu_ctx {
   double *d_lam;                           // 5 per cell
   double *d_B;                             // projection intermediate: ncell*N*4*Nv^2 complex
   size_t cap_cells;        // capacity (in cells) of the collision work arrays
+  // ---- optional CUDA-event timing of the ComputeQ launches (bench.py roofline)
+  bool prof_on;
+  std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+  size_t prof_used;        // events used so far
 };
 
 // error plumbing

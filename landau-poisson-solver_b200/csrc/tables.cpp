@@ -171,6 +171,11 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
       t.T[o] = T.re; t.T[o + 1] = T.im; t.M[o] = Mm.re; t.M[o + 1] = Mm.im; t.S[o] = S.re; t.S[o + 1] = S.im;
     }
 
+  // ---- eta differences along one axis for the tiled ComputeQ: eta[z] - eta[N/2] (extrapolated in the pad)
+  t.Etab.resize(N + 2 * LP_ETAB_PAD);
+  for (int z = -LP_ETAB_PAD; z < N + LP_ETAB_PAD; z++)
+    t.Etab[z + LP_ETAB_PAD] = (z >= 0 && z < N) ? t.eta[z] - t.eta[N / 2] : (double)(z - N / 2) * t.h_eta;
+
   // ---- spectral node -> DG cell: identical expression to the reference, evaluated on the host
   t.node_cell.resize(N); t.node_xi.resize(N);
   for (int l = 0; l < N; l++) {

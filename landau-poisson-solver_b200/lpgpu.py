@@ -42,6 +42,7 @@ EXPORTS = [
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
+    "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak",
 ]
 
 _lib = None
@@ -74,6 +75,9 @@ def load_library():
     L.lpgpu_conserveMoments.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.lpgpu_get_stage_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.lpgpu_moments_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lpgpu_profile_computeQ.argtypes = [C.c_void_p, C.c_int]
+    L.lpgpu_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.lpgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.lpgpu_eleE_from_ms.argtypes = [C.POINTER(Params), C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -85,6 +89,16 @@ def _ptr(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def fp64_peak_tflops(device=0):
+    """DFMA micro-benchmark on `device` (TFLOP/s)."""
+    L = load_library()
+    v = C.c_double()
+    rc = L.lpgpu_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise LPGpuError("lpgpu error %d: %s" % (rc, (L.lpgpu_last_error() or b"").decode()))
+    return v.value
 
 
 class LPGpu:
@@ -207,6 +221,15 @@ class LPGpu:
         out = np.empty(1 + 4 * self.Nx)
         self._check(self.L.lpgpu_field(self.h, _ptr(out)))
         return out
+
+    # -- measurement helpers
+    def profile_computeQ(self, enable=True):
+        self._check(self.L.lpgpu_profile_computeQ(self.h, int(bool(enable))))
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_longlong()
+        self._check(self.L.lpgpu_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # -- diagnostics
     def moments_partial(self):

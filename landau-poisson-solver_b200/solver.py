@@ -1,0 +1,342 @@
+"""Host-side mirror of the reference driver for the hot path (LP_ompi.cpp:76-952), above the C ABI.
+
+What stays on the host, as in the reference: reading ``LPsolver-input.txt`` (InputParsing.cpp),
+the initial conditions (SetInit_1.cpp:68-325), the time loop, and writing ``Data/Moments_*.dc``
+(LP_ompi.cpp:442-472, 622-630, 836-844).  What runs on the GPU through include/lpgpu.h: RK3,
+setInit_spectral, ComputeQ, conserveMoments, RK4 and the moment reductions.
+
+Sharding (replaces the reference's MPI split, LP_ompi.cpp:205-220): one process per GPU, each owning
+a contiguous block of x cells.  Collisions need no communication.  Each SSP-RK3 stage needs one
+all-gather of the per-cell sums (m_i, s_i) and one periodic halo plane from each x neighbour
+(advection_1.cpp:297,306); both go through ``torch.distributed`` (NCCL on GPUs, gloo in CPU tests).
+"""
+import math
+import os
+
+import numpy as np
+
+from . import lpgpu
+
+# 5-point Gauss-Legendre rule used by every SetInit_* (advection_1.cpp:12-13)
+_GW = np.array([0.5688888888888889, 0.4786286704993665, 0.4786286704993665, 0.2369268850561891, 0.2369268850561891])
+_GT = np.array([0., -0.5384693101056831, 0.5384693101056831, -0.9061798459386640, 0.9061798459386640])
+
+
+# ------------------------------------------------------------------------------------------------
+# input file (GRVY syntax subset the reference uses: key = value  # comment, [Section], True/False, 'str')
+def parse_input_file(path):
+    kv, section = {}, ""
+    with open(path) as fh:
+        for raw in fh:
+            line, inq = "", False
+            for ch in raw:
+                if ch in "'\"":
+                    inq = not inq
+                if ch == "#" and not inq:
+                    break
+                line += ch
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith("["):
+                section = line[1:line.index("]")].strip()
+                continue
+            if "=" not in line:
+                continue
+            k, v = (s.strip() for s in line.split("=", 1))
+            if len(v) >= 2 and v[0] in "'\"" and v[-1] == v[0]:
+                v = v[1:-1]
+            kv[(section + "/" if section else "") + k] = v
+    return kv
+
+
+def _bool(kv, key, default=False):
+    return kv.get(key, str(default)).strip().lower() in ("true", "1", "yes", ".true.")
+
+
+class RunConfig:
+    """The scalars main() derives from the input file (LP_ompi.cpp:142-184; InputParsing.cpp:291-470)."""
+
+    def __init__(self, kv):
+        self.flag = kv["flag"]
+        self.nT, self.Nx, self.Nv, self.N = int(kv["nT"]), int(kv["Nx"]), int(kv["Nv"]), int(kv["N"])
+        self.nu, self.dt = float(kv["nu"]), float(kv["dt"])
+        self.gamma = int(kv.get("gamma", -3))
+        ics = [n for n in ("Damping", "TwoStream", "FourHump", "TwoHump", "Doping") if _bool(kv, n)]
+        if len(ics) != 1:
+            raise ValueError("exactly one of Damping, TwoStream, FourHump, TwoHump, Doping must be True (got %s)" % ics)
+        self.ic = ics[0]
+        if _bool(kv, "First") == _bool(kv, "Second"):
+            raise ValueError("exactly one of First / Second must be True")
+        self.second = _bool(kv, "Second")
+        self.second_name = kv.get("Second/Name")
+        self.homogeneous = _bool(kv, "Homogeneous")
+        for unsupported in ("FullandLinear", "LinearLandau", "MassConsOnly"):
+            if _bool(kv, unsupported):
+                raise NotImplementedError("%s is outside the GPU hot path (SURVEY.md section 8f.4)" % unsupported)
+        if self.ic in ("Doping", "TwoHump"):
+            raise NotImplementedError("%s initial/boundary conditions are outside the GPU hot path" % self.ic)
+        sec = self.ic
+        self.A_amp = float(kv.get(sec + "/A_amp", 0.))
+        self.k_wave = float(kv.get(sec + "/k_wave", 0.5))
+        self.Lv = float(kv[sec + "/Lv"])
+        if sec == "TwoStream":
+            self.Lx = float(kv[sec + "/Lx"])
+            self.k_wave = 2 * math.pi / 4.           # forced by the reference (InputParsing.cpp:456)
+        else:
+            self.Lx = float(kv.get(sec + "/Lx", 2 * math.pi / self.k_wave))
+        if self.homogeneous and self.ic != "FourHump":
+            raise ValueError("the homogeneous code only supports the FourHump IC (LP_ompi.cpp:477-492)")
+
+    @classmethod
+    def from_file(cls, path):
+        return cls(parse_input_file(path))
+
+    def moments_filename(self):
+        """Data/Moments_... name, byte-for-byte the reference's sprintf (LP_ompi.cpp:442-443, 459-460)."""
+        g = lambda x: "%g" % x
+        if self.homogeneous:
+            return "Data/Moments_nu%sA%sk%sNv%dLv%sSpectralN%ddt%snT%d_%s.dc" % (
+                g(self.nu), g(self.A_amp), g(self.k_wave), self.Nv, g(self.Lv), self.N, g(self.dt), self.nT, self.flag)
+        return "Data/Moments_nu%sA%sk%sNx%dLx%sNv%dLv%sSpectralN%ddt%snT%d_%s.dc" % (
+            g(self.nu), g(self.A_amp), g(self.k_wave), self.Nx, g(self.Lx), self.Nv, g(self.Lv), self.N, g(self.dt), self.nT, self.flag)
+
+    def initial_condition(self, x_begin=0, x_count=None):
+        if self.homogeneous:
+            return set_init_4h_homo(self.Nv, self.Lv)
+        if self.ic in ("Damping", "TwoStream"):
+            return set_init_ld(self.Nx, self.Nv, self.Lv, self.Lx, self.A_amp, self.k_wave, self.ic == "TwoStream", x_begin, x_count)
+        return set_init_4h(self.Nx, self.Nv, self.Lv, self.Lx, x_begin, x_count)
+
+
+def format_moments_row(m, homogeneous):
+    """One line of Moments_*.dc (LP_ompi.cpp:622-630 / 836-844); m = mass, P1..3, KiE, EleE."""
+    if homogeneous:
+        return "%11.8g %11.8g %11.8g %11.8g %11.8g %11.8g %11.8g %11.8g \n" % (m[0], m[1], m[2], m[3], 0.0, 0.0, 0.0, m[4])
+    t = math.sqrt(m[5])
+    return "%11.8g %11.8g %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g \n" % (
+        m[0], m[1], m[2], m[3], m[4], m[5], t, math.log(t), m[4] + m[5])
+
+
+# ------------------------------------------------------------------------------------------------
+# initial conditions (host, run once) -- vectorised restatement of SetInit_1.cpp
+def _maxwellian(v1, v2, v3, T):
+    return np.exp(-(v1 * v1 + v2 * v2 + v3 * v3) / (2 * T)) / (2 * np.pi * T * np.sqrt(2 * T * np.pi))
+
+
+def _two_gauss(v1, v2, v3):
+    s = np.pi / 10
+    return 0.5 * (np.exp(-((v1 - 2 * s) ** 2 + v2 * v2 + v3 * v3) / (2 * s * s)) + np.exp(-((v1 + 2 * s) ** 2 + v2 * v2 + v3 * v3) / (2 * s * s))) \
+        / (2 * np.pi * s * s * np.sqrt(2 * np.pi * s * s))
+
+
+def _velocity_cell_moments(Nv, Lv, profile, shift=(0., 0., 0.)):
+    """tmp0..tmp4 of SetInit_LD / SetInit_4H (SetInit_1.cpp:80-99): cell moments of `profile`
+    against 1, xi1, xi2, xi3, |xi|^2 with the 5^3-point Gauss rule.  Returns 5 arrays [Nv,Nv,Nv]."""
+    dv = 2. * Lv / Nv
+    c = -Lv + (np.arange(Nv) + 0.5) * dv
+    q = c[:, None] + 0.5 * dv * _GT[None, :]                          # [Nv,5] quadrature points per dimension
+    V1 = q[:, None, None, :, None, None] + shift[0]
+    V2 = q[None, :, None, None, :, None] + shift[1]
+    V3 = q[None, None, :, None, None, :] + shift[2]
+    W = _GW[:, None, None] * _GW[None, :, None] * _GW[None, None, :]
+    tp = W[None, None, None] * profile(V1, V2, V3)
+    t1 = 0.5 * _GT[:, None, None] * np.ones((5, 5, 5))
+    t2 = 0.5 * _GT[None, :, None] * np.ones((5, 5, 5))
+    t3 = 0.5 * _GT[None, None, :] * np.ones((5, 5, 5))
+    t4 = 0.25 * (_GT[:, None, None] ** 2 + _GT[None, :, None] ** 2 + _GT[None, None, :] ** 2)
+    out = [np.sum(tp, axis=(3, 4, 5))]
+    for wgt in (t1, t2, t3, t4):
+        out.append(np.sum(tp * wgt[None, None, None], axis=(3, 4, 5)))
+    return [o * 0.125 for o in out]
+
+
+def set_init_ld(Nx, Nv, Lv, Lx, A_amp, k_wave, twostream=False, x_begin=0, x_count=None):
+    """SetInit_LD (SetInit_1.cpp:68-123): Maxwellian (T=0.4) or two-Gaussian profile in v times
+    1 + A cos(k x) in x, L2-projected on the DG basis.  Returns AoS U for cells [x_begin, x_begin+x_count)."""
+    x_count = Nx if x_count is None else x_count
+    prof = _two_gauss if twostream else (lambda a, b, c: _maxwellian(a, b, c, 0.4))
+    t0, t1, t2, t3, t4 = _velocity_cell_moments(Nv, Lv, prof)
+    dx = Lx / Nx
+    i = np.arange(x_begin, x_begin + x_count)
+    xp, xm = (i + 0.5 + 0.5) * dx, (i - 0.5 + 0.5) * dx
+    a, c = A_amp, k_wave
+    xf = dx + (np.sin(c * xp) - np.sin(c * xm)) * a / c
+    u1f = (0.5 * (np.sin(c * xp) + np.sin(c * xm)) + (np.cos(c * xp) - np.cos(c * xm)) / (c * dx)) * (a / c)
+    U = np.empty((x_count, Nv, Nv, Nv, 6))
+    X = xf[:, None, None, None]
+    tp0, tp5 = X * t0[None] / dx, X * t4[None] / dx
+    U[..., 0] = 19 * tp0 / 4. - 15 * tp5
+    U[..., 5] = 60 * tp5 - 15 * tp0
+    U[..., 1] = u1f[:, None, None, None] * t0[None] * 12. / dx
+    U[..., 2] = X * t1[None] * 12 / dx
+    U[..., 3] = X * t2[None] * 12 / dx
+    U[..., 4] = X * t3[None] * 12 / dx
+    return U.reshape(-1)
+
+
+def set_init_4h(Nx, Nv, Lv, Lx, x_begin=0, x_count=None):
+    """SetInit_4H (SetInit_1.cpp:175-258)."""
+    x_count = Nx if x_count is None else x_count
+    dx, C = Lx / Nx, 1.
+    i = np.arange(x_begin, x_begin + x_count)
+    xq = (i[:, None] + 0.5) * dx + 0.5 * dx * _GT[None, :]
+    U = np.zeros((x_count, Nv, Nv, Nv, 6))
+    for p in range(4):
+        sv, sx = C * (-1.) ** p, C * (-1.) ** (p // 2)
+        t0, t1, t2, t3, t4 = _velocity_cell_moments(Nv, Lv, lambda a, b, c: _maxwellian(a, b, c, 0.4), (sv, sv, sv))
+        T = 0.4
+        tpx = _GW[None, :] * np.exp(-(xq - Lx / 2 + sx) ** 2 / (2 * T)) / np.sqrt(2 * T * np.pi)
+        x0 = (0.5 * np.sum(tpx, axis=1))[:, None, None, None]
+        x1 = (0.5 * np.sum(tpx * 0.5 * _GT[None, :], axis=1))[:, None, None, None]
+        tp0, tp5 = x0 * t0[None], x0 * t4[None]
+        U[..., 0] += 19 * tp0 / 4. - 15 * tp5
+        U[..., 5] += 60 * tp5 - 15 * tp0
+        U[..., 1] += x1 * t0[None] * 12
+        U[..., 2] += x0 * t1[None] * 12
+        U[..., 3] += x0 * t2[None] * 12
+        U[..., 4] += x0 * t3[None] * 12
+    return (U / 4).reshape(-1)
+
+
+def set_init_4h_homo(Nv, Lv):
+    """SetInit_4H_Homo (SetInit_1.cpp:261-325); U1 is 0 (the reference never sets it)."""
+    C = 0.02
+    U = np.zeros((Nv, Nv, Nv, 6))
+    for p in range(4):
+        s1, s23 = C * (-1.) ** (p // 2), C * (-1.) ** p
+        t0, t1, t2, t3, t4 = _velocity_cell_moments(Nv, Lv, lambda a, b, c: _maxwellian(a, b, c, 0.4), (s1, s23, s23))
+        U[..., 0] += 19 * t0 / 4. - 15 * t4
+        U[..., 5] += 60 * t4 - 15 * t0
+        U[..., 2] += t1 * 12
+        U[..., 3] += t2 * 12
+        U[..., 4] += t3 * 12
+    return (U / 4).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# sharding helpers (pure host logic; unit-tested on CPU with gloo)
+def shard_range(Nx, world, rank):
+    """Contiguous block of x cells owned by `rank` (the reference's chunk_Nx, LP_ompi.cpp:208-220,
+    with the constraint Nx % world == 0 instead of its Nv^3 % nprocs == 0)."""
+    if Nx % world != 0:
+        raise ValueError("Nx (%d) must be divisible by the number of GPUs (%d)" % (Nx, world))
+    n = Nx // world
+    return rank * n, n
+
+
+def exchange_stage(dist, rank, world, ms_local, ms_all, send_left, send_right, recv_left, recv_right):
+    """The one exchange step of an SSP-RK3 stage: all-gather of (m_i, s_i) and the periodic halo
+    planes.  Arguments are torch tensors (CUDA for NCCL, CPU for gloo) aliasing the buffers of
+    lpgpu_exchange.  recv_left <- left neighbour's send_right, recv_right <- right neighbour's
+    send_left."""
+    if ms_all.is_cuda:
+        dist.all_gather_into_tensor(ms_all, ms_local)
+    else:
+        dist.all_gather(list(ms_all.chunk(world)), ms_local)
+    left, right = (rank - 1) % world, (rank + 1) % world
+    # order matters when left == right (world == 2): first send pairs with first recv on the peer
+    reqs = [dist.isend(send_right, right), dist.isend(send_left, left),
+            dist.irecv(recv_left, left), dist.irecv(recv_right, right)]
+    for r in reqs:
+        r.wait()
+
+
+class _DeviceBuffer:
+    """Expose a raw device address as a CUDA array so torch can alias it without copying."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class ShardedSolver:
+    """One rank of the x-sharded solver.  world == 1 needs no process group."""
+
+    def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.homogeneous = bool(homogeneous)
+        if homogeneous:
+            self.x_begin, self.x_count = 0, 1
+        else:
+            self.x_begin, self.x_count = shard_range(Nx, world, rank)
+        self.g = lpgpu.LPGpu(Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=homogeneous, x_begin=self.x_begin,
+                             x_count=self.x_count, device=device)
+        self.nu = nu
+        self._ex = None
+        if world > 1 and not homogeneous:
+            import torch
+            self.torch = torch
+            self.g.set_stream(torch.cuda.current_stream().cuda_stream)
+            self._ex = []
+            for stage in range(3):
+                e = self.g.exchange_info(stage)
+                n = e.plane_doubles
+                wrap = lambda p, cnt: torch.as_tensor(_DeviceBuffer(p, cnt), device="cuda:%d" % device)
+                self._ex.append(dict(ms_local=wrap(e.ms_local, 2 * self.x_count), ms_all=wrap(e.ms_all, 2 * Nx),
+                                     send_left=wrap(e.send_left, n), send_right=wrap(e.send_right, n),
+                                     recv_left=wrap(e.recv_left, n), recv_right=wrap(e.recv_right, n)))
+
+    def upload(self, U_shard):
+        self.g.upload_U(U_shard)
+
+    def download(self, out=None):
+        return self.g.download_U(out)
+
+    def advect(self):
+        if self.homogeneous:
+            return
+        if self.world == 1:
+            self.g.advect_rk3()
+            return
+        for stage in range(3):
+            self.g.advect_reduce(stage)
+            exchange_stage(self.dist, self.rank, self.world, **self._ex[stage])
+            self.g.advect_apply(stage)
+
+    def step(self, nsteps=1):
+        """nsteps passes of the while(t<nT) body (LP_ompi.cpp:662-813) without diagnostics."""
+        if self.world == 1 or self.homogeneous:
+            self.g.step(nsteps)
+            return
+        for _ in range(nsteps):
+            self.advect()
+            if self.nu > 0:
+                self.g.collide_step()
+
+    def moments(self):
+        """Global mass, P1..3, KiE, EleE (LP_ompi.cpp:820-827) on every rank."""
+        m5, ms = self.g.moments_partial()
+        if self.world > 1 and not self.homogeneous:
+            torch = self.torch
+            t = torch.from_numpy(m5).cuda()
+            self.dist.all_reduce(t)
+            m5 = t.cpu().numpy()
+            loc = torch.from_numpy(ms).cuda()
+            allms = torch.empty(2 * self.g.Nx, dtype=torch.float64, device=loc.device)
+            self.dist.all_gather_into_tensor(allms, loc)
+            ms = allms.cpu().numpy()
+        ele = 0. if self.homogeneous else self.g.eleE_from_ms(ms)
+        return np.concatenate([m5, [ele]])
+
+    def close(self):
+        self.g.close()
+
+
+def run_from_input_file(path="LPsolver-input.txt", outdir=".", device=0, quiet=False):
+    """Single-GPU equivalent of running the reference's `solver` in a directory holding
+    LPsolver-input.txt: writes Data/Moments_*.dc with one row per step (row 1 = initial state)."""
+    cfg = RunConfig.from_file(path)
+    s = ShardedSolver(cfg.Nx, cfg.Nv, cfg.N, cfg.Lv, cfg.Lx, cfg.nu, cfg.dt, homogeneous=cfg.homogeneous, device=device)
+    s.upload(cfg.initial_condition())
+    out = os.path.join(outdir, cfg.moments_filename())
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as fh:
+        for t in range(cfg.nT + 1):
+            m = s.moments()
+            fh.write(format_moments_row(m, cfg.homogeneous))
+            if not quiet:
+                print("step %d: " % t + " ".join("%11.8g" % x for x in m))
+            if t < cfg.nT:
+                s.step(1)
+    s.close()
+    return out
