@@ -41,11 +41,58 @@ struct CqCfg {
   static constexpr int NI = (NITEM + CS - 1) / CS;
   static constexpr int ZP = (N + 2 * (R - 1)) | 1; // padded, odd row length of the b slab (bank-conflict free)
   static constexpr int NT = 32 * KG * JG * CSW;   // threads per CTA
+  static constexpr int NE = N + 2 * LP_ETAB_PAD;   // eta-difference table, also staged in shared memory
   static constexpr size_t SLAB_BYTES = ((size_t)N * N + (size_t)N * ZP) * 16 + (size_t)N * N * 6 * 8;
   static constexpr size_t RED_BYTES = (size_t)CS * N * N * 16;
-  static constexpr size_t SMEM = SLAB_BYTES > RED_BYTES ? SLAB_BYTES : RED_BYTES;
+  static constexpr size_t SMEM = (SLAB_BYTES > RED_BYTES ? SLAB_BYTES : RED_BYTES) + (size_t)NE * 8;
   static_assert(JL * CSL == 32, "a warp is JL row pairs x CSL slices");
   static_assert(H % JL == 0 && N % (2 * R) == 0, "tiling must divide N");
+};
+
+
+// One n-step of a tile: R pairs  acc[r] += Wt(e3_r) * a * b_r  against the z-window held in rotated
+// registers.  U is the rotation phase: logical window slot r lives in physical slot (r - U) mod R, so
+// sliding the window by one z costs no register moves -- the slot that drops out receives the next
+// element.  Wt(e3) = c0 + e3 (c1 + e3 c2) with c0 = r0 + e2 (r1 + e2 r2), c1 = p1 + p2 e2.
+template <int R, int U>
+__device__ __forceinline__ void cq_step(double2 (&acc)[R], double2 (&bw)[R], double (&ew)[R], const double2 *ap,
+                                        const double *cp, const double2 *bnew, const double *enew, double e2)
+{
+  const double2 a = *ap;
+  const double2 c01 = reinterpret_cast<const double2 *>(cp)[0], c23 = reinterpret_cast<const double2 *>(cp)[1],
+                c45 = reinterpret_cast<const double2 *>(cp)[2];
+  const double c0 = fma(e2, fma(e2, c23.x, c01.y), c01.x);
+  const double c1 = fma(c45.x, e2, c23.y);
+  const double c2 = c45.y;
+  #pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int p = (r - U + R) % R;
+    const double W = fma(ew[p], fma(ew[p], c2, c1), c0);
+    const double war = W * a.x, wai = W * a.y;
+    acc[r].x = fma(war, bw[p].x, acc[r].x);
+    acc[r].x = fma(-wai, bw[p].y, acc[r].x);
+    acc[r].y = fma(war, bw[p].y, acc[r].y);
+    acc[r].y = fma(wai, bw[p].x, acc[r].y);
+  }
+  constexpr int pn = (R - 1 - U + R) % R;
+  bw[pn] = *bnew; ew[pn] = *enew;
+}
+// steps U .. R-1 of a chunk; FULL = false stops after `cnt` steps (tail of the n loop)
+template <int R, int U, bool FULL>
+struct CqChunk {
+  static __device__ __forceinline__ void run(double2 (&acc)[R], double2 (&bw)[R], double (&ew)[R], const double2 *ap,
+                                             const double *cp, const double2 *bp, const double *ep, double e2, int cnt)
+  {
+    if (FULL || U < cnt) {
+      cq_step<R, U>(acc, bw, ew, ap + U, cp + 6 * U, bp - U, ep - U, e2);
+      CqChunk<R, U + 1, FULL>::run(acc, bw, ew, ap, cp, bp, ep, e2, cnt);
+    }
+  }
+};
+template <int R, bool FULL>
+struct CqChunk<R, R, FULL> {
+  static __device__ __forceinline__ void run(double2 (&)[R], double2 (&)[R], double (&)[R], const double2 *, const double *,
+                                             const double2 *, const double *, double, int) {}
 };
 
 template <int N, int R, int JL, int CSL, int CSW, int MINB>
@@ -59,6 +106,7 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
   double2 *As = sm2;                                        // [N][N]      a = fhat[l, m, n]
   double2 *Bs = As + N * N;                                 // [N][ZP]     b = fhat[x, y, z] at zz = z + R - 1
   double *Cf = reinterpret_cast<double *>(Bs + N * ZP);     // [N][N][6]   r0 r1 r2 p1 p2 c2
+  double *Es = reinterpret_cast<double *>(reinterpret_cast<char *>(sm2) + (C::SMEM - (size_t)C::NE * 8));   // eta[z] - eta[N/2]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int jj = lane % JL, csl = lane / JL;
@@ -68,10 +116,11 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
   const int wA = j + H + 1;                                 // items c < wA: row A, m = c; else row B, m = c - H
 
   // heavy CTAs (large l-window) first
-  const int b = blockIdx.x;
+  const int nB = gridDim.x / N;                             // cells in this launch
+  const int b = blockIdx.x / nB;                            // rank of i by window size: all cells of the heaviest i first
   const int i = (b & 1) ? H + (b >> 1) : H - 1 - (b >> 1);
   const int sl = blockIdx.y;
-  const long long cell = blockIdx.z;
+  const long long cell = blockIdx.x % nB;
   const double2 *fh = fhat + cell * (long long)(N * N * N);
 
   int ls, le;
@@ -89,6 +138,7 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
     #pragma unroll
     for (int r = 0; r < R; r++) { live[t][r] = make_double2(0., 0.); saved[t][r] = make_double2(0., 0.); }
   bool liveB = false;
+  for (int t = tid; t < C::NE; t += NT) Es[t] = Etab[t];
 
   for (int l = lo; l < hi; l++) {
     const int x = i + H - l;
@@ -125,7 +175,7 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
       const double2 *brow = Bs + y * ZP + (R - 1);
       const double2 *arow = As + m * N;
       const double *crow = Cf + 6 * m * N;
-      const double *et = Etab + LP_ETAB_PAD;                 // et[z] = eta[z] - eta[N/2], z in [-PAD, N+PAD)
+      const double *et = Es + LP_ETAB_PAD;                   // et[z] = eta[z] - eta[N/2], z in [-PAD, N+PAD)
 
       #pragma unroll
       for (int t = 0; t < 2; t++) {
@@ -133,29 +183,17 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
         double2 bw[R]; double ew[R];
         #pragma unroll
         for (int r = 0; r < R; r++) { bw[r] = brow[dmax + r]; ew[r] = et[dmax + r]; }
-        #pragma unroll 2
-        for (int d = dmax; d >= dmin; d--) {
-          const int n = k0 + H - d;
-          const double2 a = arow[n];
-          const double2 c01 = *reinterpret_cast<const double2 *>(crow + 6 * n);
-          const double2 c23 = *reinterpret_cast<const double2 *>(crow + 6 * n + 2);
-          const double2 c45 = *reinterpret_cast<const double2 *>(crow + 6 * n + 4);
-          const double c0 = fma(e2, fma(e2, c23.x, c01.y), c01.x);   // r0 + e2 (r1 + e2 r2)
-          const double c1 = fma(c45.x, e2, c23.y);                    // p1 + p2 e2
-          const double c2 = c45.y;
-          #pragma unroll
-          for (int r = 0; r < R; r++) {
-            const double W = fma(ew[r], fma(ew[r], c2, c1), c0);
-            const double war = W * a.x, wai = W * a.y;
-            live[t][r].x = fma(war, bw[r].x, live[t][r].x);
-            live[t][r].x = fma(-wai, bw[r].y, live[t][r].x);
-            live[t][r].y = fma(war, bw[r].y, live[t][r].y);
-            live[t][r].y = fma(wai, bw[r].x, live[t][r].y);
-          }
-          #pragma unroll
-          for (int r = R - 1; r > 0; r--) { bw[r] = bw[r - 1]; ew[r] = ew[r - 1]; }
-          if (d > dmin) { bw[0] = brow[d - 1]; ew[0] = et[d - 1]; }
+        // d runs dmax .. dmin (n = k0 + H - d ascending); pointers to a[n], coefficients, next b and next e3
+        const double2 *ap = arow + (k0 + H - dmax);
+        const double *cp = crow + 6 * (k0 + H - dmax);
+        const double2 *bp = brow + (dmax - 1);
+        const double *ep = et + (dmax - 1);
+        int cnt = dmax - dmin + 1;
+        for (; cnt >= R; cnt -= R) {
+          CqChunk<R, 0, true>::run(live[t], bw, ew, ap, cp, bp, ep, e2, R);
+          ap += R; cp += 6 * R; bp -= R; ep -= R;
         }
+        CqChunk<R, 0, false>::run(live[t], bw, ew, ap, cp, bp, ep, e2, cnt);
       }
     }
   }
@@ -208,7 +246,7 @@ static int launch_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B)
     while (SL > 1 && (size_t)B * SL > c->cap_part) SL--;
   }
   double2 *out = reinterpret_cast<double2 *>(SL > 1 ? c->d_qpart : q);
-  dim3 grid(N, SL, B);
+  dim3 grid(N * B, SL, 1);
   const bool prof = c->prof_on && c->prof_used + 2 <= c->prof_ev.size();
   if (prof) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   kern<<<grid, C::NT, C::SMEM, c->stream>>>(reinterpret_cast<const double2 *>(fhat), out, c->d_G, c->d_eta, c->d_Etab, SL);
