@@ -42,7 +42,12 @@ struct CqCfg {
   static constexpr int ZP = (N + 2 * (R - 1)) | 1; // padded, odd row length of the b slab (bank-conflict free)
   static constexpr int NT = 32 * KG * JG * CSW;   // threads per CTA
   static constexpr int NE = N + 2 * LP_ETAB_PAD;   // eta-difference table, also staged in shared memory
-  static constexpr size_t SLAB_BYTES = ((size_t)N * N + (size_t)N * ZP) * 16 + (size_t)N * N * 6 * 8;
+  // a-slab and coefficient rows are padded, and rows m >= H shifted by 32 bytes, so that the (up to four) distinct rows a warp
+  // touches in one load -- m, m+1 (two slices) and m-H, m+1-H (row B lanes) -- fall into different banks: one wavefront.
+  static constexpr int SA = N + 1;                 // a-slab row stride (complex)
+  static constexpr int SC = 6 * N + 2;             // coefficient row stride (doubles)
+  static constexpr int A_ELEMS = N * SA + 2, C_ELEMS = N * SC + 4;
+  static constexpr size_t SLAB_BYTES = ((size_t)A_ELEMS + (size_t)N * ZP) * 16 + (size_t)C_ELEMS * 8;
   static constexpr size_t RED_BYTES = (size_t)CS * N * N * 16;
   static constexpr size_t SMEM = (SLAB_BYTES > RED_BYTES ? SLAB_BYTES : RED_BYTES) + (size_t)NE * 8;
   static_assert(JL * CSL == 32, "a warp is JL row pairs x CSL slices");
@@ -104,7 +109,7 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
   constexpr int H = C::H, KG = C::KG, JG = C::JG, CS = C::CS, NITEM = C::NITEM, NI = C::NI, ZP = C::ZP, NT = C::NT;
   extern __shared__ double2 sm2[];
   double2 *As = sm2;                                        // [N][N]      a = fhat[l, m, n]
-  double2 *Bs = As + N * N;                                 // [N][ZP]     b = fhat[x, y, z] at zz = z + R - 1
+  double2 *Bs = As + C::A_ELEMS;                            // [N][ZP]     b = fhat[x, y, z] at zz = z + R - 1
   double *Cf = reinterpret_cast<double *>(Bs + N * ZP);     // [N][N][6]   r0 r1 r2 p1 p2 c2
   double *Es = reinterpret_cast<double *>(reinterpret_cast<char *>(sm2) + (C::SMEM - (size_t)C::NE * 8));   // eta[z] - eta[N/2]
 
@@ -145,9 +150,10 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
     const double e1 = eta[i] - eta[l];
     __syncthreads();
     for (int t = tid; t < N * N; t += NT) {
-      As[t] = fh[l * N * N + t];
+      const int m = t / N, n = t % N, up = (m >= H);
+      As[m * C::SA + 2 * up + n] = fh[l * N * N + t];
       const double *gg = G + 7LL * (l * N * N + t);
-      double *cf = Cf + 6 * t;
+      double *cf = Cf + m * C::SC + 4 * up + 6 * n;
       cf[0] = gg[0] - gg[1] * e1 * e1; cf[1] = -gg[4] * e1; cf[2] = -gg[2];
       cf[3] = -gg[5] * e1; cf[4] = -gg[6]; cf[5] = -gg[3];
     }
@@ -173,8 +179,8 @@ k_computeQ_tiled(const double2 *__restrict__ fhat, double2 *__restrict__ out, co
       const int y = row + H - m;
       const double e2 = eta[row] - eta[m];
       const double2 *brow = Bs + y * ZP + (R - 1);
-      const double2 *arow = As + m * N;
-      const double *crow = Cf + 6 * m * N;
+      const double2 *arow = As + m * C::SA + (m >= H ? 2 : 0);
+      const double *crow = Cf + m * C::SC + (m >= H ? 4 : 0);
       const double *et = Es + LP_ETAB_PAD;                   // et[z] = eta[z] - eta[N/2], z in [-PAD, N+PAD)
 
       #pragma unroll

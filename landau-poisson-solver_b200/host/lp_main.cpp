@@ -1,0 +1,257 @@
+// lpsolver -- host driver above the C ABI (include/lpgpu.h), the counterpart of the reference's
+// `solver` binary (LP_ompi.cpp:76-952) for the in-scope physics: it reads ./LPsolver-input.txt in the
+// reference's GRVY syntax, sets the initial condition on the host (SetInit_1.cpp:68-325), runs the
+// time loop with every hot-path call going to the GPU, and writes Data/Moments_*.dc (one row per step,
+// row 1 = initial state; format LP_ompi.cpp:622-630, 836-844) and the final Data/U_*.dc checkpoint
+// (raw doubles, LP_ompi.cpp:896).  `Second = True` restarts from the last U in Data/<Second/Name>
+// (LP_ompi.cpp:529-571).  Out-of-scope options (Doping, TwoHump, FullandLinear, LinearLandau,
+// MassConsOnly, gamma != -3) stop with an error, as the reference does for bad input (exit(1)).
+//
+// usage: lpsolver [input-file] [--device k] [--quiet]
+#include "../../include/lpgpu.h"
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+namespace {
+
+struct Deck {
+  std::map<std::string, std::string> kv;
+  bool load(const std::string &path)
+  {
+    std::ifstream in(path);
+    if (!in.good()) return false;
+    std::string line, section;
+    while (std::getline(in, line)) {
+      bool quoted = false;
+      size_t cut = std::string::npos;
+      for (size_t i = 0; i < line.size(); i++) {
+        if (line[i] == '\'' || line[i] == '"') quoted = !quoted;
+        if (line[i] == '#' && !quoted) { cut = i; break; }
+      }
+      if (cut != std::string::npos) line.erase(cut);
+      auto trim = [](std::string s) {
+        size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+        return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+      };
+      line = trim(line);
+      if (line.empty()) continue;
+      if (line[0] == '[') { section = trim(line.substr(1, line.find(']') - 1)); continue; }
+      size_t eq = line.find('=');
+      if (eq == std::string::npos) continue;
+      std::string k = trim(line.substr(0, eq)), v = trim(line.substr(eq + 1));
+      if (v.size() >= 2 && (v[0] == '\'' || v[0] == '"') && v.back() == v[0]) v = v.substr(1, v.size() - 2);
+      kv[section.empty() ? k : section + "/" + k] = v;
+    }
+    return true;
+  }
+  bool has(const std::string &k) const { return kv.count(k) != 0; }
+  std::string str(const std::string &k, const std::string &d = "") const { auto it = kv.find(k); return it == kv.end() ? d : it->second; }
+  double num(const std::string &k, double d) const { return has(k) ? atof(kv.at(k).c_str()) : d; }
+  int integer(const std::string &k, int d) const { return has(k) ? atoi(kv.at(k).c_str()) : d; }
+  bool flag(const std::string &k) const
+  {
+    std::string s = str(k, "false");
+    for (auto &c : s) c = (char)tolower(c);
+    return s == "true" || s == "1" || s == "yes";
+  }
+};
+
+[[noreturn]] void die(const std::string &msg)
+{
+  fprintf(stderr, "Program cannot run... %s\n", msg.c_str());
+  exit(1);
+}
+
+// 5-point Gauss-Legendre rule of the reference's projections (advection_1.cpp:12-13)
+const double GW[5] = {0.5688888888888889, 0.4786286704993665, 0.4786286704993665, 0.2369268850561891, 0.2369268850561891};
+const double GT[5] = {0., -0.5384693101056831, 0.5384693101056831, -0.9061798459386640, 0.9061798459386640};
+
+struct Grid { int Nx, Nv; double Lv, Lx, dv, dx; };
+double vcentre(const Grid &g, double m) { return -g.Lv + (m + 0.5) * g.dv; }
+double xcentre(const Grid &g, double m) { return (m + 0.5) * g.dx; }
+double maxwell3(double a, double b, double c, double T) { return exp(-(a * a + b * b + c * c) / (2 * T)) / (2 * M_PI * T * sqrt(2 * T * M_PI)); }
+double twogauss(double a, double b, double c)
+{
+  const double s = M_PI / 10;
+  return 0.5 * (exp(-((a - 2 * s) * (a - 2 * s) + b * b + c * c) / (2 * s * s)) + exp(-((a + 2 * s) * (a + 2 * s) + b * b + c * c) / (2 * s * s)))
+         / (2 * M_PI * s * s * sqrt(2 * M_PI * s * s));
+}
+// moments of a velocity profile over DG cell (j1,j2,j3) against {1, xi1, xi2, xi3, |xi|^2}
+void cell_moments(const Grid &g, bool two, const double sh[3], int j1, int j2, int j3, double t[5])
+{
+  for (int l = 0; l < 5; l++) t[l] = 0.;
+  for (int a = 0; a < 5; a++) for (int b = 0; b < 5; b++) for (int c = 0; c < 5; c++) {
+    const double v1 = vcentre(g, j1) + 0.5 * g.dv * GT[a] + sh[0], v2 = vcentre(g, j2) + 0.5 * g.dv * GT[b] + sh[1],
+                 v3 = vcentre(g, j3) + 0.5 * g.dv * GT[c] + sh[2];
+    const double w = GW[a] * GW[b] * GW[c] * (two ? twogauss(v1, v2, v3) : maxwell3(v1, v2, v3, 0.4));
+    t[0] += w; t[1] += w * 0.5 * GT[a]; t[2] += w * 0.5 * GT[b]; t[3] += w * 0.5 * GT[c];
+    t[4] += w * 0.25 * (GT[a] * GT[a] + GT[b] * GT[b] + GT[c] * GT[c]);
+  }
+  for (int l = 0; l < 5; l++) t[l] *= 0.125;
+}
+// SetInit_LD (SetInit_1.cpp:68-123): Damping (Maxwellian) or TwoStream (two Gaussians) times 1 + A cos(kx)
+void ic_perturbed(const Grid &g, bool two, double A, double kw, std::vector<double> &U)
+{
+  const double zero[3] = {0, 0, 0};
+  const int sv = g.Nv * g.Nv * g.Nv;
+  for (int j1 = 0; j1 < g.Nv; j1++) for (int j2 = 0; j2 < g.Nv; j2++) for (int j3 = 0; j3 < g.Nv; j3++) {
+    double t[5]; cell_moments(g, two, zero, j1, j2, j3, t);
+    for (int i = 0; i < g.Nx; i++) {
+      double *u = &U[6 * ((size_t)i * sv + (j1 * g.Nv + j2) * g.Nv + j3)];
+      const double xp = xcentre(g, i + 0.5), xm = xcentre(g, i - 0.5);
+      const double xf = g.dx + (sin(kw * xp) - sin(kw * xm)) * A / kw, tp0 = xf * t[0] / g.dx, tp5 = xf * t[4] / g.dx;
+      u[0] = 19 * tp0 / 4. - 15 * tp5;
+      u[5] = 60 * tp5 - 15 * tp0;
+      u[1] = (0.5 * (sin(kw * xp) + sin(kw * xm)) + (cos(kw * xp) - cos(kw * xm)) / (kw * g.dx)) * (A / kw) * t[0] * 12. / g.dx;
+      u[2] = xf * t[1] * 12 / g.dx; u[3] = xf * t[2] * 12 / g.dx; u[4] = xf * t[3] * 12 / g.dx;
+    }
+  }
+}
+// SetInit_4H (SetInit_1.cpp:175-258) and SetInit_4H_Homo (:261-325)
+void ic_four_hump(const Grid &g, bool homogeneous, std::vector<double> &U)
+{
+  const int sv = g.Nv * g.Nv * g.Nv, ncell = homogeneous ? 1 : g.Nx;
+  std::fill(U.begin(), U.end(), 0.);
+  const double C = homogeneous ? 0.02 : 1.;
+  for (int p = 0; p < 4; p++) {
+    const double sa = C * pow(-1, p), sb = C * pow(-1, p / 2);
+    const double sh[3] = {homogeneous ? sb : sa, sa, sa};
+    for (int j1 = 0; j1 < g.Nv; j1++) for (int j2 = 0; j2 < g.Nv; j2++) for (int j3 = 0; j3 < g.Nv; j3++) {
+      double t[5]; cell_moments(g, false, sh, j1, j2, j3, t);
+      for (int i = 0; i < ncell; i++) {
+        double x0 = 1., x1 = 0.;
+        if (!homogeneous) {
+          x0 = 0.;
+          for (int m = 0; m < 5; m++) {
+            const double x = xcentre(g, i) + 0.5 * g.dx * GT[m] - g.Lx / 2 + sb, w = GW[m] * exp(-x * x / 0.8) / sqrt(0.8 * M_PI);
+            x0 += w; x1 += w * 0.5 * GT[m];
+          }
+          x0 *= 0.5; x1 *= 0.5;
+        }
+        double *u = &U[6 * ((size_t)i * sv + (j1 * g.Nv + j2) * g.Nv + j3)];
+        const double tp0 = x0 * t[0], tp5 = x0 * t[4];
+        u[0] += 19 * tp0 / 4. - 15 * tp5; u[5] += 60 * tp5 - 15 * tp0;
+        u[1] += x1 * t[0] * 12; u[2] += x0 * t[1] * 12; u[3] += x0 * t[2] * 12; u[4] += x0 * t[3] * 12;
+      }
+    }
+  }
+  for (auto &v : U) v /= 4;
+}
+
+void make_parent_dir(const std::string &path)
+{
+  for (size_t pos = path.find('/'); pos != std::string::npos; pos = path.find('/', pos + 1))
+    if (pos > 0) mkdir(path.substr(0, pos).c_str(), 0755);
+}
+#define CHECK(call)                                                                          \
+  do { int rc_ = (call); if (rc_ != LPGPU_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, lpgpu_last_error()); exit(1); } } while (0)
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+  std::string input = "./LPsolver-input.txt";
+  int device = 0; bool quiet = false;
+  for (int a = 1; a < argc; a++) {
+    if (!strcmp(argv[a], "--device") && a + 1 < argc) device = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "--quiet")) quiet = true;
+    else input = argv[a];
+  }
+  Deck d;
+  if (!d.load(input)) die("The file " + input + " cannot be found. Please create an appropriate input file before running again.");
+
+  const char *ics[] = {"Damping", "TwoStream", "FourHump", "TwoHump", "Doping"};
+  std::string ic; int nic = 0;
+  for (const char *n : ics) if (d.flag(n)) { ic = n; nic++; }
+  if (nic == 0) die("No initial condition has been chosen.");
+  if (nic > 1) die("Please ONLY set ONE of Damping, TwoStream, FourHump or TwoHump to true.");
+  if (d.flag("First") == d.flag("Second")) die("Need to choose if this is a first run or a subsequent one (First / Second).");
+  for (const char *n : {"FullandLinear", "LinearLandau", "MassConsOnly"})
+    if (d.flag(n)) die(std::string(n) + " is not part of the GPU hot path.");
+  if (ic == "Doping" || ic == "TwoHump") die(ic + " initial/boundary conditions are not part of the GPU hot path.");
+  if (!d.has("flag")) die("Please set the name of 'flag' in the input file.");
+  for (const char *n : {"nT", "Nx", "Nv", "N", "nu", "dt"}) if (!d.has(n)) die(std::string("Please set ") + n + " in the input file.");
+
+  lpgpu_params p;
+  memset(&p, 0, sizeof(p));
+  const int nT = d.integer("nT", 0);
+  p.Nx = d.integer("Nx", 0); p.Nv = d.integer("Nv", 0); p.N = d.integer("N", 0);
+  p.nu = d.num("nu", 0.); p.dt = d.num("dt", 0.); p.gamma = d.integer("gamma", -3);
+  p.homogeneous = d.flag("Homogeneous");
+  if (!d.has(ic + "/Lv")) die("Please set " + ic + "/Lv in the input file.");
+  p.Lv = d.num(ic + "/Lv", 0.);
+  double A_amp = d.num(ic + "/A_amp", 0.), k_wave = d.num(ic + "/k_wave", 0.5);
+  if (ic == "TwoStream") { if (!d.has("TwoStream/Lx")) die("Please set TwoStream/Lx."); p.Lx = d.num("TwoStream/Lx", 0.); k_wave = 2 * M_PI / 4.; }
+  else p.Lx = d.num(ic + "/Lx", 2 * M_PI / k_wave);
+  if (p.homogeneous && ic != "FourHump") die("Trying to run the space homogeneous code, but current IC is not available (only FourHump).");
+  p.x_begin = 0; p.x_count = p.homogeneous ? 1 : p.Nx; p.device = device; p.computeq_variant = 0;
+
+  char name[512], tail[400];
+  const std::string flag = d.str("flag");
+  if (p.homogeneous) snprintf(tail, sizeof tail, "nu%gA%gk%gNv%dLv%gSpectralN%ddt%gnT%d_%s.dc", p.nu, A_amp, k_wave, p.Nv, p.Lv, p.N, p.dt, nT, flag.c_str());
+  else snprintf(tail, sizeof tail, "nu%gA%gk%gNx%dLx%gNv%dLv%gSpectralN%ddt%gnT%d_%s.dc", p.nu, A_amp, k_wave, p.Nx, p.Lx, p.Nv, p.Lv, p.N, p.dt, nT, flag.c_str());
+  snprintf(name, sizeof name, "Data/Moments_%s", tail);
+  const std::string fmom_name = name;
+  snprintf(name, sizeof name, "Data/U_%s", tail);
+  const std::string fu_name = name;
+
+  const int sv = p.Nv * p.Nv * p.Nv, ncell = p.x_count;
+  std::vector<double> U((size_t)6 * sv * ncell);
+  Grid g = {p.Nx, p.Nv, p.Lv, p.Lx, 2. * p.Lv / p.Nv, p.homogeneous ? 1. : p.Lx / p.Nx};
+  if (d.flag("Second")) {
+    if (!d.has("Second/Name")) die("Please set the name of the file from the previous run under Second/Name.");
+    FILE *f = fopen(("Data/" + d.str("Second/Name")).c_str(), "rb");
+    if (!f) die("cannot open Data/" + d.str("Second/Name"));
+    fseek(f, 0, SEEK_END);
+    const long bytes = ftell(f), need = (long)(U.size() * sizeof(double));
+    if (bytes < need || bytes % need != 0) die("Error reading file (size does not match 6*size doubles)");
+    fseek(f, bytes - need, SEEK_SET);
+    if (fread(U.data(), sizeof(double), U.size(), f) != U.size()) die("Error reading file");
+    fclose(f);
+  } else if (ic == "FourHump") ic_four_hump(g, p.homogeneous, U);
+  else ic_perturbed(g, ic == "TwoStream", A_amp, k_wave, U);
+
+  lpgpu_ctx *ctx = nullptr;
+  CHECK(lpgpu_init(&p, &ctx));
+  CHECK(lpgpu_upload_U(ctx, U.data()));
+  make_parent_dir(fmom_name);
+  FILE *fmom = fopen(fmom_name.c_str(), "w");
+  if (!fmom) die("cannot open " + fmom_name);
+
+  auto diagnostics = [&](int step) {
+    double m5[5], ele = 0.;
+    std::vector<double> ms((size_t)2 * ncell);
+    CHECK(lpgpu_moments_partial(ctx, m5, ms.data()));
+    if (!p.homogeneous) CHECK(lpgpu_eleE_from_ms(&p, ms.data(), &ele));
+    if (p.homogeneous) {
+      if (!quiet) printf("step %d: %11.8g  %11.8g  %11.8g  %11.8g  %11.8g \n", step, m5[0], m5[1], m5[2], m5[3], m5[4]);
+      fprintf(fmom, "%11.8g %11.8g %11.8g %11.8g %11.8g %11.8g %11.8g %11.8g \n", m5[0], m5[1], m5[2], m5[3], 0.0, 0.0, 0.0, m5[4]);
+    } else {
+      const double t = sqrt(ele);
+      if (!quiet) printf("step %d: %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g %11.8g \n", step, m5[0], m5[1], m5[2], m5[3], m5[4], ele, t, log(t), m5[4] + ele);
+      fprintf(fmom, "%11.8g %11.8g %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g \n", m5[0], m5[1], m5[2], m5[3], m5[4], ele, t, log(t), m5[4] + ele);
+    }
+  };
+  diagnostics(0);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int t = 0; t < nT; t++) {
+    CHECK(lpgpu_step(ctx, 1));
+    diagnostics(t + 1);
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("\nTime duration for %d time steps is %gs\n\n", nT, secs);
+  fclose(fmom);
+  CHECK(lpgpu_download_U(ctx, U.data()));
+  FILE *fu = fopen(fu_name.c_str(), "wb");
+  if (fu) { fwrite(U.data(), sizeof(double), U.size(), fu); fclose(fu); }
+  CHECK(lpgpu_finalize(ctx));
+  return 0;
+}

@@ -1,0 +1,37 @@
+"""Run under torchrun: the x-sharded solver (NCCL exchange) must reproduce the single-GPU solver
+bit for bit.  Prints MGPU_OK on rank 0."""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as graft
+graft.load_package()
+from lpsolver_b200 import solver
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cfg = dict(Nx=8 * world, Nv=8, N=8, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
+s = solver.ShardedSolver(rank=rank, world=world, device=local, dist=dist, **cfg)
+U0 = solver.set_init_ld(cfg["Nx"], cfg["Nv"], cfg["Lv"], cfg["Lx"], 0.5, np.pi / 2, True)
+n = U0.size // world
+s.upload(U0[rank * n:(rank + 1) * n])
+s.step(3)
+mine = torch.from_numpy(s.download()).cuda()
+allU = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(allU, mine)
+mom = s.moments()
+s.close()
+if rank == 0:
+    one = solver.ShardedSolver(device=local, **cfg)
+    one.upload(U0)
+    one.step(3)
+    want = one.download()
+    mom1 = one.moments()
+    one.close()
+    got = torch.cat(allU).cpu().numpy()
+    same = np.array_equal(got, want)
+    print("max |diff| = %.3e, moments diff = %.3e" % (np.max(np.abs(got - want)), np.max(np.abs(mom - mom1))))
+    print("MGPU_OK" if same and np.allclose(mom, mom1, rtol=1e-13, atol=1e-15) else "MGPU_FAIL")
+dist.destroy_process_group()

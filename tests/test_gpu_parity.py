@@ -297,3 +297,31 @@ def test_against_committed_reference_vectors(pkg):
     assert relerr(got, z["Uh_collide"]) < TOL_U and relerr(got - z["Uh0"], z["Uh_collide"] - z["Uh0"]) < TOL_DU
     assert relerr(gh.moments()[:5], z["moments_h"][:5]) < 1e-10 or np.allclose(gh.moments()[:5], z["moments_h"][:5], rtol=1e-10, atol=1e-12)
     gh.close()
+
+
+@pytest.mark.parametrize("case,homog", [("test0", False), ("test4", True)])
+def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
+    """The reference's own end-to-end test (tests/LPsolver_tests + moment_differ.sh): run the driver in a
+    directory holding LPsolver-input.txt and compare row 6 of the Moments file it writes with the golden."""
+    import json, os, shutil, subprocess
+    here = os.path.dirname(__file__)
+    exe = os.path.join(os.path.dirname(here), "landau-poisson-solver_b200", "host", "lpsolver")
+    if not os.path.exists(exe):
+        pytest.skip("host driver not built")
+    shutil.copy(os.path.join(here, "golden", "LPsolver-input-%s.txt" % case), tmp_path / "LPsolver-input.txt")
+    out = subprocess.run([exe, "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    name = {"test0": "Data/Moments_nu0.05A0.2k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test0.dc",
+            "test4": "Data/Moments_nu0.05A0k0.5Nv16Lv5.25SpectralN8dt0.01nT5_Test4.dc"}[case]
+    rows = [[float(x) for x in line.split()] for line in open(tmp_path / name) if line.strip()]
+    gold = json.load(open(os.path.join(here, "golden", "reference_moments.json")))["Moments_T%s.dc" % case[1:]]
+    assert len(rows) == 6
+    r, g = rows[5], gold[5]
+    assert abs(r[0] - g[0]) <= 2e-6                                      # moment_differ.sh:9,30
+    assert all(abs(r[d] - g[d]) <= 1e-10 for d in (1, 2, 3))              # :10-12
+    last = len(g) - 1
+    assert r[last] - g[last] <= 3e-5 and g[last] - r[last] <= 1e-7        # :13,83 (golden holds 8 digits)
+    for row, grow in zip(rows, gold):                                     # every printed digit of the non-noise columns
+        for col in ([0, 4, 5, 6, 7, 8] if not homog else [0, 7]):
+            assert abs(row[col] - grow[col]) <= 1.5e-7 * max(1.0, abs(grow[col])), (row, grow, col)
+    assert os.path.exists(tmp_path / name.replace("Moments_", "U_"))
