@@ -77,8 +77,13 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_upload(&c->d_G, t.G));
   A_(dev_upload(&c->d_C5, t.C5));
   { std::vector<double> cct(t.CCt, t.CCt + 25); A_(dev_upload(&c->d_CCt, cct)); }
-  A_(dev_upload(&c->d_Ffwd, t.Ffwd));
-  A_(dev_upload(&c->d_Finv, t.Finv));
+  A_(dev_upload(&c->d_Wfwd, t.Wfwd));
+  A_(dev_upload(&c->d_Winv, t.Winv));
+  A_(dev_upload(&c->d_pre_fwd, t.pre_fwd));
+  A_(dev_upload(&c->d_pre_inv, t.pre_inv));
+  A_(dev_upload(&c->d_post_fwd, t.post_fwd));
+  A_(dev_upload(&c->d_post_inv, t.post_inv));
+  A_(dev_upload(&c->d_wt, t.wt));
   A_(dev_upload(&c->d_T, t.T));
   A_(dev_upload(&c->d_M, t.M));
   A_(dev_upload(&c->d_S, t.S));
@@ -119,7 +124,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   if (!c) return LPGPU_OK;
   cudaSetDevice(c->p.device);
   cudaDeviceSynchronize();
-  double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Ffwd, c->d_Finv, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
+  double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
                     c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart};
   for (double *q : ptrs) if (q) cudaFree(q);

@@ -82,11 +82,13 @@ int lp_launch_sample(lpgpu_ctx *c, const double *planes, double *f, int ncell)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shifted transforms.  fft3D (collisionRoutines_1.cpp:285-319) and FS (:363-398) are separable:
-// per dimension  fhat(eta_k) = sum_j Ffwd[k][j] f(v_j)  and  Q(v_j) = sum_k Finv[j][k] Qhat(eta_k)
-// with the N x N complex matrices built in tables.cpp (pre-phase * DFT * post-phase folded).
-// N <= 32, so each 1-D transform is a dense N-point sum out of shared memory; the two kernels
-// below cover axes (1,2) of one x-slab and axis 0 of one y-slab.
+// Shifted transforms: fft3D (collisionRoutines_1.cpp:285-319) and FS (:363-398).  Both are
+//   pre-phase (by s = i+j+k)  ->  unnormalised 3-D DFT (sign -1 / +1)  ->  post-phase (by (i,j,k))
+// with the phase factors tabulated on the host from the reference's own double expressions
+// (tables.cpp) and applied here with un-fused multiplies/subtractions, so the reference's rounding of
+// the phases is reproduced; only the DFT itself (dense N-point sums out of shared memory, N <= 32, vs
+// FFTW's butterflies) differs, at the 1e-16 level.  k_dft_jk covers axes (1,2) of one x-slab,
+// k_dft_i axis 0 of one y-slab.  fft3D = jk (pre) then i (post); FS = i (pre) then jk (post + epilogue).
 //
 // EPI: 0 complex out; 1..3 = FS real part + RK stage update (RK4_Inhomo/RK4_Homo,
 // collisionRoutines_1.cpp:910-941 / 1094-1123); 4 = FS real part stored as (re, 0).
@@ -96,20 +98,36 @@ struct FsEpilogue {
   double *Qv;        // first-stage Q (written in mode 1, read in 2,3)
   double *f1;        // stage input for the next ComputeQ
 };
+struct PhaseTabs {
+  const double2 *pre;    // [3N-2]  pre-phase by i+j+k            (null: none)
+  const double2 *post;   // [N^3]   post-phase by (i,j,k)         (null: none)
+  const double *wt;      // [N]     trapezoid weights, forward pre-factor only (null: none)
+  double c3;             // scale3*h_v^3 (forward pre-factor)
+};
+// (c + i s) * (x + i y) exactly as the reference writes it: cos*re - sin*im, cos*im + sin*re
+__device__ __forceinline__ double2 phase_mul(double2 cs, double2 x)
+{
+  return make_double2(__dsub_rn(__dmul_rn(cs.x, x.x), __dmul_rn(cs.y, x.y)), __dadd_rn(__dmul_rn(cs.x, x.y), __dmul_rn(cs.y, x.x)));
+}
 
-template <bool IN_REAL, int EPI>
+template <bool IN_REAL, int EPI, bool PRE, bool POST>
 __global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, double *__restrict__ out,
-                                                 const double2 *__restrict__ Fm, int N, FsEpilogue ep)
+                                                 const double2 *__restrict__ Wm, int N, PhaseTabs ph, FsEpilogue ep)
 {
   extern __shared__ double2 sm2[];
   const int P = N + 1;
   double2 *X = sm2, *Y = X + N * P, *F = Y + N * P;
   const long long slab = blockIdx.x;                 // cell*N + i
+  const int i = (int)(slab % N);
   const int tid = threadIdx.x, r = tid / N, cc = tid % N;
   const long long g = slab * N * N + tid;
-  if (IN_REAL) X[r * P + cc] = make_double2(in[g], 0.);
-  else X[r * P + cc] = reinterpret_cast<const double2 *>(in)[g];
-  F[r * P + cc] = Fm[tid];
+  double2 x = IN_REAL ? make_double2(in[g], 0.) : reinterpret_cast<const double2 *>(in)[g];
+  if (PRE) {
+    x = phase_mul(ph.pre[i + r + cc], x);
+    if (ph.wt) { const double fac = ph.c3 * ph.wt[i] * ph.wt[r] * ph.wt[cc]; x.x = __dmul_rn(fac, x.x); x.y = __dmul_rn(fac, x.y); }
+  }
+  X[r * P + cc] = x;
+  F[r * P + cc] = Wm[tid];
   __syncthreads();
   double2 acc = make_double2(0., 0.);
   for (int j = 0; j < N; j++) cfma(acc, F[cc * P + j], X[r * P + j]);   // axis 2
@@ -117,6 +135,7 @@ __global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, 
   __syncthreads();
   acc = make_double2(0., 0.);
   for (int j = 0; j < N; j++) cfma(acc, F[r * P + j], Y[j * P + cc]);   // axis 1
+  if (POST) acc = phase_mul(ph.post[(i * N + r) * N + cc], acc);
   if (EPI == 0) {
     reinterpret_cast<double2 *>(out)[g] = acc;
   } else {
@@ -129,8 +148,9 @@ __global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, 
 }
 
 // axis 0: block = (cell, j); slab X[i][k] = in[cell][i][j][k]
+template <bool PRE, bool POST>
 __global__ void __launch_bounds__(1024) k_dft_i(const double2 *__restrict__ in, double2 *__restrict__ out,
-                                                const double2 *__restrict__ Fm, int N)
+                                                const double2 *__restrict__ Wm, int N, PhaseTabs ph)
 {
   extern __shared__ double2 sm2[];
   const int P = N + 1;
@@ -138,33 +158,39 @@ __global__ void __launch_bounds__(1024) k_dft_i(const double2 *__restrict__ in, 
   const long long cell = blockIdx.x / N; const int j = blockIdx.x % N;
   const int tid = threadIdx.x, i = tid / N, k = tid % N;
   const long long g = ((cell * N + i) * N + j) * N + k;
-  X[i * P + k] = in[g];
-  F[i * P + k] = Fm[tid];
+  double2 x = in[g];
+  if (PRE) x = phase_mul(ph.pre[i + j + k], x);
+  X[i * P + k] = x;
+  F[i * P + k] = Wm[tid];
   __syncthreads();
   double2 acc = make_double2(0., 0.);
   for (int a = 0; a < N; a++) cfma(acc, F[i * P + a], X[a * P + k]);
+  if (POST) acc = phase_mul(ph.post[(i * N + j) * N + k], acc);
   out[g] = acc;
 }
 
 static size_t dft_smem(int N, int arrays) { return (size_t)arrays * N * (N + 1) * sizeof(double2); }
 
-template <bool IN_REAL, int EPI>
-static int launch_jk(lpgpu_ctx *c, const double *in, double *out, const double *Fm, int B, FsEpilogue ep)
+template <bool IN_REAL, int EPI, bool PRE, bool POST>
+static int launch_jk(lpgpu_ctx *c, const double *in, double *out, const double *Wm, int B, PhaseTabs ph, FsEpilogue ep)
 {
   const int N = c->p.N;
   const size_t smem = dft_smem(N, 3);
-  LP_CUDA(cudaFuncSetAttribute(k_dft_jk<IN_REAL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dft_jk<IN_REAL, EPI><<<B * N, N * N, smem, c->stream>>>(in, out, reinterpret_cast<const double2 *>(Fm), N, ep);
+  auto kern = k_dft_jk<IN_REAL, EPI, PRE, POST>;
+  LP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B * N, N * N, smem, c->stream>>>(in, out, reinterpret_cast<const double2 *>(Wm), N, ph, ep);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
-static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *Fm, int B)
+template <bool PRE, bool POST>
+static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *Wm, int B, PhaseTabs ph)
 {
   const int N = c->p.N;
   const size_t smem = dft_smem(N, 2);
-  LP_CUDA(cudaFuncSetAttribute(k_dft_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dft_i<<<B * N, N * N, smem, c->stream>>>(reinterpret_cast<const double2 *>(in), reinterpret_cast<double2 *>(out),
-                                              reinterpret_cast<const double2 *>(Fm), N);
+  auto kern = k_dft_i<PRE, POST>;
+  LP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B * N, N * N, smem, c->stream>>>(reinterpret_cast<const double2 *>(in), reinterpret_cast<double2 *>(out),
+                                          reinterpret_cast<const double2 *>(Wm), N, ph);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -172,9 +198,12 @@ static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *F
 int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, int B)
 {
   FsEpilogue ep = {};
-  int rc = in_real ? launch_jk<true, 0>(c, in, c->d_tmp, c->d_Ffwd, B, ep) : launch_jk<false, 0>(c, in, c->d_tmp, c->d_Ffwd, B, ep);
+  PhaseTabs pre = {reinterpret_cast<const double2 *>(c->d_pre_fwd), nullptr, c->d_wt, c->tab.c3_fwd};
+  PhaseTabs post = {nullptr, reinterpret_cast<const double2 *>(c->d_post_fwd), nullptr, 0.};
+  int rc = in_real ? launch_jk<true, 0, true, false>(c, in, c->d_tmp, c->d_Wfwd, B, pre, ep)
+                   : launch_jk<false, 0, true, false>(c, in, c->d_tmp, c->d_Wfwd, B, pre, ep);
   if (rc) return rc;
-  return launch_i(c, c->d_tmp, out, c->d_Ffwd, B);
+  return launch_i<false, true>(c, c->d_tmp, out, c->d_Wfwd, B, post);
 }
 
 int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B)
@@ -182,13 +211,15 @@ int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, i
   FsEpilogue ep;
   ep.scaleL = c->tab.scaleL; ep.scale3 = c->tab.scale3;
   ep.dt = c->p.dt; ep.nu = c->p.nu; ep.f = c->d_f; ep.Qv = c->d_Qv; ep.f1 = c->d_f1;
-  int rc = launch_i(c, q, c->d_tmp, c->d_Finv, B);
+  PhaseTabs pre = {reinterpret_cast<const double2 *>(c->d_pre_inv), nullptr, nullptr, 0.};
+  PhaseTabs post = {nullptr, reinterpret_cast<const double2 *>(c->d_post_inv), nullptr, 0.};
+  int rc = launch_i<true, false>(c, q, c->d_tmp, c->d_Winv, B, pre);
   if (rc) return rc;
   switch (mode) {
-    case 0: return launch_jk<false, 4>(c, c->d_tmp, out_complex, c->d_Finv, B, ep);
-    case 1: return launch_jk<false, 1>(c, c->d_tmp, nullptr, c->d_Finv, B, ep);
-    case 2: return launch_jk<false, 2>(c, c->d_tmp, nullptr, c->d_Finv, B, ep);
-    case 3: return launch_jk<false, 3>(c, c->d_tmp, nullptr, c->d_Finv, B, ep);
+    case 0: return launch_jk<false, 4, false, true>(c, c->d_tmp, out_complex, c->d_Winv, B, post, ep);
+    case 1: return launch_jk<false, 1, false, true>(c, c->d_tmp, nullptr, c->d_Winv, B, post, ep);
+    case 2: return launch_jk<false, 2, false, true>(c, c->d_tmp, nullptr, c->d_Winv, B, post, ep);
+    case 3: return launch_jk<false, 3, false, true>(c, c->d_tmp, nullptr, c->d_Winv, B, post, ep);
   }
   lp_set_error("lp_launch_fs: bad mode");
   return LPGPU_EINVAL;

@@ -15,7 +15,10 @@ struct LpTables {
   std::vector<double> G;                   // 7*N^3  folded kernel symbols, [w*7 + t]
   std::vector<double> C5;                  // 5*N^3  conservation rows, [q*5 + m] (interleaved)
   double CCt[25];                          // (C C^T)^-1
-  std::vector<double> Ffwd, Finv;          // N*N complex: forward / inverse 1-D transform matrices
+  std::vector<double> Wfwd, Winv;          // N*N complex: DFT twiddle matrices exp(-/+ 2 pi i jk/N)
+  std::vector<double> pre_fwd, pre_inv;    // (3N-2) complex: pre-phases by s = i+j+k
+  std::vector<double> post_fwd, post_inv;  // N^3 complex: post-phases
+  double c3_fwd;                           // scale3*h_v^3
   std::vector<double> T, M, S;             // N*Nv complex: 1-D IntModes factors [k*Nv + j]
   std::vector<int> node_cell;              // N
   std::vector<double> node_xi;             // N
@@ -33,7 +36,7 @@ struct lpgpu_ctx {
   // ---- device tables
   double *d_Etab, *d_qpart;
   size_t cap_part;         // capacity of d_qpart in spectra (cells x l-splits)
-  double *d_eta, *d_G, *d_C5, *d_CCt, *d_Ffwd, *d_Finv, *d_T, *d_M, *d_S, *d_node_xi, *d_vc;
+  double *d_eta, *d_G, *d_C5, *d_CCt, *d_Wfwd, *d_Winv, *d_pre_fwd, *d_pre_inv, *d_post_fwd, *d_post_inv, *d_wt, *d_T, *d_M, *d_S, *d_node_xi, *d_vc;
   int *d_node_cell;
   // ---- DG state, plane-major: buf[((p*6 + c)*sv + j)], p = 0..ncell+1 (planes 0 and ncell+1 are x halos)
   double *d_U[3];

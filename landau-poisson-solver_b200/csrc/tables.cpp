@@ -128,22 +128,40 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
     }
   invert_in_place(t.CCt, 5);
 
-  // ---- 1-D transform matrices.  fft3D == (2 pi)^(-1/2) h_v wt_j exp(-i v_j eta_k) per dimension,
-  // FS == exp(+i v_j eta_k) per dimension (pre-phase * DFT twiddle * post-phase of
-  // collisionRoutines_1.cpp:291-317 and :370-396, with the twiddle index reduced mod N).
-  t.Ffwd.resize((size_t)2 * N * N); t.Finv.resize((size_t)2 * N * N);
-  const long double s1d = 1.0L / sqrtl(2.0L * M_PIl) * (long double)t.h_v;
+  // ---- shifted transforms (collisionRoutines_1.cpp:285-319 fft3D, :363-398 FS).  The reference multiplies
+  // by a pre-phase, runs an unnormalised DFT and multiplies by a post-phase; its phase angles are rounded
+  // in double ((i+j+k)*L_eta*h_v reaches ~290 rad, so the factors carry ~3e-14 relative error).  For
+  // near-equilibrium data Qhat is the ~1e-4 remainder of cancelling terms, so those roundings are visible
+  // at 1e-10 in Qhat.  To match the reference the same double expressions are tabulated here and applied
+  // element-wise; the DFT matrices are pure twiddles exp(-/+ 2 pi i (jk mod N)/N), correctly rounded.
+  t.Wfwd.resize((size_t)2 * N * N); t.Winv.resize((size_t)2 * N * N);
   for (int k = 0; k < N; k++)
     for (int j = 0; j < N; j++) {
       const long double tw = 2.0L * M_PIl * (long double)((j * k) % N) / (long double)N;
-      const long double af = (long double)j * (long double)t.L_eta * (long double)t.h_v - tw + (long double)p.Lv * (long double)t.eta[k];
-      t.Ffwd[2 * ((size_t)k * N + j)] = (double)(s1d * (long double)t.wt[j] * cosl(af));
-      t.Ffwd[2 * ((size_t)k * N + j) + 1] = (double)(s1d * (long double)t.wt[j] * sinl(af));
-      // inverse: row = velocity node j, column = Fourier node k
-      const long double ai = -(long double)k * (long double)p.Lv * (long double)t.h_eta + tw - (long double)t.L_eta * (long double)t.v[j];
-      t.Finv[2 * ((size_t)j * N + k)] = (double)cosl(ai);
-      t.Finv[2 * ((size_t)j * N + k) + 1] = (double)sinl(ai);
+      t.Wfwd[2 * ((size_t)k * N + j)] = (double)cosl(tw);
+      t.Wfwd[2 * ((size_t)k * N + j) + 1] = (double)(-sinl(tw));
+      t.Winv[2 * ((size_t)k * N + j)] = (double)cosl(tw);
+      t.Winv[2 * ((size_t)k * N + j) + 1] = (double)sinl(tw);
     }
+  const int NS = 3 * N - 2;
+  t.pre_fwd.resize((size_t)2 * NS); t.pre_inv.resize((size_t)2 * NS);
+  for (int sidx = 0; sidx < NS; sidx++) {
+    const double sf = (double)sidx * t.L_eta * t.h_v;          // ((double)i+(double)j+(double)k)*L_eta*h_v
+    const double si = -((double)sidx * p.Lv * t.h_eta);        // -(((double)i+...)*L_v*h_eta)
+    t.pre_fwd[2 * sidx] = std::cos(sf); t.pre_fwd[2 * sidx + 1] = std::sin(sf);
+    t.pre_inv[2 * sidx] = std::cos(si); t.pre_inv[2 * sidx + 1] = std::sin(si);
+  }
+  t.post_fwd.resize((size_t)2 * N3); t.post_inv.resize((size_t)2 * N3);
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++)
+      for (int k = 0; k < N; k++) {
+        const size_t q = k + (size_t)N * (j + (size_t)N * i);
+        const double sf = p.Lv * (t.eta[i] + t.eta[j] + t.eta[k]);
+        const double si = -(t.L_eta * (t.v[i] + t.v[j] + t.v[k]));
+        t.post_fwd[2 * q] = std::cos(sf); t.post_fwd[2 * q + 1] = std::sin(sf);
+        t.post_inv[2 * q] = std::cos(si); t.post_inv[2 * q + 1] = std::sin(si);
+      }
+  t.c3_fwd = t.scale3 * t.h_v * t.h_v * t.h_v;                 // scale3*h_v*h_v*h_v, left to right as in :301
 
   // ---- IntModes 1-D factors: T = int_cell e^{i eta v}, M = int e^{i eta v}(v-c)/dv, S = int e^{i eta v}((v-c)/dv)^2
   t.T.resize((size_t)2 * N * Nv); t.M.resize((size_t)2 * N * Nv); t.S.resize((size_t)2 * N * Nv);

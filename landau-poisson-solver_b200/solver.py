@@ -235,10 +235,12 @@ def exchange_stage(dist, rank, world, ms_local, ms_all, send_left, send_right, r
     else:
         dist.all_gather(list(ms_all.chunk(world)), ms_local)
     left, right = (rank - 1) % world, (rank + 1) % world
-    # order matters when left == right (world == 2): first send pairs with first recv on the peer
-    reqs = [dist.isend(send_right, right), dist.isend(send_left, left),
-            dist.irecv(recv_left, left), dist.irecv(recv_right, right)]
-    for r in reqs:
+    # One grouped launch (ncclGroupStart/End): separately issued NCCL sends would deadlock, each rank's
+    # send waiting for a receive queued behind the peer's own send.  Order matters when left == right
+    # (world == 2): the first send to a peer pairs with the first receive from it on the other side.
+    ops = [dist.P2POp(dist.isend, send_right, right), dist.P2POp(dist.isend, send_left, left),
+           dist.P2POp(dist.irecv, recv_left, left), dist.P2POp(dist.irecv, recv_right, right)]
+    for r in dist.batch_isend_irecv(ops):
         r.wait()
 
 

@@ -17,5 +17,5 @@ def test_sharded_solver_matches_single_gpu(world):
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "scripts", "mgpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
