@@ -124,6 +124,12 @@ int lpgpu_fp64_peak(int device, double *tflops);
  * MomentCalculations.cpp:23-131); sum over shards for the global value.  ms_local_host (may be
  * NULL) receives the 2*x_count (m_i, s_i) pairs needed by lpgpu_eleE_from_ms. */
 int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host);
+/* The remaining per-step diagnostics of the reference's rank 0 (LP_ompi.cpp:819,829,846), partial over
+ * this shard: out4 = entropy (computeEntropy, EntropyCalculations.cpp:23-122), sum of the KiE terms over
+ * cells with non-negative average, the same over cells with negative average (computeKiEratio =
+ * out4[2]/out4[1] after summing over shards, MomentCalculations.cpp:133-199), number of cells FindNegVals
+ * flags (NegativityChecks.cpp:24-160). */
+int lpgpu_diagnostics_partial(lpgpu_ctx *c, double *out4);
 /* computeEleE (MomentCalculations.cpp:201-230) from the gathered per-cell sums; host-only. */
 int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms_all, double *EleE);
 

@@ -256,6 +256,69 @@ __global__ void k_moments_fold(const double *__restrict__ part, double *__restri
   out[1] = v[1] * xs * dv * dv; out[2] = v[2] * xs * dv * dv; out[3] = v[3] * xs * dv * dv;
   out[4] = 0.5 * v[4] * xs * dv * dv;
 }
+// ---------------------------------------------------------------------------------------------
+// The other per-step diagnostics of the reference's rank 0 (LP_ompi.cpp:819,829,846):
+// computeEntropy (EntropyCalculations.cpp:23-122: 5^4-point Gauss rule of f log f per DG cell, 5^3 when
+// homogeneous), FindNegVals (NegativityChecks.cpp:24-160: sign of the cell average by the same rule) and
+// computeKiEratio (MomentCalculations.cpp:133-199).  One thread per DG cell; per-cell-block partials
+// are folded in order.  out4 = entropy (scaled), KiE terms over non-negative cells, over negative cells,
+// number of negative cells.
+__constant__ double c_gw[5] = {0.5688888888888889, 0.4786286704993665, 0.4786286704993665, 0.2369268850561891, 0.2369268850561891};
+__constant__ double c_gt[5] = {0., -0.5384693101056831, 0.5384693101056831, -0.9061798459386640, 0.9061798459386640};
+__global__ void __launch_bounds__(256) k_diag_cell(const double *__restrict__ planes, double *__restrict__ part, int Nv, int sv,
+                                                   double dv, double Lv, int homogeneous)
+{
+  __shared__ double red[4 * 32];
+  const long long cell = blockIdx.x;
+  const double *u = planes + ((cell + 1) * 6) * (long long)sv;
+  double v[4] = {0., 0., 0., 0.};
+  const int nxq = homogeneous ? 1 : 5;
+  const int per = (sv + gridDim.y - 1) / gridDim.y, jlo = blockIdx.y * per, jhi = min(sv, jlo + per);
+  for (int j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
+    const double U0 = u[j], U1 = u[1LL * sv + j], U2 = u[2LL * sv + j], U3 = u[3LL * sv + j], U4 = u[4LL * sv + j], U5 = u[5LL * sv + j];
+    double e = 0., avg = 0.;
+    for (int a = 0; a < nxq; a++)
+      for (int b = 0; b < 5; b++)
+        for (int cc = 0; cc < 5; cc++)
+          #pragma unroll
+          for (int d = 0; d < 5; d++) {
+            const double xs = homogeneous ? 0. : 0.5 * c_gt[a], x1 = 0.5 * c_gt[b], x2 = 0.5 * c_gt[cc], x3 = 0.5 * c_gt[d];
+            const double f = U0 + (homogeneous ? 0. : U1 * xs) + U2 * x1 + U3 * x2 + U4 * x3 + U5 * (x1 * x1 + x2 * x2 + x3 * x3);
+            const double w = (homogeneous ? 1. : c_gw[a]) * c_gw[b] * c_gw[cc] * c_gw[d];
+            if (f > 0) e += w * f * log(f);
+            avg += w * f;
+          }
+    const int j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
+    const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv, c3 = -Lv + (j3 + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
+    const double ke = U0 * (r2 + dv * dv / 4.) * dv + (c1 * U2 + c2 * U3 + c3 * U4) * dv * dv / 6. + U5 * (dv * dv * dv * 19. / 240. + r2 * dv / 4.);
+    v[0] += e;
+    if (avg < 0) { v[2] += ke; v[3] += 1.; } else v[1] += ke;
+  }
+  block_sum<4>(v, red);
+  if (threadIdx.x == 0)
+    for (int m = 0; m < 4; m++) part[4 * (cell * gridDim.y + blockIdx.y) + m] = v[m];
+}
+__global__ void k_diag_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double scale)
+{
+  if (threadIdx.x != 0) return;
+  double v[4] = {0., 0., 0., 0.};
+  for (int c = 0; c < ncell; c++)
+    for (int m = 0; m < 4; m++) v[m] += part[4 * c + m];
+  out[0] = v[0] * scale; out[1] = v[1]; out[2] = v[2]; out[3] = v[3];
+}
+int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev)
+{
+  double *part = c->d_B;   // free outside the projection
+  const int chunks = 16;   // blocks per x cell
+  k_diag_cell<<<dim3(c->ncell, chunks), 256, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv, c->p.homogeneous);
+  LP_LAUNCHED(c);
+  const double dv = c->tab.dv, dx = c->p.Lx / c->p.Nx;
+  const double scale = 0.5 * dv * 0.5 * dv * 0.5 * dv * (c->p.homogeneous ? 1. : 0.5 * dx);
+  k_diag_fold<<<1, 32, 0, c->stream>>>(part, out4_dev, c->ncell * chunks, scale);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
 int lp_launch_moments(lpgpu_ctx *c, const double *planes)
 {
   // d_B is free outside the projection: use its head for the per-cell partials

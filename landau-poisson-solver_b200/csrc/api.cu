@@ -111,7 +111,7 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_alloc(&c->d_fhat, 2 * n3));
   A_(dev_alloc(&c->d_tmp, 2 * n3));
   for (int s = 0; s < 4; s++) A_(dev_alloc(&c->d_q[s], 2 * n3));
-  A_(dev_alloc(&c->d_lam, (size_t)5 * c->cap_cells));
+  A_(dev_alloc(&c->d_lam, (size_t)5 * 8 * c->cap_cells + 8));   // conservation partials: 8 chunks x 5 per cell
   A_(dev_alloc(&c->d_B, (size_t)2 * c->cap_cells * p->N * 4 * p->Nv * p->Nv));
 #undef A_
   if (rc != LPGPU_OK) { lpgpu_finalize(c); return rc; }
@@ -398,6 +398,16 @@ int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host)
     LP_TRY(lp_launch_field_reduce(c, c->d_U[0]));
     LP_CUDA(cudaMemcpyAsync(ms_local_host, c->d_ms_local, (size_t)2 * c->ncell * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+int lpgpu_diagnostics_partial(lpgpu_ctx *c, double *out4)
+{
+  LP_ENTER(c);
+  if (!out4) return LPGPU_EINVAL;
+  LP_TRY(lp_launch_diagnostics(c, c->d_U[0], c->d_lam));
+  LP_CUDA(cudaMemcpyAsync(out4, c->d_lam, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   LP_CUDA(cudaStreamSynchronize(c->stream));
   return LPGPU_OK;
 }

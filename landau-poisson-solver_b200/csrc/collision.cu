@@ -321,9 +321,64 @@ __global__ void __launch_bounds__(512) k_conserve(double2 *__restrict__ q, const
     qc[idx] = v;
   }
 }
+// Two-kernel form for large spectra: CH blocks per cell compute partial dot products, then CH blocks per
+// cell fold them (fixed order), apply CCt and correct their slice.  One block per cell leaves 116 of 148
+// SMs idle when a GPU holds 32 cells.
+#define LP_CONS_CH 8
+__global__ void __launch_bounds__(256) k_conserve_dots(const double2 *__restrict__ q, const double *__restrict__ C5,
+                                                       double *__restrict__ part, int N3)
+{
+  __shared__ double red[5][8];
+  const long long cell = blockIdx.x; const int ch = blockIdx.y;
+  const double2 *qc = q + cell * N3;
+  const int per = (N3 + LP_CONS_CH - 1) / LP_CONS_CH, lo = ch * per, hi = min(N3, lo + per);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double s[5] = {0., 0., 0., 0., 0.};
+  for (int idx = lo + tid; idx < hi; idx += blockDim.x) {
+    const double2 v = qc[idx];
+    s[0] += v.x * C5[idx]; s[1] += v.y * C5[N3 + idx]; s[2] += v.y * C5[2 * N3 + idx];
+    s[3] += v.y * C5[3 * N3 + idx]; s[4] += v.x * C5[4 * N3 + idx];
+  }
+  #pragma unroll
+  for (int m = 0; m < 5; m++) {
+    double v = s[m];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[m][wid] = v;
+  }
+  __syncthreads();
+  if (tid < 5) { double v = 0.; for (int w = 0; w < 8; w++) v += red[tid][w]; part[(cell * LP_CONS_CH + ch) * 5 + tid] = v; }
+}
+__global__ void __launch_bounds__(256) k_conserve_apply(double2 *__restrict__ q, const double *__restrict__ C5,
+                                                        const double *__restrict__ CCt, const double *__restrict__ part, int N3)
+{
+  __shared__ double lam[5];
+  const long long cell = blockIdx.x; const int ch = blockIdx.y;
+  if (threadIdx.x == 0) {
+    double tot[5];
+    for (int m = 0; m < 5; m++) { double v = 0.; for (int k = 0; k < LP_CONS_CH; k++) v += part[(cell * LP_CONS_CH + k) * 5 + m]; tot[m] = v; }
+    for (int a = 0; a < 5; a++) { double v = 0.; for (int b = 0; b < 5; b++) v += CCt[b + a * 5] * tot[b]; lam[a] = v; }
+  }
+  __syncthreads();
+  const double b0 = lam[0], b1 = lam[1], b2 = lam[2], b3 = lam[3], b4 = lam[4];
+  double2 *qc = q + cell * N3;
+  const int per = (N3 + LP_CONS_CH - 1) / LP_CONS_CH, lo = ch * per, hi = min(N3, lo + per);
+  for (int idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
+    double2 v = qc[idx];
+    v.x -= (C5[idx] * b0 + C5[4 * N3 + idx] * b4);
+    v.y -= (C5[N3 + idx] * b1 + C5[2 * N3 + idx] * b2 + C5[3 * N3 + idx] * b3);
+    qc[idx] = v;
+  }
+}
 int lp_launch_conserve(lpgpu_ctx *c, double *q, int B)
 {
-  k_conserve<<<B, 512, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->N3);
+  if (c->N3 < 4096) {
+    k_conserve<<<B, 512, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->N3);
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
+  k_conserve_dots<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(q), c->d_C5, c->d_lam, c->N3);
+  LP_LAUNCHED(c);
+  k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->d_lam, c->N3);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }

@@ -2,7 +2,7 @@
 // `solver` binary (LP_ompi.cpp:76-952) for the in-scope physics: it reads ./LPsolver-input.txt in the
 // reference's GRVY syntax, sets the initial condition on the host (SetInit_1.cpp:68-325), runs the
 // time loop with every hot-path call going to the GPU, and writes Data/Moments_*.dc (one row per step,
-// row 1 = initial state; format LP_ompi.cpp:622-630, 836-844) and the final Data/U_*.dc checkpoint
+// row 1 = initial state; format LP_ompi.cpp:622-630, 836-844), Data/EntropyVals_*.dc (:632, :846) and the final Data/U_*.dc checkpoint
 // (raw doubles, LP_ompi.cpp:896).  `Second = True` restarts from the last U in Data/<Second/Name>
 // (LP_ompi.cpp:529-571).  Out-of-scope options (Doping, TwoHump, FullandLinear, LinearLandau,
 // MassConsOnly, gamma != -3) stop with an error, as the reference does for bad input (exit(1)).
@@ -202,6 +202,8 @@ int main(int argc, char **argv)
   const std::string fmom_name = name;
   snprintf(name, sizeof name, "Data/U_%s", tail);
   const std::string fu_name = name;
+  snprintf(name, sizeof name, "Data/EntropyVals_%s", tail);
+  const std::string fent_name = name;
 
   const int sv = p.Nv * p.Nv * p.Nv, ncell = p.x_count;
   std::vector<double> U((size_t)6 * sv * ncell);
@@ -225,12 +227,19 @@ int main(int argc, char **argv)
   make_parent_dir(fmom_name);
   FILE *fmom = fopen(fmom_name.c_str(), "w");
   if (!fmom) die("cannot open " + fmom_name);
+  FILE *fent = fopen(fent_name.c_str(), "w");
+  if (!fent) die("cannot open " + fent_name);
 
   auto diagnostics = [&](int step) {
     double m5[5], ele = 0.;
     std::vector<double> ms((size_t)2 * ncell);
     CHECK(lpgpu_moments_partial(ctx, m5, ms.data()));
     if (!p.homogeneous) CHECK(lpgpu_eleE_from_ms(&p, ms.data(), &ele));
+    double d4[4];                                   // entropy, KiE over positive / negative cells, #negative cells
+    CHECK(lpgpu_diagnostics_partial(ctx, d4));
+    const double ent = d4[0], lent = log(fabs(ent));
+    fprintf(fent, "%11.8g %11.8g %11.8g \n", ent, lent, log(fabs(lent)));   // LP_ompi.cpp:632, 846
+    if (!quiet) printf("entropy = %11.8g, Kinetic Energy Ratio = %g\n", ent, d4[2] / d4[1]);
     if (p.homogeneous) {
       if (!quiet) printf("step %d: %11.8g  %11.8g  %11.8g  %11.8g  %11.8g \n", step, m5[0], m5[1], m5[2], m5[3], m5[4]);
       fprintf(fmom, "%11.8g %11.8g %11.8g %11.8g %11.8g %11.8g %11.8g %11.8g \n", m5[0], m5[1], m5[2], m5[3], 0.0, 0.0, 0.0, m5[4]);
@@ -249,6 +258,7 @@ int main(int argc, char **argv)
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("\nTime duration for %d time steps is %gs\n\n", nT, secs);
   fclose(fmom);
+  fclose(fent);
   CHECK(lpgpu_download_U(ctx, U.data()));
   FILE *fu = fopen(fu_name.c_str(), "wb");
   if (fu) { fwrite(U.data(), sizeof(double), U.size(), fu); fclose(fu); }

@@ -42,7 +42,7 @@ EXPORTS = [
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
-    "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak",
+    "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak", "lpgpu_diagnostics_partial",
 ]
 
 _lib = None
@@ -65,7 +65,7 @@ def load_library():
     for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_sample_device"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.lpgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
-    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field"):
+    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
     for name in ("lpgpu_step", "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_eval_device"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_int]
@@ -244,6 +244,12 @@ class LPGpu:
         v = C.c_double()
         self._check(self.L.lpgpu_eleE_from_ms(C.byref(self.params), _ptr(ms_all), C.byref(v)))
         return v.value
+
+    def diagnostics_partial(self):
+        """entropy, KiE sum over non-negative cells, over negative cells, number of negative cells (this shard)."""
+        out = np.empty(4)
+        self._check(self.L.lpgpu_diagnostics_partial(self.h, _ptr(out)))
+        return out
 
     def moments(self):
         """mass, P1, P2, P3, KiE, EleE for a single-shard context."""

@@ -834,6 +834,37 @@ void lpo_moments(const lpo_ctx *c, const double *U, double *out)
   }
 }
 
+/* Per-step diagnostics the reference runs on rank 0: computeEntropy_Inhomo/_Homo
+ * (EntropyCalculations.cpp:23-77 / 79-122), FindNegVals (NegativityChecks.cpp:24-160, cell averages by
+ * the same Gauss rule) and computeKiEratio (MomentCalculations.cpp:133-199).
+ * out4 = entropy, sum of KiE terms over cells with f_avg >= 0, over cells with f_avg < 0, number of
+ * negative cells. */
+void lpo_diagnostics(const lpo_ctx *c, const double *U, double *out4)
+{
+  const int Nv = c->Nv, sv = c->size_v, nxq = c->homogeneous ? 1 : 5;
+  const double dv = c->dv;
+  const size_t n = (size_t)c->ncell * sv;
+  double ent = 0., kpos = 0., kneg = 0., nneg = 0.;
+  for (size_t k = 0; k < n; k++) {
+    const double *u = U + 6 * k;
+    int j = (int)(k % sv), j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
+    double e = 0., avg = 0.;
+    for (int a = 0; a < nxq; a++) for (int b = 0; b < 5; b++) for (int cc = 0; cc < 5; cc++) for (int d = 0; d < 5; d++) {
+      double xs = c->homogeneous ? 0. : 0.5 * GT[a], x1 = 0.5 * GT[b], x2 = 0.5 * GT[cc], x3 = 0.5 * GT[d];
+      double f = u[0] + (c->homogeneous ? 0. : u[1] * xs) + u[2] * x1 + u[3] * x2 + u[4] * x3 + u[5] * (x1 * x1 + x2 * x2 + x3 * x3);
+      double w = (c->homogeneous ? 1. : GW[a]) * GW[b] * GW[cc] * GW[d];
+      if (f > 0) e += w * f * log(f);
+      avg += w * f;
+    }
+    ent += e;
+    double c1 = gridv(c, (double)j1), c2 = gridv(c, (double)j2), c3 = gridv(c, (double)j3), r2 = c1 * c1 + c2 * c2 + c3 * c3;
+    double ke = u[0] * (r2 + dv * dv / 4.) * dv + (c1 * u[2] + c2 * u[3] + c3 * u[4]) * dv * dv / 6. + u[5] * (dv * dv * dv * 19. / 240. + r2 * dv / 4.);
+    if (avg < 0) { kneg += ke; nneg += 1.; } else kpos += ke;
+  }
+  out4[0] = ent * 0.5 * dv * 0.5 * dv * 0.5 * dv * (c->homogeneous ? 1. : 0.5 * c->dx);
+  out4[1] = kpos; out4[2] = kneg; out4[3] = nneg;
+}
+
 /* one pass of the while(t<nT) body without diagnostics: LP_ompi.cpp:662-813 */
 void lpo_step(const lpo_ctx *c, double *U)
 {

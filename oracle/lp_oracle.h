@@ -55,6 +55,7 @@ void lpo_SetInit_LD(const lpo_ctx *c, double *U, double A_amp, double k_wave, in
 void lpo_SetInit_4H(const lpo_ctx *c, double *U);
 void lpo_SetInit_4H_Homo(const lpo_ctx *c, double *U);
 void lpo_moments(const lpo_ctx *c, const double *U, double *out6);
+void lpo_diagnostics(const lpo_ctx *c, const double *U, double *out4);
 
 /* whole time step (advection then collision), LP_ompi.cpp:662-813 */
 void lpo_step(const lpo_ctx *c, double *U);

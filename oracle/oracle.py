@@ -187,6 +187,12 @@ class PortOracle:
         self._call("lpo_moments", _f64(U), out)
         return out
 
+    def diagnostics(self, U):
+        """entropy, KiE ratio (negative / positive cells), number of negative cells"""
+        out = np.empty(4)
+        self._call("lpo_diagnostics", _f64(U), out)
+        return np.array([out[0], out[2] / out[1], out[3]])
+
 
 class RefOracle:
     """The unmodified reference (global state: one live configuration per process)."""
@@ -303,3 +309,8 @@ class RefOracle:
         U = _f64(U); out = np.empty(6)
         self.L.ref_moments(self._p(U), self._p(out))
         return out
+
+    def diagnostics(self, U):
+        U = _f64(U); out = np.empty(4)
+        self.L.ref_diagnostics(self._p(U), self._p(out))
+        return out[:3].copy()

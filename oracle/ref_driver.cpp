@@ -200,5 +200,16 @@ void ref_moments(const double *U_in, double *out)
   out[5] = Homogeneous ? 0. : computeEleE(U);
 }
 double ref_entropy(const double *U) { return computeEntropy((double *)U); }
+/* out4 = entropy, KiEneg/KiEpos ratio, number of negative cells, 0 -- LP_ompi.cpp:819,829,846 */
+void ref_diagnostics(const double *U_in, double *out4)
+{
+  double *U = (double *)U_in;
+  FindNegVals(U, fNegVals, fAvgVals);
+  out4[0] = computeEntropy(U);
+  out4[1] = computeKiEratio(U, fNegVals);
+  double n = 0.;
+  for (int k = 0; k < size; k++) n += fNegVals[k];
+  out4[2] = n; out4[3] = 0.;
+}
 int ref_num_threads(void) { return omp_get_max_threads(); }
 }

@@ -156,6 +156,28 @@ def test_full_step_small(small):
     assert np.all(np.abs(mg[1:4] - mo[1:4]) <= 1e-10)     # momentum: absolute, as moment_differ.sh does
 
 
+def test_entropy_and_negativity_diagnostics(small, pkg):
+    """computeEntropy / FindNegVals / computeKiEratio (LP_ompi.cpp:819,829,846) on the GPU."""
+    ora, g = small
+    for seed, amp in ((1, 0.05), (2, 0.6)):                # the second input has negative cell averages
+        U = ora.SetInit_LD(0.2, 0.5)
+        rng = np.random.default_rng(seed)
+        U = U * (1 + amp * rng.standard_normal(U.shape)) - (2e-4 if amp > 0.1 else 0.)
+        g.upload_U(U)
+        d = g.diagnostics_partial()
+        want = ora.diagnostics(U)
+        assert abs(d[0] - want[0]) <= 1e-12 * abs(want[0])
+        assert abs(d[2] / d[1] - want[1]) <= 1e-12 * max(1.0, abs(want[1]))
+        assert d[3] == want[2]
+    gh = pkg.LPGpu(homogeneous=True, **TEST0)
+    oh = PortOracle(homogeneous=True, **TEST0)
+    Uh = oh.SetInit_4H_Homo()
+    gh.upload_U(Uh)
+    d, want = gh.diagnostics_partial(), oh.diagnostics(Uh)
+    assert abs(d[0] - want[0]) <= 1e-12 * abs(want[0]) and d[3] == want[2]
+    gh.close()
+
+
 def test_two_stream_step(pkg):
     cfg = dict(Nx=8, Nv=8, N=8, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
     ora = PortOracle(**cfg)
