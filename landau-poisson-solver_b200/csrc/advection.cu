@@ -49,9 +49,41 @@ __global__ void __launch_bounds__(256) k_field_reduce(const double *__restrict__
   block_sum<2>(v, red);
   if (threadIdx.x == 0) { ms[2 * cell] = v[0] * scalev; ms[2 * cell + 1] = v[1] * scalev; }
 }
+// large velocity grids: LP_FR_CH blocks per x cell (one block per cell would use ncell of 148 SMs), partials
+// folded in a fixed order
+#define LP_FR_CH 8
+__global__ void __launch_bounds__(256) k_field_reduce_part(const double *__restrict__ planes, double *__restrict__ part, int sv)
+{
+  __shared__ double red[2 * 32];
+  const long long cell = blockIdx.x;
+  const double *u = planes + ((cell + 1) * 6) * (long long)sv;
+  const int per = (sv + LP_FR_CH - 1) / LP_FR_CH, lo = blockIdx.y * per, hi = min(sv, lo + per);
+  double v[2] = {0., 0.};
+  for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    v[0] += u[j] + u[5LL * sv + j] / 4.;
+    v[1] += u[1LL * sv + j];
+  }
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0) { part[2 * (cell * LP_FR_CH + blockIdx.y)] = v[0]; part[2 * (cell * LP_FR_CH + blockIdx.y) + 1] = v[1]; }
+}
+__global__ void k_field_reduce_fold(const double *__restrict__ part, double *__restrict__ ms, int ncell, double scalev)
+{
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncell) return;
+  double a = 0., b = 0.;
+  for (int k = 0; k < LP_FR_CH; k++) { a += part[2 * (cell * LP_FR_CH + k)]; b += part[2 * (cell * LP_FR_CH + k) + 1]; }
+  ms[2 * cell] = a * scalev; ms[2 * cell + 1] = b * scalev;
+}
 int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes)
 {
-  k_field_reduce<<<c->ncell, 256, 0, c->stream>>>(planes, c->d_ms_local, c->sv, c->tab.scalev);
+  if (c->sv < 8192) {
+    k_field_reduce<<<c->ncell, 256, 0, c->stream>>>(planes, c->d_ms_local, c->sv, c->tab.scalev);
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
+  k_field_reduce_part<<<dim3(c->ncell, LP_FR_CH), 256, 0, c->stream>>>(planes, c->d_ms_part, c->sv);
+  LP_LAUNCHED(c);
+  k_field_reduce_fold<<<(c->ncell + 127) / 128, 128, 0, c->stream>>>(c->d_ms_part, c->d_ms_local, c->ncell, c->tab.scalev);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }

@@ -42,6 +42,7 @@ struct lpgpu_ctx {
   double *d_U[3];
   double *d_aos;           // staging for AoS <-> plane-major (ncell*sv*6)
   // ---- field
+  double *d_ms_part;       // per-cell partial density sums (2 * 8 chunks * ncell)
   double *d_ms_local, *d_ms_all, *d_fld;   // 2*ncell, 2*Nx, 1 + 4*ncell (ce | cp,iE,iE1,iE2 interleaved by 4)
   double *d_mom;           // 5 partial moments
   // ---- collision work arrays (ncell cells each)
