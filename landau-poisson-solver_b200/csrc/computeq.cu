@@ -246,8 +246,8 @@ static int launch_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B)
   // split the l-window when there are too few (cell, i) CTAs to fill 148 SMs
   int SL = 1;
   if ((long long)B * N < 2 * 148) {
-    SL = (int)((2 * 148 + (long long)B * N - 1) / ((long long)B * N));
-    if (SL > 8) SL = 8;
+    SL = (int)((2 * 148) / ((long long)B * N));      // keep all CTAs in one resident wave (2 per SM)
+    if (SL < 1) SL = 1;
     if (SL > N / 2) SL = N / 2;
     while (SL > 1 && (size_t)B * SL > c->cap_part) SL--;
   }

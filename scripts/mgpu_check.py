@@ -1,5 +1,5 @@
 """Run under torchrun: the x-sharded solver (NCCL exchange) must reproduce the single-GPU solver
-bit for bit.  Prints MGPU_OK on rank 0."""
+(to round-off: 1e-12 of the update).  Prints MGPU_OK on rank 0."""
 import os, sys
 import numpy as np
 import torch
@@ -31,7 +31,10 @@ if rank == 0:
     mom1 = one.moments()
     one.close()
     got = torch.cat(allU).cpu().numpy()
-    same = np.array_equal(got, want)
-    print("max |diff| = %.3e, moments diff = %.3e" % (np.max(np.abs(got - want)), np.max(np.abs(mom - mom1))))
-    print("MGPU_OK" if same and np.allclose(mom, mom1, rtol=1e-13, atol=1e-15) else "MGPU_FAIL")
+    # not bit-identical on purpose: ComputeQ splits the omega_1 window by the number of cells per launch
+    # (8 per GPU here, 16 on one GPU), which reorders its sums; advection alone is bit-identical (see
+    # tests/test_gpu_parity.py::test_sharded_advection_matches_single)
+    err = np.max(np.abs((got - U0) - (want - U0))) / np.max(np.abs(want - U0))
+    print("rel err of the 3-step update = %.3e, moments diff = %.3e" % (err, np.max(np.abs(mom - mom1))))
+    print("MGPU_OK" if err < 1e-12 and np.allclose(mom, mom1, rtol=1e-13, atol=1e-15) else "MGPU_FAIL")
 dist.destroy_process_group()
