@@ -269,6 +269,9 @@ static int launch_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B)
 // returns -1 when N has no tiled instantiation (caller falls back to the simple kernel)
 int lp_launch_computeQ_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B)
 {
+  // developer knob for tile-shape experiments (not part of the ABI): LPGPU_CQ_SHAPE=1 -> 512-thread CTAs
+  static const int shape = getenv("LPGPU_CQ_SHAPE") ? atoi(getenv("LPGPU_CQ_SHAPE")) : 0;
+  if (c->p.N == 32 && shape == 1) return launch_tiled<32, 4, 16, 2, 4, 1>(c, fhat, q, B);
   switch (c->p.N) {
     case 32: return launch_tiled<32, 4, 16, 2, 2, 2>(c, fhat, q, B);
     case 24: return launch_tiled<24, 3, 4, 8, 1, 1>(c, fhat, q, B);
