@@ -217,32 +217,70 @@ def main():
     e2e = {"value": 4. * Nx * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 8 * world),
            "d2h_bytes_per_step": int(back.numel() * 8 * world), "steps": e2e_steps, "timesteps_per_s": e2e_steps / t_e2e}
 
-    # ---- roofline of the dominant kernel (ComputeQ, FP64-pipe bound) ----------------------------
-    roof = None
+    # ---- roofline of the dominant kernels --------------------------------------------------------
+    # (1) the step's ComputeQ = seven zero-padded FFT convolutions (k_fc_fwd_yz + k_fc_x + k_fc_inv_yz, timed
+    #     together by the library's events).  Bound: HBM.  Algorithmic bytes of this formulation per cell:
+    #     fhat in + 14 transformed y-z plane sets written and read once + the x-reduced array written and read
+    #     once + Qhat out.
+    # (2) the north star's direct O(N^6) sum (k_computeQ_tiled, computeq_variant = 3), timed here on the same
+    #     cells outside the step: FP64-pipe bound, 10 flop per (xi, omega) pair.
+    roof = roof_direct = None
+    fp64_peak = pkg.lpgpu.fp64_peak_tflops(local)
+    peaks = {}
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        peaks = json.load(open(ppath))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s fallback of B200_PROFILING.md (of fallback)"
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "computeq_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
     if cq_n > 0:
+        Mpad = 2 * NSPEC
+        bytes_per_cell = 16 * (NSPEC ** 3 + 2 * 14 * NSPEC * Mpad * Mpad + 2 * NSPEC * Mpad * Mpad + NSPEC ** 3)
         avg_s = cq_ms * 1e-3 / cq_n
-        achieved = flop_per_eval(NSPEC) * s.x_count / avg_s / 1e12
-        peak = pkg.lpgpu.fp64_peak_tflops(local)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "computeq_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        roof = {"bound": "fp64", "kernel": "k_computeQ_tiled", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "avg_launch_ms": avg_s * 1e3, "launches": cq_n,
-                "share_of_step": cq_ms * 1e-3 / t_dev,
-                "peak_source": "DFMA micro-benchmark run live on this GPU (lpgpu_fp64_peak); MEASURED_PEAKS.json holds only HBM and bf16 peaks; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
-                "algorithmic_flop_per_launch": flop_per_eval(NSPEC) * s.x_count}
+        achieved = bytes_per_cell * s.x_count / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": "ComputeQ as FFT convolutions: k_fc_fwd_yz + k_fc_x + k_fc_inv_yz", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic.get("fftconv_dram_bytes_per_launch"),
+                "avg_launch_ms": avg_s * 1e3, "launches": cq_n, "share_of_step": cq_ms * 1e-3 / t_dev, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": bytes_per_cell * s.x_count,
+                "direct_form_equivalent_tflops": flop_per_eval(NSPEC) * s.x_count / avg_s / 1e12,
+                "note": "direct_form_equivalent_tflops counts the 10 flop/pair of the O(N^6) sum this kernel replaces; it exceeds the FP64 peak because the FFT form executes ~13x fewer flops for the same result (parity-tested)"}
+    try:
+        d = pkg.LPGpu(Nx, NV, NSPEC, homogeneous=False, x_begin=s.x_begin, x_count=s.x_count, device=local, computeq_variant=3, **PHYS)
+        d.set_stream(torch.cuda.current_stream().cuda_stream)
+        d.upload_U(host_np)
+        d.sample_device()
+        for _ in range(2):
+            d.eval_device(s.x_count)
+        d.profile_computeQ(True)
+        for _ in range(4):
+            d.eval_device(s.x_count)
+        dq_ms, dq_n = d.profile_read()
+        d.close()
+        avg_d = dq_ms * 1e-3 / dq_n
+        ach = flop_per_eval(NSPEC) * s.x_count / avg_d / 1e12
+        roof_direct = {"bound": "fp64", "kernel": "k_computeQ_tiled (computeq_variant=3, the reference's O(N^6) form)", "achieved": ach,
+                       "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic.get("dram_bytes_per_launch"),
+                       "avg_launch_ms": avg_d * 1e3, "launches": dq_n, "evals_per_s": s.x_count / avg_d,
+                       "peak_source": "DFMA micro-benchmark run live on this GPU (lpgpu_fp64_peak); MEASURED_PEAKS.json holds only HBM and bf16 peaks; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
+                       "algorithmic_flop_per_launch": flop_per_eval(NSPEC) * s.x_count}
+    except Exception as e:
+        roof_direct = {"error": repr(e)}
 
     line = None
     if rank == 0:
-        ws_mb = (3 * (s.x_count + 2) * 6 * NV ** 3 * 8 + s.x_count * NSPEC ** 3 * 8 * (3 + 2 * 6) + s.x_count * NSPEC * 4 * NV * NV * 16) / 2 ** 20
+        ws_mb = (3 * (s.x_count + 2) * 6 * NV ** 3 * 8 + s.x_count * NSPEC ** 3 * 8 * (3 + 2 * 6) + s.x_count * NSPEC * 4 * NV * NV * 16
+                 + s.x_count * 15 * NSPEC * (2 * NSPEC) ** 2 * 16) / 2 ** 20
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "two-stream Landau-Poisson timestep (SSP-RK3 DG advection + RK4 spectral Landau collision), %d x-cells per GPU, Nv=%d, N=%d (BASELINE config Nx=256,Nv=32^3 on 8 GPUs, per-GPU shard)" % (CELLS_PER_GPU, NV, NSPEC),
                            "Nx": Nx, "Nv": NV, "N": NSPEC, "evals_per_step": 4 * Nx, "parallelism": "x-cells sharded over %d GPU(s)" % world,
                            "l2": "per-GPU working set %.0f MB > 126 MB L2; no flush between steps" % ws_mb},
-                "timesteps_per_s": args.steps / t_dev, "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "timesteps_per_s": args.steps / t_dev, "roofline": roof, "roofline_direct": roof_direct, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks}
 
     # ---- BASELINE's single-cell homogeneous config, and the CPU baseline (N=1 only) --------------
     if world == 1:

@@ -39,7 +39,11 @@ typedef struct lpgpu_params {
   int homogeneous;  /* reference flag Homogeneous */
   int x_begin, x_count;
   int device;       /* CUDA device ordinal */
-  int computeq_variant; /* 0 = default (fastest validated), 1 = simple reference kernel */
+  int computeq_variant; /* which ComputeQ kernel evaluates the weighted spectral convolution (same result to round-off):
+                           0 = fastest validated: seven zero-padded FFT convolutions when N is a power of two,
+                               otherwise the register-tiled direct sum;
+                           1 = simple one-thread-per-xi direct kernel (on-device cross-check);
+                           2 = FFT convolutions; 3 = register-tiled direct sum (the O(N^6) form of the reference) */
 } lpgpu_params;
 
 const char *lpgpu_last_error(void);

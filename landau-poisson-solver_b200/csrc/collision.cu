@@ -267,9 +267,18 @@ __global__ void __launch_bounds__(128) k_computeQ_simple(const double2 *__restri
 
 int lp_launch_computeQ_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B);   // computeq.cu
 
+int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B);   // fftconv.cu
+
 int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B)
 {
-  if (c->p.computeq_variant != 1) {
+  // 0 = fastest validated path (FFT convolutions when N is a power of two, else the tiled direct sum),
+  // 1 = simple direct kernel, 2 = FFT convolutions, 3 = tiled direct sum
+  const int variant = c->p.computeq_variant;
+  if (variant == 0 || variant == 2) {
+    int rc = lp_launch_computeQ_fftconv(c, fhat, q, B);
+    if (rc != -1) return rc;   // -1: N is not a power of two -> direct kernels
+  }
+  if (variant != 1) {
     int rc = lp_launch_computeQ_tiled(c, fhat, q, B);
     if (rc != -1) return rc;   // -1: size not covered by the tiled kernel -> simple kernel
   }

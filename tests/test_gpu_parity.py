@@ -60,7 +60,7 @@ def test_fft3D_and_FS(pkg, N):
     g.close()
 
 
-@pytest.mark.parametrize("N,variant", [(8, 0), (8, 1), (16, 0), (16, 1)])
+@pytest.mark.parametrize("N,variant", [(8, 0), (8, 1), (8, 2), (8, 3), (16, 0), (16, 1), (16, 2), (16, 3), (24, 0), (24, 3)])
 def test_ComputeQ_and_conserve(pkg, N, variant):
     cfg = dict(TEST0, N=N, Nv=16)
     ora = PortOracle(homogeneous=True, **cfg)
@@ -178,6 +178,19 @@ def test_entropy_and_negativity_diagnostics(small, pkg):
     gh.close()
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_full_step_each_ComputeQ_variant(pkg, variant):
+    """Every ComputeQ kernel (simple direct, FFT convolutions, tiled direct) through a whole timestep."""
+    ora = PortOracle(**SMALL)
+    g = pkg.LPGpu(computeq_variant=variant, **SMALL)
+    U = _perturbed(ora, 7)
+    g.upload_U(U)
+    g.step(1)
+    want, got = ora.step(U), g.download_U()
+    g.close()
+    assert relerr(got, want) < TOL_U and relerr(got - U, want - U) < TOL_DU
+
+
 def test_two_stream_step(pkg):
     cfg = dict(Nx=8, Nv=8, N=8, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
     ora = PortOracle(**cfg)
@@ -225,9 +238,14 @@ def test_ComputeQ_checksums_full_size(pkg, N):
     g1 = pkg.LPGpu(homogeneous=True, computeq_variant=1, **cfg)
     q1 = g1.conserveMoments(g1.ComputeQ(f)[0])[0]
     g1.close()
-    # tiled kernel vs simple kernel on device.  At N=32 each output sums 13.8k products with heavy
+    # default kernel vs simple kernel on device.  At N=32 each output sums 13.8k products with heavy
     # cancellation (conserved |q| is ~1e-3 of the raw terms): two FP64 orderings differ by ~1e-12.
     assert relerr(q, q1) < (TOL_SPEC if N < 32 else 1e-11)
+    for variant in (2, 3):                                  # FFT convolutions (power-of-two N) and the tiled direct sum
+        g2 = pkg.LPGpu(homogeneous=True, computeq_variant=variant, **cfg)
+        q2 = g2.conserveMoments(g2.ComputeQ(f)[0])[0]
+        g2.close()
+        assert relerr(q2, q1) < (TOL_SPEC if N < 32 else 1e-11), variant
     s = float(np.sum(q[:, 0] ** 2))
     mid = q[(N // 2) * (N * N + N + 1), 0]
     assert abs(s - known[0]) <= 1e-9 * known[0]
