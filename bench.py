@@ -237,7 +237,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     if cq_n > 0:
-        Mpad = 2 * NSPEC
+        Mpad = 3 * NSPEC // 2                      # cyclic transform size per dimension (fftconv.cu)
         bytes_per_cell = 16 * (NSPEC ** 3 + 2 * 14 * NSPEC * Mpad * Mpad + 2 * NSPEC * Mpad * Mpad + NSPEC ** 3)
         avg_s = cq_ms * 1e-3 / cq_n
         achieved = bytes_per_cell * s.x_count / avg_s / 1e9
@@ -272,7 +272,7 @@ def main():
     line = None
     if rank == 0:
         ws_mb = (3 * (s.x_count + 2) * 6 * NV ** 3 * 8 + s.x_count * NSPEC ** 3 * 8 * (3 + 2 * 6) + s.x_count * NSPEC * 4 * NV * NV * 16
-                 + s.x_count * 15 * NSPEC * (2 * NSPEC) ** 2 * 16) / 2 ** 20
+                 + s.x_count * 15 * NSPEC * (3 * NSPEC // 2) ** 2 * 16) / 2 ** 20
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

@@ -1,18 +1,21 @@
-// ComputeQ as seven zero-padded linear convolutions (computeq_variant = 2) -- the O(N^3 log N) form of the
+// ComputeQ as seven zero-padded linear convolutions (computeq_variant 0/2) -- the O(N^3 log N) form of the
 // same sum (identity checked against the reference's table to 1.5e-16):
 //
 //   Wt(xi,omega) = G0(omega) - sum_{p=1..6} G_p(omega) mono_p(E(beta)),   beta = xi + N/2 - omega,
 //   mono = {e1^2, e2^2, e3^2, e1 e2, e1 e3, e2 e3},  e_a = E(beta_a) = eta[beta_a] - eta[N/2]
 //   => Qhat[xi] = sum_p ( u_p (*) v_p )[xi + N/2],   u_p = G_p fhat,  v_p = h_p(E) fhat   (linear convolution)
 //
-// computed with cyclic transforms of size M = 2N per dimension (no aliasing since M >= 2N-1):
-//   F1  per (cell, x, p): build the padded y-z plane of u_p / v_p, DIF-FFT along z (N non-zero rows) and y
-//   F2  per (cell, ky, 8 kz): DIF-FFT along x of the 14 lines, sum_p u_p v_p, inverse DIT along x, keep N outputs
-//   F3  per (cell, x'): inverse DIT along y and z, scale by M^-3, extract the N x N window
-// Forward transforms are decimation-in-frequency (natural in, bit-reversed out), inverse transforms are
-// decimation-in-time (bit-reversed in, natural out), so no permutation pass exists anywhere: products are
-// formed position-wise in bit-reversed order.  Radix-2 butterflies on shared-memory lines, correctly rounded
-// twiddles from the host.  Power-of-two N only (N = 8, 16, 32); other sizes use the tiled direct kernel.
+// computed with cyclic transforms of size M = 3N/2 per dimension.  The linear convolution lives on
+// [0, 2N-2]; only s = xi + N/2 in [N/2, 3N/2) is wanted, and with period M the indices that alias onto
+// that window would be s + M >= 2N (outside the support) -- so 1.5 N points suffice instead of 2N
+// (2.4x fewer points in 3-D).  M = 12, 24, 36, 48 for N = 8, 16, 24, 32: radix-2 and radix-3 stages.
+//   F1  per (cell, x, p): build the padded y-z plane of u_p / v_p, transform along z (N non-zero rows) and y
+//   F2  per (cell, ky, 8 kz): transform the 14 x-lines, sum_p u_p v_p, inverse transform along x, keep N outputs
+//   F3  per (cell, x'): inverse transform along y and z, scale by M^-3, extract the N x N window
+// Forward transforms are decimation-in-frequency (natural in, digit-reversed out), inverse transforms are
+// the conjugate-transposed stages in reverse order (digit-reversed in, natural out), so no permutation pass
+// exists anywhere: products are formed position-wise.  Butterflies run on shared-memory lines with
+// correctly rounded twiddles from the host.  Sizes whose M has another prime factor use the tiled direct kernel.
 #include "lpgpu_internal.h"
 
 #define LP_LAUNCHED(c)                                  \
@@ -23,65 +26,117 @@
 
 namespace {
 
+struct FcPlan { int M, nst, radix[8]; };
+
 __device__ __forceinline__ double2 cxmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cxmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a * conj(b)
+__device__ __forceinline__ double2 cxadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cxsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+#define LP_SQRT3_2 0.86602540378443864676
 
-// one DIF (forward) butterfly: span h, butterfly index b in [0, M/2); element i of the line is x[i*st]
-__device__ __forceinline__ void dif_bfly(double2 *x, int st, int M, int h, int b, const double2 *tw)
+// One forward (DIF) butterfly of radix r on the block of length L = r*Ls that starts at p: elements p[q*Ls*st];
+// outputs are multiplied by w_L^(j k) = tw[j*k*step], tw[t] = exp(-2 pi i t / M), step = M / L.
+__device__ __forceinline__ void fwd_bfly(double2 *p, int r, int stride, int j, int step, const double2 *tw)
 {
-  const int j = b & (h - 1), i0 = ((b - j) << 1) + j, i1 = i0 + h;
-  const double2 a = x[i0 * st], c = x[i1 * st];
-  x[i0 * st] = make_double2(a.x + c.x, a.y + c.y);
-  x[i1 * st] = cxmul(make_double2(a.x - c.x, a.y - c.y), tw[j * (M / (2 * h))]);
-}
-// one DIT (inverse) butterfly: twiddle conjugated
-__device__ __forceinline__ void dit_bfly(double2 *x, int st, int M, int h, int b, const double2 *tw)
-{
-  const int j = b & (h - 1), i0 = ((b - j) << 1) + j, i1 = i0 + h;
-  const double2 a = x[i0 * st], t = cxmulc(x[i1 * st], tw[j * (M / (2 * h))]);
-  x[i0 * st] = make_double2(a.x + t.x, a.y + t.y);
-  x[i1 * st] = make_double2(a.x - t.x, a.y - t.y);
-}
-// whole line by one warp: lanes = butterflies (M/2 <= 32)
-template <bool FWD>
-__device__ __forceinline__ void line_fft_warp(double2 *x, int M, const double2 *tw, int lane)
-{
-  if (FWD) {
-    for (int h = M / 2; h >= 1; h >>= 1) { if (lane < M / 2) dif_bfly(x, 1, M, h, lane, tw); __syncwarp(); }
+  if (r == 2) {
+    const double2 a = p[0], b = p[stride];
+    p[0] = cxadd(a, b);
+    p[stride] = cxmul(cxsub(a, b), tw[j * step]);
   } else {
-    for (int h = 1; h <= M / 2; h <<= 1) { if (lane < M / 2) dit_bfly(x, 1, M, h, lane, tw); __syncwarp(); }
+    const double2 a0 = p[0], a1 = p[stride], a2 = p[2 * stride];
+    const double2 t1 = cxadd(a1, a2), t2 = make_double2(a0.x - 0.5 * t1.x, a0.y - 0.5 * t1.y);
+    const double2 d = cxsub(a1, a2), t3 = make_double2(LP_SQRT3_2 * d.x, LP_SQRT3_2 * d.y);
+    p[0] = cxadd(a0, t1);
+    p[stride] = cxmul(make_double2(t2.x + t3.y, t2.y - t3.x), tw[j * step]);        // t2 - i t3
+    p[2 * stride] = cxmul(make_double2(t2.x - t3.y, t2.y + t3.x), tw[2 * j * step]); // t2 + i t3
   }
 }
-// all M columns of a [M][P] plane by the whole block: lanes = columns, warps share the butterflies of a stage
-template <bool FWD>
-__device__ __forceinline__ void columns_fft_block(double2 *plane, int M, int P, const double2 *tw)
+// The conjugate-transposed butterfly (inverse): conj twiddles first, then the inverse r-point DFT.
+__device__ __forceinline__ void inv_bfly(double2 *p, int r, int stride, int j, int step, const double2 *tw)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (r == 2) {
+    const double2 y0 = p[0], y1 = cxmulc(p[stride], tw[j * step]);
+    p[0] = cxadd(y0, y1);
+    p[stride] = cxsub(y0, y1);
+  } else {
+    const double2 y0 = p[0], y1 = cxmulc(p[stride], tw[j * step]), y2 = cxmulc(p[2 * stride], tw[2 * j * step]);
+    const double2 t1 = cxadd(y1, y2), t2 = make_double2(y0.x - 0.5 * t1.x, y0.y - 0.5 * t1.y);
+    const double2 d = cxsub(y1, y2), t3 = make_double2(LP_SQRT3_2 * d.x, LP_SQRT3_2 * d.y);
+    p[0] = cxadd(y0, t1);
+    p[stride] = make_double2(t2.x - t3.y, t2.y + t3.x);        // t2 + i t3
+    p[2 * stride] = make_double2(t2.x + t3.y, t2.y - t3.x);    // t2 - i t3
+  }
+}
+
+// A whole line (elements x[i*st]) by one warp: lanes share the M/r butterflies of each stage.
+template <bool FWD>
+__device__ __forceinline__ void line_fft_warp(double2 *x, int st, const FcPlan &pl, const double2 *tw, int lane)
+{
+  const int M = pl.M;
   if (FWD) {
-    for (int h = M / 2; h >= 1; h >>= 1) {
-      for (int b = warp; b < M / 2; b += nw)
-        for (int col = lane; col < M; col += 32) dif_bfly(plane + col, P, M, h, b, tw);
-      __syncthreads();
+    int L = M;
+    for (int s = 0; s < pl.nst; s++) {
+      const int r = pl.radix[s], Ls = L / r, step = M / L;
+      for (int it = lane; it < M / r; it += 32) {
+        const int blk = it / Ls, j = it - blk * Ls;
+        fwd_bfly(x + (blk * L + j) * st, r, Ls * st, j, step, tw);
+      }
+      __syncwarp();
+      L = Ls;
     }
   } else {
-    for (int h = 1; h <= M / 2; h <<= 1) {
-      for (int b = warp; b < M / 2; b += nw)
-        for (int col = lane; col < M; col += 32) dit_bfly(plane + col, P, M, h, b, tw);
+    int Ls = 1;
+    for (int s = pl.nst - 1; s >= 0; s--) {
+      const int r = pl.radix[s], L = Ls * r, step = M / L;
+      for (int it = lane; it < M / r; it += 32) {
+        const int blk = it / Ls, j = it - blk * Ls;
+        inv_bfly(x + (blk * L + j) * st, r, Ls * st, j, step, tw);
+      }
+      __syncwarp();
+      Ls = L;
+    }
+  }
+}
+// All M columns of a [M][P] plane by the whole block: lanes = columns, warps share the butterflies of a stage.
+template <bool FWD>
+__device__ __forceinline__ void columns_fft_block(double2 *plane, int P, const FcPlan &pl, const double2 *tw)
+{
+  const int M = pl.M, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (FWD) {
+    int L = M;
+    for (int s = 0; s < pl.nst; s++) {
+      const int r = pl.radix[s], Ls = L / r, step = M / L;
+      for (int it = warp; it < M / r; it += nw) {
+        const int blk = it / Ls, j = it - blk * Ls;
+        for (int col = lane; col < M; col += 32) fwd_bfly(plane + (blk * L + j) * P + col, r, Ls * P, j, step, tw);
+      }
       __syncthreads();
+      L = Ls;
+    }
+  } else {
+    int Ls = 1;
+    for (int s = pl.nst - 1; s >= 0; s--) {
+      const int r = pl.radix[s], L = Ls * r, step = M / L;
+      for (int it = warp; it < M / r; it += nw) {
+        const int blk = it / Ls, j = it - blk * Ls;
+        for (int col = lane; col < M; col += 32) inv_bfly(plane + (blk * L + j) * P + col, r, Ls * P, j, step, tw);
+      }
+      __syncthreads();
+      Ls = L;
     }
   }
 }
 
 // F1: padded y-z plane of u_p (p < 7) or v_{p-7}, transformed along z and y
 __global__ void __launch_bounds__(256) k_fc_fwd_yz(const double2 *__restrict__ fhat, double2 *__restrict__ Fxy, const double *__restrict__ G,
-                                                   const double *__restrict__ Etab, const double2 *__restrict__ twg, int N)
+                                                   const double *__restrict__ Etab, const double2 *__restrict__ twg, int N, FcPlan pl)
 {
   extern __shared__ double2 smf[];
-  const int M = 2 * N, P = M + 1;
+  const int M = pl.M, P = M + 1;
   double2 *plane = smf, *tw = plane + M * P;
   const int x = blockIdx.x, p = blockIdx.y; const long long cell = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  for (int t = tid; t < M / 2; t += blockDim.x) tw[t] = twg[t];
+  for (int t = tid; t < M; t += blockDim.x) tw[t] = twg[t];
   for (int t = tid; t < M * P; t += blockDim.x) plane[t] = make_double2(0., 0.);
   __syncthreads();
   const double *E = Etab + LP_ETAB_PAD;
@@ -107,41 +162,38 @@ __global__ void __launch_bounds__(256) k_fc_fwd_yz(const double2 *__restrict__ f
     plane[y * P + z] = make_double2(m * f.x, m * f.y);
   }
   __syncthreads();
-  for (int y = warp; y < N; y += nw) line_fft_warp<true>(plane + y * P, M, tw, lane);
+  for (int y = warp; y < N; y += nw) line_fft_warp<true>(plane + y * P, 1, pl, tw, lane);
   __syncthreads();
-  columns_fft_block<true>(plane, M, P, tw);
+  columns_fft_block<true>(plane, P, pl, tw);
   double2 *o = Fxy + ((cell * 14 + p) * N + x) * (long long)(M * M);
   for (int t = tid; t < M * M; t += blockDim.x) o[t] = plane[(t / M) * P + (t % M)];
 }
 
 // F2: x-lines of the 14 arrays at 8 consecutive kz: transform, multiply-accumulate over p, inverse transform
-__global__ void __launch_bounds__(256) k_fc_x(const double2 *__restrict__ Fxy, double2 *__restrict__ Cx, const double2 *__restrict__ twg, int N)
+__global__ void __launch_bounds__(256) k_fc_x(const double2 *__restrict__ Fxy, double2 *__restrict__ Cx, const double2 *__restrict__ twg, int N, FcPlan pl)
 {
   extern __shared__ double2 smf[];
-  const int M = 2 * N, P = M + 1, H = N / 2;
+  const int M = pl.M, P = M + 1, H = N / 2;
   double2 *U = smf, *V = U + 8 * P, *tw = V + 8 * P;
   const int kz0 = blockIdx.x * 8, ky = blockIdx.y; const long long cell = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;   // 8 warps: warp = line
-  for (int t = tid; t < M / 2; t += blockDim.x) tw[t] = twg[t];
-  for (int t = tid; t < 8 * P; t += blockDim.x) { U[t] = make_double2(0., 0.); V[t] = make_double2(0., 0.); }
+  const int nkz = (M - kz0 < 8) ? M - kz0 : 8;                       // M need not be a multiple of 8
+  for (int t = tid; t < M; t += blockDim.x) tw[t] = twg[t];
   double2 acc[2] = {make_double2(0., 0.), make_double2(0., 0.)};
   const long long MM = (long long)M * M;
   for (int p = 0; p < 7; p++) {
     __syncthreads();
     const double2 *su = Fxy + ((cell * 14 + p) * N) * MM + (long long)ky * M + kz0;
     const double2 *sv = Fxy + ((cell * 14 + p + 7) * N) * MM + (long long)ky * M + kz0;
-    for (int t = tid; t < 8 * N; t += blockDim.x) {
+    for (int t = tid; t < 8 * M; t += blockDim.x) {
       const int x = t >> 3, kzi = t & 7;
-      U[kzi * P + x] = su[x * MM + kzi];
-      V[kzi * P + x] = sv[x * MM + kzi];
-    }
-    for (int t = tid; t < 8 * N; t += blockDim.x) {           // re-zero the padded half (previous transform filled it)
-      const int x = N + (t >> 3), kzi = t & 7;
-      U[kzi * P + x] = make_double2(0., 0.); V[kzi * P + x] = make_double2(0., 0.);
+      const bool live = x < N && kzi < nkz;
+      U[kzi * P + x] = live ? su[x * MM + kzi] : make_double2(0., 0.);
+      V[kzi * P + x] = live ? sv[x * MM + kzi] : make_double2(0., 0.);
     }
     __syncthreads();
-    line_fft_warp<true>(U + warp * P, M, tw, lane);
-    line_fft_warp<true>(V + warp * P, M, tw, lane);
+    line_fft_warp<true>(U + warp * P, 1, pl, tw, lane);
+    line_fft_warp<true>(V + warp * P, 1, pl, tw, lane);
     #pragma unroll
     for (int q = 0; q < 2; q++) {
       const int idx = lane + 32 * q;
@@ -152,29 +204,29 @@ __global__ void __launch_bounds__(256) k_fc_x(const double2 *__restrict__ Fxy, d
   #pragma unroll
   for (int q = 0; q < 2; q++) { const int idx = lane + 32 * q; if (idx < M) U[warp * P + idx] = acc[q]; }
   __syncwarp();
-  line_fft_warp<false>(U + warp * P, M, tw, lane);
+  line_fft_warp<false>(U + warp * P, 1, pl, tw, lane);
   __syncthreads();
   double2 *o = Cx + (cell * N) * MM + (long long)ky * M + kz0;
   for (int t = tid; t < 8 * N; t += blockDim.x) {
     const int xo = t >> 3, kzi = t & 7;
-    o[xo * MM + kzi] = U[kzi * P + xo + H];
+    if (kzi < nkz) o[xo * MM + kzi] = U[kzi * P + xo + H];
   }
 }
 
 // F3: inverse along y and z of one x' plane, scale, extract the [N/2, N/2+N) window
-__global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ Cx, double2 *__restrict__ q, const double2 *__restrict__ twg, int N)
+__global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ Cx, double2 *__restrict__ q, const double2 *__restrict__ twg, int N, FcPlan pl)
 {
   extern __shared__ double2 smf[];
-  const int M = 2 * N, P = M + 1, H = N / 2;
+  const int M = pl.M, P = M + 1, H = N / 2;
   double2 *plane = smf, *tw = plane + M * P;
   const int xo = blockIdx.x; const long long cell = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  for (int t = tid; t < M / 2; t += blockDim.x) tw[t] = twg[t];
+  for (int t = tid; t < M; t += blockDim.x) tw[t] = twg[t];
   const double2 *s = Cx + (cell * N + xo) * (long long)(M * M);
   for (int t = tid; t < M * M; t += blockDim.x) plane[(t / M) * P + (t % M)] = s[t];
   __syncthreads();
-  columns_fft_block<false>(plane, M, P, tw);
-  for (int y = H + warp; y < H + N; y += nw) line_fft_warp<false>(plane + y * P, M, tw, lane);
+  columns_fft_block<false>(plane, P, pl, tw);
+  for (int y = H + warp; y < H + N; y += nw) line_fft_warp<false>(plane + y * P, 1, pl, tw, lane);
   __syncthreads();
   const double sc = 1.0 / ((double)M * M * M);
   double2 *o = q + (cell * N + xo) * (long long)(N * N);
@@ -184,29 +236,39 @@ __global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ C
   }
 }
 
+// factor M into radix-3 and radix-2 stages (3s first); false if another prime divides M
+bool make_plan(int M, FcPlan &pl)
+{
+  pl.M = M; pl.nst = 0;
+  int m = M;
+  while (m % 3 == 0 && pl.nst < 8) { pl.radix[pl.nst++] = 3; m /= 3; }
+  while (m % 2 == 0 && pl.nst < 8) { pl.radix[pl.nst++] = 2; m /= 2; }
+  return m == 1 && M <= 64 && M >= 2;
+}
+
 } // namespace
 
-// returns -1 when N is not a power of two (caller uses the tiled direct kernel)
+// returns -1 when M = 3N/2 is not of the form 2^a 3^b (caller uses the tiled direct kernel)
 int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B)
 {
-  const int N = c->p.N, M = 2 * N;
-  if (N & (N - 1)) return -1;
-  const size_t plane_bytes = ((size_t)M * (M + 1) + M / 2) * sizeof(double2);
-  const size_t line_bytes = ((size_t)16 * (M + 1) + M / 2) * sizeof(double2);
+  const int N = c->p.N, M = 3 * N / 2;
+  FcPlan pl;
+  if ((N & 1) || !make_plan(M, pl)) return -1;
+  const size_t plane_bytes = ((size_t)M * (M + 1) + M) * sizeof(double2);
+  const size_t line_bytes = ((size_t)16 * (M + 1) + M) * sizeof(double2);
   if (!c->d_fc1) {
-    // chunk of cells whose 14 transformed arrays fit a fixed budget (29 MB per cell at N = 32)
+    // chunk of cells whose 14 transformed arrays fit a fixed budget (12.4 MB per cell at N = 32)
     const size_t per_cell = (size_t)14 * N * M * M * sizeof(double2);
-    size_t chunk = (size_t)1 << 30;
-    chunk /= per_cell;
+    size_t chunk = ((size_t)1 << 30) / per_cell;
     if (chunk < 1) chunk = 1;
     if (chunk > c->cap_cells) chunk = c->cap_cells;
     c->fc_chunk = (int)chunk;
     LP_CUDA(cudaMalloc((void **)&c->d_fc1, per_cell * chunk));
     LP_CUDA(cudaMalloc((void **)&c->d_fc2, (size_t)N * M * M * sizeof(double2) * chunk));
-    std::vector<double> tw(M);   // exp(-2 pi i k / M), k < M/2
-    for (int k = 0; k < M / 2; k++) { const long double a = 2.0L * M_PIl * k / M; tw[2 * k] = (double)cosl(a); tw[2 * k + 1] = (double)(-sinl(a)); }
-    LP_CUDA(cudaMalloc((void **)&c->d_fctw, M * sizeof(double)));
-    LP_CUDA(cudaMemcpy(c->d_fctw, tw.data(), M * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double> tw(2 * M);   // exp(-2 pi i t / M), t < M
+    for (int t = 0; t < M; t++) { const long double a = 2.0L * M_PIl * t / M; tw[2 * t] = (double)cosl(a); tw[2 * t + 1] = (double)(-sinl(a)); }
+    LP_CUDA(cudaMalloc((void **)&c->d_fctw, 2 * M * sizeof(double)));
+    LP_CUDA(cudaMemcpy(c->d_fctw, tw.data(), 2 * M * sizeof(double), cudaMemcpyHostToDevice));
     LP_CUDA(cudaFuncSetAttribute(k_fc_fwd_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     LP_CUDA(cudaFuncSetAttribute(k_fc_inv_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
@@ -218,11 +280,11 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     const double2 *fh = reinterpret_cast<const double2 *>(fhat) + (size_t)b0 * c->N3;
     double2 *qo = reinterpret_cast<double2 *>(q) + (size_t)b0 * c->N3;
     double2 *F1 = reinterpret_cast<double2 *>(c->d_fc1), *F2 = reinterpret_cast<double2 *>(c->d_fc2);
-    k_fc_fwd_yz<<<dim3(N, 14, nb), 256, plane_bytes, c->stream>>>(fh, F1, c->d_G, c->d_Etab, tw, N);
+    k_fc_fwd_yz<<<dim3(N, 14, nb), 256, plane_bytes, c->stream>>>(fh, F1, c->d_G, c->d_Etab, tw, N, pl);
     LP_LAUNCHED(c);
-    k_fc_x<<<dim3(M / 8, M, nb), 256, line_bytes, c->stream>>>(F1, F2, tw, N);
+    k_fc_x<<<dim3((M + 7) / 8, M, nb), 256, line_bytes, c->stream>>>(F1, F2, tw, N, pl);
     LP_LAUNCHED(c);
-    k_fc_inv_yz<<<dim3(N, nb), 256, plane_bytes, c->stream>>>(F2, qo, tw, N);
+    k_fc_inv_yz<<<dim3(N, nb), 256, plane_bytes, c->stream>>>(F2, qo, tw, N, pl);
     LP_LAUNCHED(c);
   }
   if (prof) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
