@@ -109,10 +109,23 @@ __device__ __forceinline__ double2 phase_mul(double2 cs, double2 x)
 {
   return make_double2(__dsub_rn(__dmul_rn(cs.x, x.x), __dmul_rn(cs.y, x.y)), __dadd_rn(__dmul_rn(cs.x, x.y), __dmul_rn(cs.y, x.x)));
 }
+__device__ __forceinline__ int bitrev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - bits)); }
+// N-point decimation-in-time FFT across N consecutive lanes (N = 2^k <= 32): lane l supplies element bitrev(l) and
+// returns output l.  W[t] = W_N^t carries the sign of the transform.  All 32 lanes of the warp must call it.
+__device__ __forceinline__ double2 lanes_fft(double2 v, int l, int N, const double2 *W)
+{
+  for (int h = 1; h < N; h <<= 1) {
+    const bool up = (l & h) != 0;
+    const double2 m = up ? cmul(v, W[(l & (h - 1)) * (N / (2 * h))]) : v;
+    const double2 o = make_double2(__shfl_xor_sync(0xffffffffu, m.x, h), __shfl_xor_sync(0xffffffffu, m.y, h));
+    v = up ? make_double2(o.x - m.x, o.y - m.y) : make_double2(o.x + m.x, o.y + m.y);
+  }
+  return v;
+}
 
 template <bool IN_REAL, int EPI, bool PRE, bool POST>
 __global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, double *__restrict__ out,
-                                                 const double2 *__restrict__ Wm, int N, PhaseTabs ph, FsEpilogue ep)
+                                                 const double2 *__restrict__ Wm, int N, int logn, PhaseTabs ph, FsEpilogue ep)
 {
   extern __shared__ double2 sm2[];
   const int P = N + 1;
@@ -130,11 +143,24 @@ __global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, 
   F[r * P + cc] = Wm[tid];
   __syncthreads();
   double2 acc = make_double2(0., 0.);
-  for (int j = 0; j < N; j++) cfma(acc, F[cc * P + j], X[r * P + j]);   // axis 2
-  Y[r * P + cc] = acc;
-  __syncthreads();
-  acc = make_double2(0., 0.);
-  for (int j = 0; j < N; j++) cfma(acc, F[r * P + j], Y[j * P + cc]);   // axis 1
+  if (logn) {
+    // power-of-two N: each line is a decimation-in-time FFT across N lanes (one element per lane, partners by
+    // __shfl_xor); bit-reversed input index, natural output.  F row 1 holds the twiddles W_N^t.
+    acc = lanes_fft(X[r * P + bitrev(cc, logn)], cc, N, F + P);            // axis 2: line = row r, lane = cc
+    Y[r * P + cc] = acc;
+    __syncthreads();
+    acc = lanes_fft(Y[bitrev(cc, logn) * P + r], cc, N, F + P);            // axis 1: line = column r, lane = output row cc
+    __syncthreads();
+    X[cc * P + r] = acc;
+    __syncthreads();
+    acc = X[r * P + cc];
+  } else {
+    for (int j = 0; j < N; j++) cfma(acc, F[cc * P + j], X[r * P + j]);   // axis 2
+    Y[r * P + cc] = acc;
+    __syncthreads();
+    acc = make_double2(0., 0.);
+    for (int j = 0; j < N; j++) cfma(acc, F[r * P + j], Y[j * P + cc]);   // axis 1
+  }
   if (POST) acc = phase_mul(ph.post[(i * N + r) * N + cc], acc);
   if (EPI == 0) {
     reinterpret_cast<double2 *>(out)[g] = acc;
@@ -150,7 +176,7 @@ __global__ void __launch_bounds__(1024) k_dft_jk(const double *__restrict__ in, 
 // axis 0: block = (cell, j); slab X[i][k] = in[cell][i][j][k]
 template <bool PRE, bool POST>
 __global__ void __launch_bounds__(1024) k_dft_i(const double2 *__restrict__ in, double2 *__restrict__ out,
-                                                const double2 *__restrict__ Wm, int N, PhaseTabs ph)
+                                                const double2 *__restrict__ Wm, int N, int logn, PhaseTabs ph)
 {
   extern __shared__ double2 sm2[];
   const int P = N + 1;
@@ -164,11 +190,29 @@ __global__ void __launch_bounds__(1024) k_dft_i(const double2 *__restrict__ in, 
   F[i * P + k] = Wm[tid];
   __syncthreads();
   double2 acc = make_double2(0., 0.);
-  for (int a = 0; a < N; a++) cfma(acc, F[i * P + a], X[a * P + k]);
+  if (logn) {
+    // thread (i,k) takes lane k of the line "column i": transforms along the slab's first index
+    acc = lanes_fft(X[bitrev(k, logn) * P + i], k, N, F + P);             // output index k of column i
+    __syncthreads();
+    X[k * P + i] = acc;
+    __syncthreads();
+    acc = X[i * P + k];
+  } else {
+    for (int a = 0; a < N; a++) cfma(acc, F[i * P + a], X[a * P + k]);
+  }
   if (POST) acc = phase_mul(ph.post[(i * N + j) * N + k], acc);
   out[g] = acc;
 }
 
+// log2(N) when N is a power of two >= 8 and the block is whole warps (shuffle FFT lines), else 0 (dense N-point sums)
+static int lp_log2_pow2(int N)
+{
+  static const bool dense_only = getenv("LPGPU_DFT_DENSE") != nullptr;   // developer knob
+  if (dense_only || (N & (N - 1)) || N < 8 || N > 32) return 0;
+  int l = 0;
+  while ((1 << l) < N) l++;
+  return l;
+}
 static size_t dft_smem(int N, int arrays) { return (size_t)arrays * N * (N + 1) * sizeof(double2); }
 
 template <bool IN_REAL, int EPI, bool PRE, bool POST>
@@ -178,7 +222,7 @@ static int launch_jk(lpgpu_ctx *c, const double *in, double *out, const double *
   const size_t smem = dft_smem(N, 3);
   auto kern = k_dft_jk<IN_REAL, EPI, PRE, POST>;
   LP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<B * N, N * N, smem, c->stream>>>(in, out, reinterpret_cast<const double2 *>(Wm), N, ph, ep);
+  kern<<<B * N, N * N, smem, c->stream>>>(in, out, reinterpret_cast<const double2 *>(Wm), N, lp_log2_pow2(N), ph, ep);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -190,7 +234,7 @@ static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *W
   auto kern = k_dft_i<PRE, POST>;
   LP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<B * N, N * N, smem, c->stream>>>(reinterpret_cast<const double2 *>(in), reinterpret_cast<double2 *>(out),
-                                          reinterpret_cast<const double2 *>(Wm), N, ph);
+                                          reinterpret_cast<const double2 *>(Wm), N, lp_log2_pow2(N), ph);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }

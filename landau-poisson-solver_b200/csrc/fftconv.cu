@@ -482,7 +482,10 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
   if (!c->d_fc1) {
     // chunk of cells whose 14 transformed arrays fit a fixed budget (12.4 MB per cell at N = 32)
     const size_t per_cell = (size_t)14 * N * M * M * sizeof(double2);
-    size_t chunk = ((size_t)1 << 30) / per_cell;
+    // 1 GB of transformed planes per chunk.  Measured: chunks small enough for F2 to read F1's output out of the
+    // 126 MB L2 (96 MB) are 15 % slower than one big launch -- the kernels are not HBM-limited, launch tails are.
+    const size_t budget_mb = getenv("LPGPU_FC_CHUNK_MB") ? (size_t)atoi(getenv("LPGPU_FC_CHUNK_MB")) : 1024;
+    size_t chunk = (budget_mb << 20) / per_cell;
     if (chunk < 1) chunk = 1;
     if (chunk > c->cap_cells) chunk = c->cap_cells;
     c->fc_chunk = (int)chunk;
