@@ -17,6 +17,7 @@
 // exists anywhere: products are formed position-wise.  Butterflies run on shared-memory lines with
 // correctly rounded twiddles from the host.  Sizes whose M has another prime factor use the tiled direct kernel.
 #include "lpgpu_internal.h"
+#include "fc3.cuh"
 
 #define LP_LAUNCHED(c)                                  \
   do {                                                  \
@@ -459,6 +460,79 @@ int launch_regs(lpgpu_ctx *c, const double2 *fh, double2 *F1, double2 *F2, doubl
   return LPGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Register-resident pipeline (fc3.cuh): F1 z-lines -> F2 (y, x, product, inverse x, inverse y) -> F3 inverse z.
+template <int L>
+__global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__restrict__ fhat, const double *__restrict__ Gt,
+                                                           const double *__restrict__ E, double2 *__restrict__ Z)
+{
+  typedef fc3::F1<L> K;
+  __shared__ double2 FS[K::SMEM_C2];
+  __shared__ double sE[K::N];
+  const int y = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
+  K::load(tid, cell, y, fhat, E, FS, sE);
+  __syncthreads();
+  K::lines(tid, cell, y, Gt, FS, sE, Z);
+}
+template <int L>
+__global__ void __launch_bounds__(fc3::F2<L>::NT, 1) k_fc3_f2(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
+{
+  typedef fc3::F2<L> K;
+  extern __shared__ double2 smf[];
+  double2 *IN = smf, *Y = IN + K::IN_C2;
+  double *sE = reinterpret_cast<double *>(Y + K::Y_C2);
+  const int kz = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
+  K::issue_loads(tid, cell, kz, 0, Z, IN);
+  for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
+  double2 acc[L];
+  #pragma unroll
+  for (int q = 0; q < L; q++) acc[q] = make_double2(0., 0.);
+  #pragma unroll 1
+  for (int p = 0; p < 7; p++) {
+    fc3::cp_wait_all();
+    __syncthreads();                       // planes of p landed; every x-stage read of Y from p-1 is done
+    K::ystage(tid, p, IN, sE, Y);
+    __syncthreads();                       // Y complete; IN consumed
+    if (p < 6) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
+    K::xstage(tid, Y, acc);
+  }
+  __syncthreads();
+  K::xinverse(tid, acc, Y);                // T aliases Y
+  __syncthreads();
+  K::yinverse(tid, Y, IN);                 // T2 aliases IN
+  __syncthreads();
+  K::store(tid, cell, kz, IN, C);
+}
+template <int L>
+__global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__restrict__ C, double2 *__restrict__ q)
+{
+  typedef fc3::F3<L> K;
+  __shared__ double2 T3[K::SMEM_C2];
+  const int xo = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
+  K::zinverse(tid, cell, xo, C, T3);
+  __syncthreads();
+  K::store(tid, cell, xo, T3, q);
+}
+template <int L>
+int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb)
+{
+  typedef fc3::F2<L> K2;
+  constexpr int N = 2 * L, M = 3 * L;
+  const size_t smem2 = (size_t)(K2::IN_C2 + K2::Y_C2) * sizeof(double2) + N * sizeof(double);
+  if (!c->fc3_attr) {
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    c->fc3_attr = true;
+  }
+  const double *E = c->d_Etab + LP_ETAB_PAD;
+  k_fc3_f1<L><<<dim3(N, nb), fc3::F1<L>::NT, 0, c->stream>>>(fh, c->d_Gt, E, Z);
+  LP_LAUNCHED(c);
+  k_fc3_f2<L><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
+  LP_LAUNCHED(c);
+  k_fc3_f3<L><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
 // factor M into radix-3 and radix-2 stages (3s first); false if another prime divides M
 bool make_plan(int M, FcPlan &pl)
 {
@@ -495,6 +569,16 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     for (int t = 0; t < M; t++) { const long double a = 2.0L * M_PIl * t / M; tw[2 * t] = (double)cosl(a); tw[2 * t + 1] = (double)(-sinl(a)); }
     LP_CUDA(cudaMalloc((void **)&c->d_fctw, 2 * M * sizeof(double)));
     LP_CUDA(cudaMemcpy(c->d_fctw, tw.data(), 2 * M * sizeof(double), cudaMemcpyHostToDevice));
+    {
+      // kernel symbols re-laid as Gt[a][y][z][x] (x fastest): the lanes of an F1 warp are consecutive x
+      std::vector<double> gt((size_t)7 * c->N3);
+      for (int a = 0; a < 7; a++)
+        for (int x = 0; x < N; x++)
+          for (int y = 0; y < N; y++)
+            for (int z = 0; z < N; z++) gt[(((size_t)a * N + y) * N + z) * N + x] = c->tab.G[(size_t)7 * (z + N * (y + N * x)) + a];
+      LP_CUDA(cudaMalloc((void **)&c->d_Gt, gt.size() * sizeof(double)));
+      LP_CUDA(cudaMemcpy(c->d_Gt, gt.data(), gt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     LP_CUDA(cudaFuncSetAttribute(k_fc_fwd_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     LP_CUDA(cudaFuncSetAttribute(k_fc_inv_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
@@ -507,6 +591,13 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     double2 *qo = reinterpret_cast<double2 *>(q) + (size_t)b0 * c->N3;
     double2 *F1 = reinterpret_cast<double2 *>(c->d_fc1), *F2 = reinterpret_cast<double2 *>(c->d_fc2);
     static const bool generic_only = getenv("LPGPU_FFT_GENERIC") != nullptr;   // developer knob: force the shared-memory stages
+    static const bool old_regs = getenv("LPGPU_FC_OLD") != nullptr;            // developer knob: the shuffle-line kernels
+    if (!generic_only && !old_regs && (N == 32 || N == 24 || N == 16 || N == 8)) {
+      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb)
+             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb) : launch_fc3<4>(c, fh, F1, F2, qo, nb);
+      if (rc != LPGPU_OK) return rc;
+      continue;
+    }
     if (!generic_only && (N == 32 || N == 16 || N == 8)) {
       int rc = N == 32 ? launch_regs<16>(c, fh, F1, F2, qo, tw, nb) : N == 16 ? launch_regs<8>(c, fh, F1, F2, qo, tw, nb) : launch_regs<4>(c, fh, F1, F2, qo, tw, nb);
       if (rc != LPGPU_OK) return rc;

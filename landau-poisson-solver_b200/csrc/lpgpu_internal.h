@@ -53,7 +53,8 @@ struct lpgpu_ctx {
   double *d_B;                             // projection intermediate: ncell*N*4*Nv^2 complex
   size_t cap_cells;        // capacity (in cells) of the collision work arrays
   // ---- FFT-convolution variant of ComputeQ (allocated on first use)
-  double *d_fc1, *d_fc2, *d_fctw;
+  double *d_fc1, *d_fc2, *d_fctw, *d_Gt;
+  bool fc3_attr;
   int fc_chunk;
   // ---- optional CUDA-event timing of the ComputeQ launches (bench.py roofline)
   bool prof_on;

@@ -1,0 +1,106 @@
+// CPU thread-loop emulator of the FFT-convolution ComputeQ pipeline (landau-poisson-solver_b200/csrc/fc3.cuh).
+// Test infrastructure only: the per-thread phase functions of the CUDA kernels are __host__ __device__;
+// here every barrier-separated phase is run for all thread ids of a CTA in turn, CTA by CTA, so the index
+// arithmetic and the transform algebra are checked in a container without a GPU.  fc3_direct is the plain
+// O(N^6) sum the pipeline must reproduce (collisionRoutines_1.cpp:706-773 with the folded weight).
+#include <cstring>
+#include <vector>
+#include "../../landau-poisson-solver_b200/csrc/fc3.cuh"
+
+template <int L>
+static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q)
+{
+  using namespace fc3;
+  constexpr int N = 2 * L, M = 3 * L;
+  std::vector<double> Gt((size_t)7 * N * N * N);
+  for (int a = 0; a < 7; a++)
+    for (int x = 0; x < N; x++)
+      for (int y = 0; y < N; y++)
+        for (int z = 0; z < N; z++) Gt[(((size_t)a * N + y) * N + z) * N + x] = G7[(size_t)7 * (z + N * (y + N * x)) + a];
+  std::vector<double2> Z((size_t)B * 10 * M * N * N), C((size_t)B * M * N * N);
+  {
+    typedef F1<L> K;
+    std::vector<double2> FS(K::SMEM_C2);
+    std::vector<double> sE(N);
+    for (int cell = 0; cell < B; cell++)
+      for (int y = 0; y < N; y++) {
+        for (int t = 0; t < K::NT; t++) K::load(t, cell, y, fhat, E, FS.data(), sE.data());
+        for (int t = 0; t < K::NT; t++) K::lines(t, cell, y, Gt.data(), FS.data(), sE.data(), Z.data());
+      }
+  }
+  {
+    typedef F2<L> K;
+    std::vector<double2> IN(K::IN_C2), Y(K::Y_C2);
+    std::vector<double> sE(E, E + N);
+    struct Acc { double2 a[L]; };
+    std::vector<Acc> acc(K::NT);
+    for (int cell = 0; cell < B; cell++)
+      for (int kz = 0; kz < M; kz++) {
+        std::memset(acc.data(), 0, sizeof(Acc) * acc.size());
+        for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, 0, Z.data(), IN.data());
+        for (int p = 0; p < 7; p++) {
+          for (int t = 0; t < K::NT; t++) K::ystage(t, p, IN.data(), sE.data(), Y.data());
+          if (p < 6) for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, p + 1, Z.data(), IN.data());
+          for (int t = 0; t < K::NT; t++) K::xstage(t, Y.data(), acc[t].a);
+        }
+        for (int t = 0; t < K::NT; t++) K::xinverse(t, acc[t].a, Y.data());
+        for (int t = 0; t < K::NT; t++) K::yinverse(t, Y.data(), IN.data());
+        for (int t = 0; t < K::NT; t++) K::store(t, cell, kz, IN.data(), C.data());
+      }
+  }
+  {
+    typedef F3<L> K;
+    std::vector<double2> T3(K::SMEM_C2);
+    for (int cell = 0; cell < B; cell++)
+      for (int xo = 0; xo < N; xo++) {
+        for (int t = 0; t < K::NT; t++) K::zinverse(t, cell, xo, C.data(), T3.data());
+        for (int t = 0; t < K::NT; t++) K::store(t, cell, xo, T3.data(), q);
+      }
+  }
+}
+
+extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+{
+  const double2 *f = reinterpret_cast<const double2 *>(fhat);
+  double2 *o = reinterpret_cast<double2 *>(q);
+  switch (N) {
+    case 8: emulate<4>(B, f, G7, E, o); return 0;
+    case 16: emulate<8>(B, f, G7, E, o); return 0;
+    case 24: emulate<12>(B, f, G7, E, o); return 0;
+    case 32: emulate<16>(B, f, G7, E, o); return 0;
+  }
+  return 1;
+}
+
+extern "C" int fc3_direct(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+{
+  const int H = N / 2, N3 = N * N * N;
+  for (int cell = 0; cell < B; cell++) {
+    const double *fh = fhat + (size_t)2 * N3 * cell;
+    #pragma omp parallel for collapse(2)
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j < N; j++)
+        for (int k = 0; k < N; k++) {
+          double t0 = 0., t1 = 0.;
+          for (int l = 0; l < N; l++) {
+            const int x = i + H - l; if (x < 0 || x >= N) continue;
+            for (int m = 0; m < N; m++) {
+              const int y = j + H - m; if (y < 0 || y >= N) continue;
+              for (int n = 0; n < N; n++) {
+                const int z = k + H - n; if (z < 0 || z >= N) continue;
+                const size_t w = n + (size_t)N * (m + N * l), b = z + (size_t)N * (y + N * x);
+                const double *g = G7 + 7 * w;
+                const double e1 = E[x], e2 = E[y], e3 = E[z];
+                const double W = g[0] - (g[1] * e1 * e1 + g[2] * e2 * e2 + g[3] * e3 * e3 + g[4] * e1 * e2 + g[5] * e1 * e3 + g[6] * e2 * e3);
+                const double ar = fh[2 * w], ai = fh[2 * w + 1], br = fh[2 * b], bi = fh[2 * b + 1];
+                t0 += W * (ar * br - ai * bi);
+                t1 += W * (ar * bi + ai * br);
+              }
+            }
+          }
+          const size_t o = (size_t)2 * (N3 * (size_t)cell + k + N * (j + N * i));
+          q[o] = t0; q[o + 1] = t1;
+        }
+  }
+  return 0;
+}
