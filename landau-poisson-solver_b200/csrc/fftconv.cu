@@ -503,6 +503,117 @@ __global__ void __launch_bounds__(fc3::F2<L>::NT, 1) k_fc3_f2(const double2 *__r
   __syncthreads();
   K::store(tid, cell, kz, IN, C);
 }
+// ---- F2 with the product accumulators parked in tensor memory (L = 16) ------------------------------------
+// The x-stage thread needs acc (16 complex) across the seven p iterations, next to uh, vh and the butterflies of
+// the transform in flight: > 200 live registers, one CTA per SM.  TMEM (256 KB per SM, idle in this kernel) takes
+// acc instead: every thread owns 64 32-bit columns of its own lane (tcgen05.ld/st .32x32b), read-modify-written
+// four complex values at a time when the products are formed.  Registers drop to <= 168 -> two CTAs per SM.
+#define LP_TM_R16(r) "{%" #r "0, %" #r "1, %" #r "2, %" #r "3, %" #r "4, %" #r "5, %" #r "6, %" #r "7, %" #r "8, %" #r "9, %" #r "10, %" #r "11, %" #r "12, %" #r "13, %" #r "14, %" #r "15}"
+__device__ __forceinline__ void tmem_ld4c(unsigned taddr, double2 (&a)[4])
+{
+  unsigned r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               "tcgen05.wait::ld.sync.aligned;\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  #pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+}
+__device__ __forceinline__ void tmem_st4c(unsigned taddr, const double2 (&a)[4])
+{
+  unsigned r[16];
+  #pragma unroll
+  for (int i = 0; i < 4; i++) {
+    r[4 * i] = (unsigned)__double2loint(a[i].x); r[4 * i + 1] = (unsigned)__double2hiint(a[i].x);
+    r[4 * i + 2] = (unsigned)__double2loint(a[i].y); r[4 * i + 3] = (unsigned)__double2hiint(a[i].y);
+  }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+               :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+#define LP_F2TM_COLS 128   // 6 warps: lane quarters 0..3 twice -> two groups of 64 columns
+__global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
+{
+  constexpr int L = 16;
+  typedef fc3::F2<L> K;
+  extern __shared__ double2 smf[];
+  __shared__ unsigned s_tmem;
+  double2 *IN = smf, *Y = IN + K::IN_C2;
+  double *sE = reinterpret_cast<double *>(Y + K::Y_C2);
+  const int kz = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tmem);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(dst), "r"((unsigned)LP_F2TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  K::issue_loads(tid, cell, kz, 0, Z, IN);
+  for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const unsigned tbase = s_tmem;
+  const unsigned tacc = tbase + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * 64);
+  // x-stage task; every lane of a warp runs it (the tcgen05 instructions are warp-wide), idle lanes on a clamped line
+  int r, ky;
+  const bool xok = K::xtask(tid, r, ky);
+  if (ky > K::M - 1) ky = K::M - 1;
+  #pragma unroll 1
+  for (int p = 0; p < 7; p++) {
+    fc3::cp_wait_all();
+    __syncthreads();                       // planes of p landed; every x-stage read of Y from p-1 is done
+    K::ystage(tid, p, IN, sE, Y);
+    __syncthreads();                       // Y complete; IN consumed
+    if (p < 6) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
+    {
+      double2 a0[L], a1[L], uh[L], vh[L];
+      #pragma unroll
+      for (int l = 0; l < L; l++) { a0[l] = Y[l * K::PY + ky]; a1[l] = Y[(l + L) * K::PY + ky]; }
+      fc3::fwd_third<L>(a0, a1, r, uh);
+      #pragma unroll
+      for (int l = 0; l < L; l++) { a0[l] = Y[K::N * K::PY + l * K::PY + ky]; a1[l] = Y[K::N * K::PY + (l + L) * K::PY + ky]; }
+      fc3::fwd_third<L>(a0, a1, r, vh);
+      #pragma unroll
+      for (int c4 = 0; c4 < L / 4; c4++) {
+        double2 a[4];
+        if (p > 0) tmem_ld4c(tacc + 16 * c4, a);
+        else { a[0] = a[1] = a[2] = a[3] = make_double2(0., 0.); }
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int q = 4 * c4 + i;
+          a[i].x += uh[q].x * vh[q].x - uh[q].y * vh[q].y;
+          a[i].y += uh[q].x * vh[q].y + uh[q].y * vh[q].x;
+        }
+        tmem_st4c(tacc + 16 * c4, a);
+      }
+      tmem_wait_st();
+    }
+  }
+  __syncthreads();
+  {
+    double2 acc[L];
+    #pragma unroll
+    for (int c4 = 0; c4 < L / 4; c4++) {
+      double2 a[4];
+      tmem_ld4c(tacc + 16 * c4, a);
+      #pragma unroll
+      for (int i = 0; i < 4; i++) acc[4 * c4 + i] = a[i];
+    }
+    if (xok) {
+      fc3::inv_third<L>(acc, r);
+      #pragma unroll
+      for (int l = 0; l < L; l++) Y[(r * L + l) * K::PY + ky] = acc[l];      // T aliases Y
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"((unsigned)LP_F2TM_COLS) : "memory");
+  K::yinverse(tid, Y, IN);                 // T2 aliases IN
+  __syncthreads();
+  K::store(tid, cell, kz, IN, C);
+}
 template <int L>
 __global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__restrict__ C, double2 *__restrict__ q)
 {
@@ -521,12 +632,15 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   const size_t smem2 = (size_t)(K2::IN_C2 + K2::Y_C2) * sizeof(double2) + N * sizeof(double);
   if (!c->fc3_attr) {
     LP_CUDA(cudaFuncSetAttribute(k_fc3_f2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    if (L == 16) LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     c->fc3_attr = true;
   }
   const double *E = c->d_Etab + LP_ETAB_PAD;
   k_fc3_f1<L><<<dim3(N, nb), fc3::F1<L>::NT, 0, c->stream>>>(fh, c->d_Gt, E, Z);
   LP_LAUNCHED(c);
-  k_fc3_f2<L><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
+  static const bool no_tmem = getenv("LPGPU_FC_NO_TMEM") != nullptr;   // developer knob: accumulators in registers, 1 CTA per SM
+  if (L == 16 && !no_tmem) k_fc3_f2_tmem<<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
+  else k_fc3_f2<L><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
   LP_LAUNCHED(c);
   k_fc3_f3<L><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo);
   LP_LAUNCHED(c);
