@@ -3,6 +3,7 @@
 // the Fourier -> DG projection.  Reference lines are cited per kernel; paths are relative to
 // /root/reference/source.
 #include "lpgpu_internal.h"
+#include "fc3.cuh"
 
 #define LP_LAUNCHED(c)                                  \
   do {                                                  \
@@ -204,6 +205,82 @@ __global__ void __launch_bounds__(1024) k_dft_i(const double2 *__restrict__ in, 
   out[g] = acc;
 }
 
+// ---- register-resident lines (N = 8, 16, 24, 32): one thread owns a whole N-point line (fc3::fftN), a CTA of N
+// threads owns one N x N slab.  k_tf_jk: coalesced load (+ pre-phase) -> shared, lines along k, lines along j,
+// post-phase / epilogue, coalesced store.  k_tf_i: the line of thread k runs along i at fixed (j, k), so loads and
+// stores are coalesced as they are and no shared memory is needed.
+template <int EPI>
+__device__ __forceinline__ void tf_epilogue(double2 acc, long long g, double *out, const FsEpilogue &ep)
+{
+  if (EPI == 0) {
+    reinterpret_cast<double2 *>(out)[g] = acc;
+  } else {
+    const double Q = acc.x / ep.scaleL / ep.scale3;
+    if (EPI == 4) reinterpret_cast<double2 *>(out)[g] = make_double2(Q, 0.);
+    if (EPI == 1) { ep.Qv[g] = Q; ep.f1[g] = ep.f[g] + ep.dt * Q * ep.nu; }
+    if (EPI == 2) ep.f1[g] = ep.f[g] + 0.5 * ep.dt * ep.Qv[g] * ep.nu + 0.5 * ep.dt * Q * ep.nu;
+    if (EPI == 3) ep.f1[g] = ep.f[g] + 0.5 * ep.Qv[g] * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
+  }
+}
+template <int N, int SIGN, bool IN_REAL, int EPI, bool PRE, bool POST>
+__global__ void __launch_bounds__(N) k_tf_jk(const double *__restrict__ in, double *__restrict__ out, PhaseTabs ph, FsEpilogue ep)
+{
+  constexpr int P = N + 1;
+  __shared__ double2 X[N * P];
+  const long long slab = blockIdx.x;                 // cell*N + i
+  const int i = (int)(slab % N), t = threadIdx.x;
+  #pragma unroll 4
+  for (int j = 0; j < N; j++) {
+    const long long g = slab * N * N + j * N + t;
+    double2 x = IN_REAL ? make_double2(in[g], 0.) : reinterpret_cast<const double2 *>(in)[g];
+    if (PRE) {
+      x = phase_mul(ph.pre[i + j + t], x);
+      if (ph.wt) { const double fac = ph.c3 * ph.wt[i] * ph.wt[j] * ph.wt[t]; x.x = __dmul_rn(fac, x.x); x.y = __dmul_rn(fac, x.y); }
+    }
+    X[j * P + t] = x;
+  }
+  __syncthreads();
+  double2 v[N];
+  #pragma unroll
+  for (int k = 0; k < N; k++) v[k] = X[t * P + k];          // row j = t
+  fc3::fftN<N, SIGN, N>(v);
+  #pragma unroll
+  for (int k = 0; k < N; k++) X[t * P + k] = v[k];
+  __syncthreads();
+  #pragma unroll
+  for (int j = 0; j < N; j++) v[j] = X[j * P + t];          // column k = t
+  fc3::fftN<N, SIGN, N>(v);
+  #pragma unroll
+  for (int j = 0; j < N; j++) {
+    double2 acc = v[j];
+    if (POST) acc = phase_mul(ph.post[(i * N + j) * N + t], acc);
+    tf_epilogue<EPI>(acc, slab * N * N + j * N + t, out, ep);
+  }
+}
+template <int N, int SIGN, bool PRE, bool POST>
+__global__ void __launch_bounds__(N) k_tf_i(const double2 *__restrict__ in, double2 *__restrict__ out, PhaseTabs ph)
+{
+  const long long cell = blockIdx.x / N; const int j = blockIdx.x % N, t = threadIdx.x;
+  double2 v[N];
+  #pragma unroll
+  for (int i = 0; i < N; i++) {
+    v[i] = in[((cell * N + i) * N + j) * N + t];
+    if (PRE) v[i] = phase_mul(ph.pre[i + j + t], v[i]);
+  }
+  fc3::fftN<N, SIGN, N>(v);
+  #pragma unroll
+  for (int i = 0; i < N; i++) {
+    double2 acc = v[i];
+    if (POST) acc = phase_mul(ph.post[(i * N + j) * N + t], acc);
+    out[((cell * N + i) * N + j) * N + t] = acc;
+  }
+}
+static bool lp_reg_lines(int N)
+{
+  static const bool dense_only = getenv("LPGPU_DFT_DENSE") != nullptr;   // developer knob: the shared-memory DFT kernels
+  return !dense_only && (N == 8 || N == 16 || N == 24 || N == 32);
+}
+
 // log2(N) when N is a power of two >= 8 and the block is whole warps (shuffle FFT lines), else 0 (dense N-point sums)
 static int lp_log2_pow2(int N)
 {
@@ -219,6 +296,16 @@ template <bool IN_REAL, int EPI, bool PRE, bool POST>
 static int launch_jk(lpgpu_ctx *c, const double *in, double *out, const double *Wm, int B, PhaseTabs ph, FsEpilogue ep)
 {
   const int N = c->p.N;
+  if (lp_reg_lines(N)) {
+    const bool fwd = Wm == c->d_Wfwd;
+#define LP_TF_JK(NN)                                                                                                          \
+    if (fwd) k_tf_jk<NN, -1, IN_REAL, EPI, PRE, POST><<<B * NN, NN, 0, c->stream>>>(in, out, ph, ep);                         \
+    else k_tf_jk<NN, +1, IN_REAL, EPI, PRE, POST><<<B * NN, NN, 0, c->stream>>>(in, out, ph, ep)
+    if (N == 32) { LP_TF_JK(32); } else if (N == 24) { LP_TF_JK(24); } else if (N == 16) { LP_TF_JK(16); } else { LP_TF_JK(8); }
+#undef LP_TF_JK
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
   const size_t smem = dft_smem(N, 3);
   auto kern = k_dft_jk<IN_REAL, EPI, PRE, POST>;
   LP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -230,6 +317,18 @@ template <bool PRE, bool POST>
 static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *Wm, int B, PhaseTabs ph)
 {
   const int N = c->p.N;
+  if (lp_reg_lines(N)) {
+    const bool fwd = Wm == c->d_Wfwd;
+    const double2 *i2 = reinterpret_cast<const double2 *>(in);
+    double2 *o2 = reinterpret_cast<double2 *>(out);
+#define LP_TF_I(NN)                                                                                   \
+    if (fwd) k_tf_i<NN, -1, PRE, POST><<<B * NN, NN, 0, c->stream>>>(i2, o2, ph);                     \
+    else k_tf_i<NN, +1, PRE, POST><<<B * NN, NN, 0, c->stream>>>(i2, o2, ph)
+    if (N == 32) { LP_TF_I(32); } else if (N == 24) { LP_TF_I(24); } else if (N == 16) { LP_TF_I(16); } else { LP_TF_I(8); }
+#undef LP_TF_I
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
   const size_t smem = dft_smem(N, 2);
   auto kern = k_dft_i<PRE, POST>;
   LP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -43,11 +43,17 @@ namespace fc3 {
 // ---- twiddles exp(+2 pi i t / M), t < M: __constant__ on the device (folded into c[bank][imm] operands once the
 // loops are unrolled), plain arrays on the host
 #ifdef __CUDACC__
+__device__ __constant__ double d_twc8[8] = LP_TWC_8, d_tws8[8] = LP_TWS_8;
+__device__ __constant__ double d_twc16[16] = LP_TWC_16, d_tws16[16] = LP_TWS_16;
+__device__ __constant__ double d_twc32[32] = LP_TWC_32, d_tws32[32] = LP_TWS_32;
 __device__ __constant__ double d_twc12[12] = LP_TWC_12, d_tws12[12] = LP_TWS_12;
 __device__ __constant__ double d_twc24[24] = LP_TWC_24, d_tws24[24] = LP_TWS_24;
 __device__ __constant__ double d_twc36[36] = LP_TWC_36, d_tws36[36] = LP_TWS_36;
 __device__ __constant__ double d_twc48[48] = LP_TWC_48, d_tws48[48] = LP_TWS_48;
 #endif
+static const double h_twc8[8] = LP_TWC_8, h_tws8[8] = LP_TWS_8;
+static const double h_twc16[16] = LP_TWC_16, h_tws16[16] = LP_TWS_16;
+static const double h_twc32[32] = LP_TWC_32, h_tws32[32] = LP_TWS_32;
 static const double h_twc12[12] = LP_TWC_12, h_tws12[12] = LP_TWS_12;
 static const double h_twc24[24] = LP_TWC_24, h_tws24[24] = LP_TWS_24;
 static const double h_twc36[36] = LP_TWC_36, h_tws36[36] = LP_TWS_36;
@@ -67,7 +73,7 @@ template <int M> struct Tw;
     static LP_HD double s(int t) { return h_tws##M[t]; }               \
   };
 #endif
-LP_TW_SPEC(12) LP_TW_SPEC(24) LP_TW_SPEC(36) LP_TW_SPEC(48)
+LP_TW_SPEC(8) LP_TW_SPEC(12) LP_TW_SPEC(16) LP_TW_SPEC(24) LP_TW_SPEC(32) LP_TW_SPEC(36) LP_TW_SPEC(48)
 
 LP_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 LP_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -111,9 +117,9 @@ LP_HD void dft4(double2 &a0, double2 &a1, double2 &a2, double2 &a3)
 template <int R, int SIGN>
 LP_HD void dftR(double2 *v)
 {
-  if (R == 2) dft2<SIGN>(v[0], v[1]);
-  if (R == 3) dft3<SIGN>(v[0], v[1], v[2]);
-  if (R == 4) dft4<SIGN>(v[0], v[1], v[2], v[3]);
+  if constexpr (R == 2) dft2<SIGN>(v[0], v[1]);
+  if constexpr (R == 3) dft3<SIGN>(v[0], v[1], v[2]);
+  if constexpr (R == 4) dft4<SIGN>(v[0], v[1], v[2], v[3]);
 }
 
 template <int L> struct Fac;
@@ -146,6 +152,38 @@ LP_HD void fft_small(double2 (&x)[L])
     if (R2 > 1) dftR<R2, SIGN>(v);
     #pragma unroll
     for (int k2 = 0; k2 < R2; k2++) x[k1 + R1 * k2] = v[k2];
+  }
+}
+
+// N-point DFT in registers for the shifted transforms fft3D / FS (N = 8, 16, 24, 32; any N = 2^a 3^b works), natural
+// order in and out, X[k] = sum_n x[n] exp(SIGN 2 pi i n k / N); twiddles from the size-TB table (N divides TB).
+template <int N> struct Rad { static constexpr int R1 = (N % 4 == 0) ? 4 : (N % 3 == 0) ? 3 : 2; };
+template <int N, int SIGN, int TB>
+LP_HD void fftN(double2 (&x)[N])
+{
+  if constexpr (N <= 4) {
+    dftR<N, SIGN>(x);
+  } else {
+    constexpr int R1 = Rad<N>::R1, R2 = N / R1;
+    double2 y[N];
+    #pragma unroll
+    for (int n2 = 0; n2 < R2; n2++) {
+      double2 v[R1];
+      #pragma unroll
+      for (int n1 = 0; n1 < R1; n1++) v[n1] = x[R2 * n1 + n2];
+      dftR<R1, SIGN>(v);
+      #pragma unroll
+      for (int k1 = 0; k1 < R1; k1++) y[k1 * R2 + n2] = mul_tw<TB, SIGN>(v[k1], (TB / N) * n2 * k1);
+    }
+    #pragma unroll
+    for (int k1 = 0; k1 < R1; k1++) {
+      double2 v[R2];
+      #pragma unroll
+      for (int n2 = 0; n2 < R2; n2++) v[n2] = y[k1 * R2 + n2];
+      fftN<R2, SIGN, TB>(v);
+      #pragma unroll
+      for (int k2 = 0; k2 < R2; k2++) x[k1 + R1 * k2] = v[k2];
+    }
   }
 }
 

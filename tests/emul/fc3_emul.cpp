@@ -104,3 +104,27 @@ extern "C" int fc3_direct(int N, int B, const double *fhat, const double *G7, co
   }
   return 0;
 }
+
+// in-register N-point DFT of fc3.cuh against the definition
+template <int N, int SIGN>
+static void run_fftN(const double *in, double *out)
+{
+  double2 x[N];
+  for (int i = 0; i < N; i++) x[i] = make_double2(in[2 * i], in[2 * i + 1]);
+  fc3::fftN<N, SIGN, N>(x);
+  for (int i = 0; i < N; i++) { out[2 * i] = x[i].x; out[2 * i + 1] = x[i].y; }
+}
+extern "C" int fc3_fftN(int N, int sign, const double *in, double *out)
+{
+  switch (N * sign) {
+    case 8: run_fftN<8, 1>(in, out); return 0;
+    case -8: run_fftN<8, -1>(in, out); return 0;
+    case 16: run_fftN<16, 1>(in, out); return 0;
+    case -16: run_fftN<16, -1>(in, out); return 0;
+    case 24: run_fftN<24, 1>(in, out); return 0;
+    case -24: run_fftN<24, -1>(in, out); return 0;
+    case 32: run_fftN<32, 1>(in, out); return 0;
+    case -32: run_fftN<32, -1>(in, out); return 0;
+  }
+  return 1;
+}

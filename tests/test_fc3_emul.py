@@ -40,3 +40,16 @@ def test_pipeline_matches_direct_sum(emul, N, B):
 def test_unsupported_size_is_refused(emul):
     z = np.zeros(8)
     assert emul.fc3_emulate(10, 1, z.ctypes.data_as(P), z.ctypes.data_as(P), z.ctypes.data_as(P), z.ctypes.data_as(P)) == 1
+
+
+@pytest.mark.parametrize("N", [8, 16, 24, 32])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_register_fft_matches_definition(emul, N, sign):
+    rng = np.random.default_rng(N + sign)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    xin = np.ascontiguousarray(np.stack([x.real, x.imag], axis=1))
+    out = np.zeros_like(xin)
+    assert emul.fc3_fftN(N, sign, xin.ctypes.data_as(P), out.ctypes.data_as(P)) == 0
+    k = np.arange(N)
+    want = np.exp(sign * 2j * np.pi * np.outer(k, k) / N) @ x
+    assert np.abs(out[:, 0] + 1j * out[:, 1] - want).max() < 1e-14 * np.abs(want).max() * N
