@@ -112,7 +112,8 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_alloc(&c->d_fhat, 2 * n3));
   A_(dev_alloc(&c->d_tmp, 2 * n3));
   for (int s = 0; s < 4; s++) A_(dev_alloc(&c->d_q[s], 2 * n3));
-  A_(dev_alloc(&c->d_lam, (size_t)5 * 8 * c->cap_cells + 8));   // conservation partials: 8 chunks x 5 per cell
+  A_(dev_alloc(&c->d_lam, (size_t)5 * 8 * c->cap_cells + 8));
+  A_(dev_alloc(&c->d_cpart, (size_t)5 * p->N * c->cap_cells));   // conservation partials: 8 chunks x 5 per cell
   A_(dev_alloc(&c->d_B, (size_t)2 * c->cap_cells * p->N * 4 * p->Nv * p->Nv));
 #undef A_
   if (rc != LPGPU_OK) { lpgpu_finalize(c); return rc; }
@@ -127,7 +128,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   cudaDeviceSynchronize();
   double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
-                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt};
+                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart};
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
@@ -221,13 +222,32 @@ int lpgpu_advect_rk3(lpgpu_ctx *c)
 // ---- collision ------------------------------------------------------------------------------
 static int eval_async(lpgpu_ctx *c, const double *f, double *q, int B)
 {
-  LP_TRY(lp_launch_fft3d(c, f, true, c->d_fhat, B));
-  LP_TRY(lp_launch_computeQ(c, c->d_fhat, q, B));
+  if (lp_fc3_available(c)) {
+    // fft3D's last pass (along i) and its post-phase run inside the first ComputeQ kernel; fhat is never stored
+    LP_TRY(lp_launch_fft3d_jk(c, f, true, B));
+    LP_TRY(lp_launch_computeQ_fftconv(c, c->d_tmp, q, B, true, c->d_cpart));
+    return lp_launch_conserve_from_parts(c, q, c->d_cpart, B);
+  } else {
+    LP_TRY(lp_launch_fft3d(c, f, true, c->d_fhat, B));
+    LP_TRY(lp_launch_computeQ(c, c->d_fhat, q, B));
+  }
   return lp_launch_conserve(c, q, B);
 }
 static int collide_async(lpgpu_ctx *c)
 {
   const int B = c->ncell;
+  if (lp_fc3_available(c)) {
+    // fused chain: per stage  fft3D(j,k) -> [fft3D(i) + z-lines] -> F2 -> [inverse z + conservation dots]
+    //                         -> [conservation correction + FS(i)] -> FS(j,k) + RK stage update
+    LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, B));
+    for (int s = 0; s <= 3; s++) {
+      LP_TRY(lp_launch_fft3d_jk(c, s == 0 ? c->d_f : c->d_f1, true, B));
+      LP_TRY(lp_launch_computeQ_fftconv(c, c->d_tmp, c->d_q[s], B, true, c->d_cpart));
+      if (s < 3) LP_TRY(lp_launch_fs_conserving(c, c->d_q[s], c->d_cpart, s + 1, B));
+      else LP_TRY(lp_launch_conserve_from_parts(c, c->d_q[s], c->d_cpart, B));
+    }
+    return lp_launch_project(c, c->d_U[0], B);
+  }
   LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, B));
   LP_TRY(eval_async(c, c->d_f, c->d_q[0], B));
   for (int s = 1; s <= 3; s++) {

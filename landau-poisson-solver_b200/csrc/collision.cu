@@ -93,23 +93,6 @@ int lp_launch_sample(lpgpu_ctx *c, const double *planes, double *f, int ncell)
 //
 // EPI: 0 complex out; 1..3 = FS real part + RK stage update (RK4_Inhomo/RK4_Homo,
 // collisionRoutines_1.cpp:910-941 / 1094-1123); 4 = FS real part stored as (re, 0).
-struct FsEpilogue {
-  double scaleL, scale3, dt, nu;
-  const double *f;   // stage-0 samples
-  double *Qv;        // first-stage Q (written in mode 1, read in 2,3)
-  double *f1;        // stage input for the next ComputeQ
-};
-struct PhaseTabs {
-  const double2 *pre;    // [3N-2]  pre-phase by i+j+k            (null: none)
-  const double2 *post;   // [N^3]   post-phase by (i,j,k)         (null: none)
-  const double *wt;      // [N]     trapezoid weights, forward pre-factor only (null: none)
-  double c3;             // scale3*h_v^3 (forward pre-factor)
-};
-// (c + i s) * (x + i y) exactly as the reference writes it: cos*re - sin*im, cos*im + sin*re
-__device__ __forceinline__ double2 phase_mul(double2 cs, double2 x)
-{
-  return make_double2(__dsub_rn(__dmul_rn(cs.x, x.x), __dmul_rn(cs.y, x.y)), __dadd_rn(__dmul_rn(cs.x, x.y), __dmul_rn(cs.y, x.x)));
-}
 __device__ __forceinline__ int bitrev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - bits)); }
 // N-point decimation-in-time FFT across N consecutive lanes (N = 2^k <= 32): lane l supplies element bitrev(l) and
 // returns output l.  W[t] = W_N^t carries the sign of the transform.  All 32 lanes of the warp must call it.
@@ -215,7 +198,7 @@ __device__ __forceinline__ void tf_epilogue(double2 acc, long long g, double *ou
   if (EPI == 0) {
     reinterpret_cast<double2 *>(out)[g] = acc;
   } else {
-    const double Q = acc.x / ep.scaleL / ep.scale3;
+    const double Q = acc.x * ep.inv;
     if (EPI == 4) reinterpret_cast<double2 *>(out)[g] = make_double2(Q, 0.);
     if (EPI == 1) { ep.Qv[g] = Q; ep.f1[g] = ep.f[g] + ep.dt * Q * ep.nu; }
     if (EPI == 2) ep.f1[g] = ep.f[g] + 0.5 * ep.dt * ep.Qv[g] * ep.nu + 0.5 * ep.dt * Q * ep.nu;
@@ -338,13 +321,19 @@ static int launch_i(lpgpu_ctx *c, const double *in, double *out, const double *W
   return LPGPU_OK;
 }
 
-int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, int B)
+// first pass of fft3D only (pre-phase, transforms along k and j) into c->d_tmp; the fused ComputeQ (fftconv.cu, F1)
+// runs the pass along i and the post-phase itself
+int lp_launch_fft3d_jk(lpgpu_ctx *c, const double *in, bool in_real, int B)
 {
   FsEpilogue ep = {};
   PhaseTabs pre = {reinterpret_cast<const double2 *>(c->d_pre_fwd), nullptr, c->d_wt, c->tab.c3_fwd};
+  return in_real ? launch_jk<true, 0, true, false>(c, in, c->d_tmp, c->d_Wfwd, B, pre, ep)
+                 : launch_jk<false, 0, true, false>(c, in, c->d_tmp, c->d_Wfwd, B, pre, ep);
+}
+int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, int B)
+{
   PhaseTabs post = {nullptr, reinterpret_cast<const double2 *>(c->d_post_fwd), nullptr, 0.};
-  int rc = in_real ? launch_jk<true, 0, true, false>(c, in, c->d_tmp, c->d_Wfwd, B, pre, ep)
-                   : launch_jk<false, 0, true, false>(c, in, c->d_tmp, c->d_Wfwd, B, pre, ep);
+  int rc = lp_launch_fft3d_jk(c, in, in_real, B);
   if (rc) return rc;
   return launch_i<false, true>(c, c->d_tmp, out, c->d_Wfwd, B, post);
 }
@@ -352,7 +341,7 @@ int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, i
 int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B)
 {
   FsEpilogue ep;
-  ep.scaleL = c->tab.scaleL; ep.scale3 = c->tab.scale3;
+  ep.scaleL = c->tab.scaleL; ep.scale3 = c->tab.scale3; ep.inv = 1. / c->tab.scaleL / c->tab.scale3;
   ep.dt = c->p.dt; ep.nu = c->p.nu; ep.f = c->d_f; ep.Qv = c->d_Qv; ep.f1 = c->d_f1;
   PhaseTabs pre = {reinterpret_cast<const double2 *>(c->d_pre_inv), nullptr, nullptr, 0.};
   PhaseTabs post = {nullptr, reinterpret_cast<const double2 *>(c->d_post_inv), nullptr, 0.};
@@ -410,7 +399,6 @@ __global__ void __launch_bounds__(128) k_computeQ_simple(const double2 *__restri
 
 int lp_launch_computeQ_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B);   // computeq.cu
 
-int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B);   // fftconv.cu
 
 int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B)
 {
@@ -418,7 +406,7 @@ int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B)
   // 1 = simple direct kernel, 2 = FFT convolutions, 3 = tiled direct sum
   const int variant = c->p.computeq_variant;
   if (variant == 0 || variant == 2) {
-    int rc = lp_launch_computeQ_fftconv(c, fhat, q, B);
+    int rc = lp_launch_computeQ_fftconv(c, fhat, q, B, false, nullptr);
     if (rc != -1) return rc;   // -1: N is not a power of two -> direct kernels
   }
   if (variant != 1) {
@@ -501,13 +489,13 @@ __global__ void __launch_bounds__(256) k_conserve_dots(const double2 *__restrict
   if (tid < 5) { double v = 0.; for (int w = 0; w < 8; w++) v += red[tid][w]; part[(cell * LP_CONS_CH + ch) * 5 + tid] = v; }
 }
 __global__ void __launch_bounds__(256) k_conserve_apply(double2 *__restrict__ q, const double *__restrict__ C5,
-                                                        const double *__restrict__ CCt, const double *__restrict__ part, int N3)
+                                                        const double *__restrict__ CCt, const double *__restrict__ part, int N3, int nparts)
 {
   __shared__ double lam[5];
   const long long cell = blockIdx.x; const int ch = blockIdx.y;
   if (threadIdx.x == 0) {
     double tot[5];
-    for (int m = 0; m < 5; m++) { double v = 0.; for (int k = 0; k < LP_CONS_CH; k++) v += part[(cell * LP_CONS_CH + k) * 5 + m]; tot[m] = v; }
+    for (int m = 0; m < 5; m++) { double v = 0.; for (int k = 0; k < nparts; k++) v += part[(cell * nparts + k) * 5 + m]; tot[m] = v; }
     for (int a = 0; a < 5; a++) { double v = 0.; for (int b = 0; b < 5; b++) v += CCt[b + a * 5] * tot[b]; lam[a] = v; }
   }
   __syncthreads();
@@ -530,9 +518,77 @@ int lp_launch_conserve(lpgpu_ctx *c, double *q, int B)
   }
   k_conserve_dots<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(q), c->d_C5, c->d_lam, c->N3);
   LP_LAUNCHED(c);
-  k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->d_lam, c->N3);
+  k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->d_lam, c->N3, LP_CONS_CH);
   LP_LAUNCHED(c);
   return LPGPU_OK;
+}
+
+int lp_launch_conserve_from_parts(lpgpu_ctx *c, double *q, const double *part, int B)
+{
+  k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, part, c->N3, c->p.N);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// conserveAllMoments_Normal folded into the first pass of FS: fold the partial dot products (fixed order), lambda =
+// CCt-applied, correct this thread's line of q in place (the projection reads the conserved spectra later), then
+// pre-phase and transform along i as k_tf_i does.
+template <int N>
+__global__ void __launch_bounds__(N) k_tf_i_conserve(double2 *__restrict__ q, double2 *__restrict__ out, PhaseTabs ph,
+                                                     const double *__restrict__ C5, const double *__restrict__ CCt, const double *__restrict__ part)
+{
+  __shared__ double tot[5];
+  const long long cell = blockIdx.x / N; const int j = blockIdx.x % N, t = threadIdx.x;
+  constexpr int N3 = N * N * N;
+  if (t < 5) { double v = 0.; for (int k = 0; k < N; k++) v += part[(cell * N + k) * 5 + t]; tot[t] = v; }
+  __syncthreads();
+  double lam[5];
+  #pragma unroll
+  for (int a = 0; a < 5; a++) { double v = 0.; for (int b = 0; b < 5; b++) v += CCt[b + a * 5] * tot[b]; lam[a] = v; }
+  double2 v[N];
+  #pragma unroll
+  for (int i = 0; i < N; i++) {
+    const int idx = (i * N + j) * N + t;
+    double2 x = q[cell * N3 + idx];
+    x.x -= (C5[idx] * lam[0] + C5[4 * N3 + idx] * lam[4]);
+    x.y -= (C5[N3 + idx] * lam[1] + C5[2 * N3 + idx] * lam[2] + C5[3 * N3 + idx] * lam[3]);
+    q[cell * N3 + idx] = x;
+    v[i] = phase_mul(ph.pre[i + j + t], x);
+  }
+  fc3::fftN<N, +1, N>(v);
+  #pragma unroll
+  for (int i = 0; i < N; i++) out[cell * N3 + (i * N + j) * N + t] = v[i];
+}
+static int launch_fs_second(lpgpu_ctx *c, int mode, double *out_complex, int B, FsEpilogue ep)
+{
+  PhaseTabs post = {nullptr, reinterpret_cast<const double2 *>(c->d_post_inv), nullptr, 0.};
+  switch (mode) {
+    case 0: return launch_jk<false, 4, false, true>(c, c->d_tmp, out_complex, c->d_Winv, B, post, ep);
+    case 1: return launch_jk<false, 1, false, true>(c, c->d_tmp, nullptr, c->d_Winv, B, post, ep);
+    case 2: return launch_jk<false, 2, false, true>(c, c->d_tmp, nullptr, c->d_Winv, B, post, ep);
+    case 3: return launch_jk<false, 3, false, true>(c, c->d_tmp, nullptr, c->d_Winv, B, post, ep);
+  }
+  lp_set_error("lp_launch_fs: bad mode");
+  return LPGPU_EINVAL;
+}
+int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mode, int B)
+{
+  const int N = c->p.N;
+  if (!lp_reg_lines(N)) {          // dense transforms: correction and FS as separate launches
+    int rc = lp_launch_conserve_from_parts(c, q, part, B);
+    return rc ? rc : lp_launch_fs(c, q, mode, nullptr, B);
+  }
+  FsEpilogue ep;
+  ep.scaleL = c->tab.scaleL; ep.scale3 = c->tab.scale3; ep.inv = 1. / c->tab.scaleL / c->tab.scale3;
+  ep.dt = c->p.dt; ep.nu = c->p.nu; ep.f = c->d_f; ep.Qv = c->d_Qv; ep.f1 = c->d_f1;
+  PhaseTabs pre = {reinterpret_cast<const double2 *>(c->d_pre_inv), nullptr, nullptr, 0.};
+  double2 *q2 = reinterpret_cast<double2 *>(q), *o2 = reinterpret_cast<double2 *>(c->d_tmp);
+  if (N == 32) k_tf_i_conserve<32><<<B * 32, 32, 0, c->stream>>>(q2, o2, pre, c->d_C5, c->d_CCt, part);
+  else if (N == 24) k_tf_i_conserve<24><<<B * 24, 24, 0, c->stream>>>(q2, o2, pre, c->d_C5, c->d_CCt, part);
+  else if (N == 16) k_tf_i_conserve<16><<<B * 16, 16, 0, c->stream>>>(q2, o2, pre, c->d_C5, c->d_CCt, part);
+  else k_tf_i_conserve<8><<<B * 8, 8, 0, c->stream>>>(q2, o2, pre, c->d_C5, c->d_CCt, part);
+  LP_LAUNCHED(c);
+  return launch_fs_second(c, mode, nullptr, B, ep);
 }
 
 // ---------------------------------------------------------------------------------------------

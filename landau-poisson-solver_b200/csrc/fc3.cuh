@@ -279,7 +279,17 @@ struct F1 {
     }
     for (int i = tid; i < N; i += NT) sE[i] = E[i];
   }
-  static LP_HD void lines(int tid, int cell, int y, const double *Gt, const double2 *FS, const double *sE, double2 *Z)
+  // stage the seven kernel-symbol slabs of this y into shared memory: Gs[a][z][x]
+  static LP_HD void issue_g(int tid, int y, const double *Gt, double *Gs)
+  {
+    constexpr int H = N * N / 2;   // double2 chunks per slab
+    for (int idx = tid; idx < 7 * H; idx += NT) {
+      const int a = idx / H, e = idx % H;
+      cp16(reinterpret_cast<double2 *>(Gs) + idx, reinterpret_cast<const double2 *>(Gt + ((long long)a * N + y) * N * N) + e);
+    }
+  }
+  // Gs + a*astride + z*N + x: the slab of array a (shared: astride = N*N; straight from Gt + y*N*N: astride = N^3)
+  static LP_HD void lines(int tid, int cell, int y, const double *Gs, long long astride, const double2 *FS, const double *sE, double2 *Z)
   {
     const int x = tid % N, r = (tid / N) % 3, slot = tid / (3 * N);
     #pragma unroll 1
@@ -287,10 +297,10 @@ struct F1 {
       const int a = round * 2 + slot;
       double2 a0[L], a1[L], yv[L];
       if (a < 7) {
-        const double *g = Gt + (((long long)a * N + y) * N) * N + x;
+        const double *g = Gs + a * astride + x;
         #pragma unroll
         for (int l = 0; l < L; l++) {
-          const double g0 = g[(long long)l * N], g1 = g[(long long)(l + L) * N];
+          const double g0 = g[l * N], g1 = g[(l + L) * N];
           const double2 f0 = FS[x * P + l], f1 = FS[x * P + l + L];
           a0[l] = make_double2(g0 * f0.x, g0 * f0.y);
           a1[l] = make_double2(g1 * f1.x, g1 * f1.y);
@@ -431,14 +441,23 @@ struct F3 {
     #pragma unroll
     for (int l = 0; l < L; l++) T3[(rz * L + l) * PN + yo] = c[l];
   }
-  static LP_HD void store(int tid, int cell, int xo, const double2 *T3, double2 *q)
+  // C5 (nullable): the five conservation rows, planar [m][N^3]; s accumulates this thread's share of the five dot
+  // products of conserveAllMoments_Normal (conservationRoutines.cpp:137-144) over the values it stores
+  static LP_HD void store(int tid, int cell, int xo, const double2 *T3, double2 *q, const double *C5, double (&s)[5])
   {
     const double sc = 1.0 / ((double)M * M * M);
-    double2 *o = q + (long long)cell * N * N * N + (long long)xo * N * N;
+    constexpr int N3 = N * N * N;
+    double2 *o = q + (long long)cell * N3 + (long long)xo * N * N;
     for (int idx = tid; idx < N * N; idx += NT) {
-      const int yo = idx / N, zo = idx % N, l = zo % L, s = zo / L + 1;
-      const double2 v = inv_combine(T3[l * PN + yo], T3[(L + l) * PN + yo], T3[(2 * L + l) * PN + yo], s);
-      o[idx] = make_double2(v.x * sc, v.y * sc);
+      const int yo = idx / N, zo = idx % N, l = zo % L, sh = zo / L + 1;
+      const double2 v = inv_combine(T3[l * PN + yo], T3[(L + l) * PN + yo], T3[(2 * L + l) * PN + yo], sh);
+      const double2 w = make_double2(v.x * sc, v.y * sc);
+      o[idx] = w;
+      if (C5) {
+        const int g = xo * N * N + idx;
+        s[0] += w.x * C5[g]; s[1] += w.y * C5[N3 + g]; s[2] += w.y * C5[2 * N3 + g];
+        s[3] += w.y * C5[3 * N3 + g]; s[4] += w.x * C5[4 * N3 + g];
+      }
     }
   }
 };

@@ -462,17 +462,35 @@ int launch_regs(lpgpu_ctx *c, const double2 *fh, double2 *F1, double2 *F2, doubl
 
 // ---------------------------------------------------------------------------------------------------------
 // Register-resident pipeline (fc3.cuh): F1 z-lines -> F2 (y, x, product, inverse x, inverse y) -> F3 inverse z.
-template <int L>
-__global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__restrict__ fhat, const double *__restrict__ Gt,
-                                                           const double *__restrict__ E, double2 *__restrict__ Z)
+// FUSED: `in` is the output of the first fft3D pass (lp_launch_fft3d_jk); the N lines along i of this y slab are
+// transformed here (one thread per line, as k_tf_i) and post-phased straight into the shared fhat slab -- fhat
+// itself never goes to memory.  The kernel symbols of this y are staged with cp.async while that happens.
+template <int L, bool FUSED>
+__global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__restrict__ in, const double *__restrict__ Gt,
+                                                           const double *__restrict__ E, double2 *__restrict__ Z, const double2 *__restrict__ post)
 {
   typedef fc3::F1<L> K;
-  __shared__ double2 FS[K::SMEM_C2];
-  __shared__ double sE[K::N];
+  constexpr int N = K::N;
+  extern __shared__ double2 smf[];
+  double2 *FS = smf;
+  double *Gs = reinterpret_cast<double *>(FS + K::SMEM_C2), *sE = Gs + 7 * N * N;
   const int y = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
-  K::load(tid, cell, y, fhat, E, FS, sE);
+  K::issue_g(tid, y, Gt, Gs);
+  if (FUSED) {
+    if (tid < N) {
+      double2 v[N];
+      #pragma unroll
+      for (int i = 0; i < N; i++) v[i] = in[(((long long)cell * N + i) * N + y) * N + tid];
+      fc3::fftN<N, -1, N>(v);
+      #pragma unroll
+      for (int i = 0; i < N; i++) FS[i * K::P + tid] = phase_mul(post[(i * N + y) * N + tid], v[i]);
+    } else if (tid < 2 * N) sE[tid - N] = E[tid - N];
+  } else {
+    K::load(tid, cell, y, in, E, FS, sE);
+  }
+  fc3::cp_wait_all();
   __syncthreads();
-  K::lines(tid, cell, y, Gt, FS, sE, Z);
+  K::lines(tid, cell, y, Gs, N * N, FS, sE, Z);
 }
 template <int L>
 __global__ void __launch_bounds__(fc3::F2<L>::NT, 1) k_fc3_f2(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
@@ -614,35 +632,56 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   __syncthreads();
   K::store(tid, cell, kz, IN, C);
 }
+// part (nullable): per (cell, xo) partial dot products of the conservation rows with the stored spectrum,
+// [cell][xo][5]; folded in a fixed order by the kernels that apply the correction (collision.cu)
 template <int L>
-__global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__restrict__ C, double2 *__restrict__ q)
+__global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__restrict__ C, double2 *__restrict__ q,
+                                                           const double *__restrict__ C5, double *__restrict__ part)
 {
   typedef fc3::F3<L> K;
   __shared__ double2 T3[K::SMEM_C2];
+  __shared__ double red[5][4];
   const int xo = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
   K::zinverse(tid, cell, xo, C, T3);
   __syncthreads();
-  K::store(tid, cell, xo, T3, q);
+  double s[5] = {0., 0., 0., 0., 0.};
+  K::store(tid, cell, xo, T3, q, part ? C5 : nullptr, s);
+  if (part) {
+    const int lane = tid & 31, wid = tid >> 5, nw = (K::NT + 31) / 32;
+    #pragma unroll
+    for (int m = 0; m < 5; m++) {
+      double v = s[m];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) red[m][wid] = v;
+    }
+    __syncthreads();
+    if (tid < 5) { double v = 0.; for (int w = 0; w < nw; w++) v += red[tid][w]; part[((long long)cell * K::N + xo) * 5 + tid] = v; }
+  }
 }
 template <int L>
-int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb)
+int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb, bool fused_i, double *part)
 {
   typedef fc3::F2<L> K2;
   constexpr int N = 2 * L, M = 3 * L;
   const size_t smem2 = (size_t)(K2::IN_C2 + K2::Y_C2) * sizeof(double2) + N * sizeof(double);
+  const size_t smem1 = (size_t)fc3::F1<L>::SMEM_C2 * sizeof(double2) + (size_t)(7 * N * N + N) * sizeof(double);
   if (!c->fc3_attr) {
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     LP_CUDA(cudaFuncSetAttribute(k_fc3_f2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     if (L == 16) LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     c->fc3_attr = true;
   }
   const double *E = c->d_Etab + LP_ETAB_PAD;
-  k_fc3_f1<L><<<dim3(N, nb), fc3::F1<L>::NT, 0, c->stream>>>(fh, c->d_Gt, E, Z);
+  const double2 *post = reinterpret_cast<const double2 *>(c->d_post_fwd);
+  if (fused_i) k_fc3_f1<L, true><<<dim3(N, nb), fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
+  else k_fc3_f1<L, false><<<dim3(N, nb), fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
   LP_LAUNCHED(c);
   static const bool no_tmem = getenv("LPGPU_FC_NO_TMEM") != nullptr;   // developer knob: accumulators in registers, 1 CTA per SM
   if (L == 16 && !no_tmem) k_fc3_f2_tmem<<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
   else k_fc3_f2<L><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
   LP_LAUNCHED(c);
-  k_fc3_f3<L><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo);
+  k_fc3_f3<L><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo, c->d_C5, part);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -660,8 +699,20 @@ bool make_plan(int M, FcPlan &pl)
 } // namespace
 
 // returns -1 when M = 3N/2 is not of the form 2^a 3^b (caller uses the tiled direct kernel)
-int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B)
+static bool fc3_knobs_off()
 {
+  static const bool off = getenv("LPGPU_FFT_GENERIC") != nullptr || getenv("LPGPU_FC_OLD") != nullptr;
+  return off;
+}
+bool lp_fc3_available(const lpgpu_ctx *c)
+{
+  const int N = c->p.N, v = c->p.computeq_variant;
+  return (v == 0 || v == 2) && !fc3_knobs_off() && (N == 32 || N == 24 || N == 16 || N == 8);
+}
+// fused_i: `fhat` is the output of lp_launch_fft3d_jk (only valid when lp_fc3_available)
+int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part)
+{
+  if ((fused_i || part) && !lp_fc3_available(c)) { lp_set_error("fused ComputeQ needs the fc3 pipeline"); return LPGPU_EINVAL; }
   const int N = c->p.N, M = 3 * N / 2;
   FcPlan pl;
   if ((N & 1) || !make_plan(M, pl)) return -1;
@@ -707,8 +758,9 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     static const bool generic_only = getenv("LPGPU_FFT_GENERIC") != nullptr;   // developer knob: force the shared-memory stages
     static const bool old_regs = getenv("LPGPU_FC_OLD") != nullptr;            // developer knob: the shuffle-line kernels
     if (!generic_only && !old_regs && (N == 32 || N == 24 || N == 16 || N == 8)) {
-      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb)
-             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb) : launch_fc3<4>(c, fh, F1, F2, qo, nb);
+      double *pp = part ? part + (size_t)b0 * N * 5 : nullptr;
+      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb, fused_i, pp) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb, fused_i, pp)
+             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb, fused_i, pp) : launch_fc3<4>(c, fh, F1, F2, qo, nb, fused_i, pp);
       if (rc != LPGPU_OK) return rc;
       continue;
     }

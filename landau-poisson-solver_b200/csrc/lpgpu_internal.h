@@ -50,6 +50,7 @@ struct lpgpu_ctx {
   double *d_fhat, *d_tmp;                  // complex N^3
   double *d_q[4];                          // complex N^3: qHat, Q1_fft..Q3_fft
   double *d_lam;                           // 5 per cell
+  double *d_cpart;                         // [cell][N][5] partial conservation dots written by the fused ComputeQ
   double *d_B;                             // projection intermediate: ncell*N*4*Nv^2 complex
   size_t cap_cells;        // capacity (in cells) of the collision work arrays
   // ---- FFT-convolution variant of ComputeQ (allocated on first use)
@@ -73,11 +74,42 @@ void lp_set_error(const std::string &s);
     }                                                                                       \
   } while (0)
 
+#ifdef __CUDACC__
+// ---- shifted-transform plumbing shared by collision.cu and fftconv.cu
+struct FsEpilogue {
+  double scaleL, scale3, dt, nu;
+  double inv;        // 1/(scaleL*scale3): the register-line kernels multiply instead of dividing twice
+  const double *f;   // stage-0 samples
+  double *Qv;        // first-stage Q (written in mode 1, read in 2,3)
+  double *f1;        // stage input for the next ComputeQ
+};
+struct PhaseTabs {
+  const double2 *pre;    // [3N-2]  pre-phase by i+j+k            (null: none)
+  const double2 *post;   // [N^3]   post-phase by (i,j,k)         (null: none)
+  const double *wt;      // [N]     trapezoid weights, forward pre-factor only (null: none)
+  double c3;             // scale3*h_v^3 (forward pre-factor)
+};
+// (c + i s) * (x + i y) exactly as the reference writes it: cos*re - sin*im, cos*im + sin*re
+__device__ __forceinline__ double2 phase_mul(double2 cs, double2 x)
+{
+  return make_double2(__dsub_rn(__dmul_rn(cs.x, x.x), __dmul_rn(cs.y, x.y)), __dadd_rn(__dmul_rn(cs.x, x.y), __dmul_rn(cs.y, x.x)));
+}
+#endif
+
 // ---- kernel launchers (collision.cu) -- all asynchronous on c->stream
 int lp_launch_aos_to_planes(lpgpu_ctx *c, const double *aos, double *planes);
 int lp_launch_planes_to_aos(lpgpu_ctx *c, const double *planes, double *aos);
 int lp_launch_sample(lpgpu_ctx *c, const double *planes, double *f, int ncell);
 int lp_launch_fft3d(lpgpu_ctx *c, const double *in, bool in_real, double *out, int B);
+int lp_launch_fft3d_jk(lpgpu_ctx *c, const double *in, bool in_real, int B);
+// true when ComputeQ runs as the fused FFT-convolution pipeline that takes the output of lp_launch_fft3d_jk
+bool lp_fc3_available(const lpgpu_ctx *c);
+// part (nullable, fc3 only): receives the [cell][N][5] partial conservation dot products of the unconserved spectrum
+int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part);
+// conservation correction from those partials (in place)
+int lp_launch_conserve_from_parts(lpgpu_ctx *c, double *q, const double *part, int B);
+// FS whose first pass also applies the conservation correction from `part` to q (in place) before transforming
+int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mode, int B);
 // FS + RK-stage epilogue.  mode 0: plain (writes complex out, imag 0); 1..3: stage updates of f1
 int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B);
 int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B);

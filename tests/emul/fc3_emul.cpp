@@ -21,11 +21,12 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
   {
     typedef F1<L> K;
     std::vector<double2> FS(K::SMEM_C2);
-    std::vector<double> sE(N);
+    std::vector<double> sE(N), Gs((size_t)7 * N * N);
     for (int cell = 0; cell < B; cell++)
       for (int y = 0; y < N; y++) {
+        for (int t = 0; t < K::NT; t++) K::issue_g(t, y, Gt.data(), Gs.data());
         for (int t = 0; t < K::NT; t++) K::load(t, cell, y, fhat, E, FS.data(), sE.data());
-        for (int t = 0; t < K::NT; t++) K::lines(t, cell, y, Gt.data(), FS.data(), sE.data(), Z.data());
+        for (int t = 0; t < K::NT; t++) K::lines(t, cell, y, Gs.data(), N * N, FS.data(), sE.data(), Z.data());
       }
   }
   {
@@ -54,7 +55,8 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
     for (int cell = 0; cell < B; cell++)
       for (int xo = 0; xo < N; xo++) {
         for (int t = 0; t < K::NT; t++) K::zinverse(t, cell, xo, C.data(), T3.data());
-        for (int t = 0; t < K::NT; t++) K::store(t, cell, xo, T3.data(), q);
+        double dummy[5] = {0., 0., 0., 0., 0.};
+        for (int t = 0; t < K::NT; t++) K::store(t, cell, xo, T3.data(), q, nullptr, dummy);
       }
   }
 }
