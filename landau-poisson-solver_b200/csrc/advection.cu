@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_field_reduce(const double *__restrict__
 }
 // large velocity grids: LP_FR_CH blocks per x cell (one block per cell would use ncell of 148 SMs), partials
 // folded in a fixed order
-#define LP_FR_CH 8
+#define LP_FR_CH 32
 __global__ void __launch_bounds__(256) k_field_reduce_part(const double *__restrict__ planes, double *__restrict__ part, int sv)
 {
   __shared__ double red[2 * 32];
@@ -92,32 +92,37 @@ int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes)
 // intE2 = Int_E2nd (advection_1.cpp:419-429) from the gathered (m_q, s_q), q = 0..Nx-1.  The scan is
 // Nx long (<= a few hundred) and sequential on purpose: ce is a catastrophic cancellation
 // (Lx/2 - O(Lx/2)), so every GPU evaluates it in the same fixed order.
-__global__ void k_field_scan(const double *__restrict__ ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
-                             double dx, double Lx)
+__global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
+                                                    double dx, double Lx)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double P = 0., acc = 0.;
-  for (int q = 0; q < Nx; q++) { const double m = ms_all[2 * q], s = ms_all[2 * q + 1]; acc += P + 0.5 * m - s / 12.; P += m; }
-  const double ce = 0.5 * Lx - acc * dx * dx / Lx;
-  fld[0] = ce;
-  P = 0.;
-  for (int q = 0; q < Nx; q++) {
-    const double m = ms_all[2 * q], s = ms_all[2 * q + 1];
-    if (q >= x_begin && q < x_begin + x_count) {
-      const double xi = (q + 0.5) * dx, xl = ((q - 0.5) + 0.5) * dx, c2 = s * dx / 2., cp = dx * P;
-      double *o = fld + 1 + 4 * (q - x_begin);
-      o[0] = cp;
-      o[1] = -ce * dx - (P + 0.5 * m - s / 12.) * dx * dx + xi * dx;
-      o[2] = (1 - m) * dx * dx / 12.;
-      o[3] = (-cp - ce + (m * xl + 0.25 * c2)) * dx / 12. + (1 - m) * dx * xi / 12. - c2 * dx / 80.;
-    }
-    P += m;
+  extern __shared__ double sms[];          // m[Nx] | s/12 [Nx] | prefix P[Nx]
+  double *sm = sms, *s12 = sms + Nx, *sP = sms + 2 * Nx;
+  __shared__ double s_ce;
+  for (int q = threadIdx.x; q < Nx; q += blockDim.x) { sm[q] = ms_all[2 * q]; s12[q] = ms_all[2 * q + 1] / 12.; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the serial part keeps the summation order of the one-thread scan: only additions are left on the chain
+    double P = 0., acc = 0.;
+    for (int q = 0; q < Nx; q++) { sP[q] = P; acc += P + 0.5 * sm[q] - s12[q]; P += sm[q]; }
+    s_ce = 0.5 * Lx - acc * dx * dx / Lx;
+    fld[0] = s_ce;
+  }
+  __syncthreads();
+  const double ce = s_ce;
+  for (int q = x_begin + threadIdx.x; q < x_begin + x_count; q += blockDim.x) {
+    const double m = sm[q], s = ms_all[2 * q + 1], P = sP[q];
+    const double xi = (q + 0.5) * dx, xl = ((q - 0.5) + 0.5) * dx, c2 = s * dx / 2., cp = dx * P;
+    double *o = fld + 1 + 4 * (q - x_begin);
+    o[0] = cp;
+    o[1] = -ce * dx - (P + 0.5 * m - s12[q]) * dx * dx + xi * dx;
+    o[2] = (1 - m) * dx * dx / 12.;
+    o[3] = (-cp - ce + (m * xl + 0.25 * c2)) * dx / 12. + (1 - m) * dx * xi / 12. - c2 * dx / 80.;
   }
 }
 int lp_launch_field_scan(lpgpu_ctx *c)
 {
   const double dx = c->p.Lx / c->p.Nx;
-  k_field_scan<<<1, 32, 0, c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx);
+  k_field_scan<<<1, 256, (size_t)3 * c->p.Nx * sizeof(double), c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -130,7 +135,7 @@ int lp_launch_field_scan(lpgpu_ctx *c)
 //   stage 2: U  = 1/3 U + 2/3 U2 + 2/3 dt H(U2)
 struct DgParams {
   int Nv, sv, ncell;
-  double dv, dx, dt, scalev, Lv;
+  double dv, dx, dt, scalev, Lv, inv_dxs;
 };
 template <int STAGE>
 __global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin, const double *__restrict__ U0,
@@ -140,6 +145,9 @@ __global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin
   if (t >= (long long)P.ncell * P.sv) return;
   const int sv = P.sv, Nv = P.Nv, NN = Nv * Nv;
   const long long cell = t / sv; const int j = (int)(t % sv), j1 = j / NN;
+  // the reference's divisions by 12, 720, dx*scalev ... are multiplications by the correctly rounded reciprocals
+  // here (1 ulp per operation away from the reference; an FP64 division costs ~20 FP64-pipe slots on this GPU)
+  constexpr double K12 = 1. / 12.;
   const double dv = P.dv, dv2 = dv * dv, dv3 = dv2 * dv;
   const double c1 = -P.Lv + (j1 + 0.5) * dv;
   const double *f4 = fld + 1 + 4 * cell;
@@ -150,10 +158,10 @@ __global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin
   for (int c = 0; c < 6; c++) u[c] = Uin[own + (long long)c * sv];
   double tp[6] = {0., 0., 0., 0., 0., 0.};
   // I1: only the phi_x test function sees the v1 f volume term
-  tp[1] += dv3 * (c1 * u[0] + dv * u[2] / 12. + u[5] * c1 / 4.);
+  tp[1] += dv3 * (c1 * u[0] + dv * u[2] * K12 + u[5] * c1 * 0.25);
   // I2: E f volume term (Int_fE, FieldCalculations.cpp:126-135)
-  tp[2] -= ((u[0] + u[5] / 4.) * E + u[1] * E1) * P.scalev / dv;
-  tp[5] -= u[2] * dv2 * E / 6.;
+  tp[2] -= ((u[0] + u[5] * 0.25) * E + u[1] * E1) * dv2;   // scalev/dv = dv^2
+  tp[5] -= u[2] * dv2 * E * (1. / 6.);
   // I3: x faces, upwind on the sign of the v1 cell index
   {
     double R[6], L[6], ur, ul;
@@ -168,12 +176,12 @@ __global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin
       for (int c = 0; c < 6; c++) { L[c] = Uin[nb + (long long)c * sv]; R[c] = u[c]; }
       ur = R[1]; ul = L[1];
     }
-    tp[0] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 + (R[2] - L[2]) * dv / 12. + (R[5] - L[5]) * c1 / 4.);
-    tp[1] -= 0.5 * dv3 * ((R[0] + 0.5 * ur + L[0] + 0.5 * ul) * c1 + (R[2] + L[2]) * dv / 12. + (R[5] + L[5]) * c1 / 4.);
-    tp[2] -= dv2 * (((R[0] - L[0]) * dv2 + (ur - ul) * 0.5 * dv2 + (R[2] - L[2]) * dv * c1) / 12. + (R[5] - L[5]) * dv2 * 19. / 720.);
-    tp[3] -= (R[3] - L[3]) * c1 * dv3 / 12.;
-    tp[4] -= (R[4] - L[4]) * c1 * dv3 / 12.;
-    tp[5] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 / 4. + (R[2] - L[2]) * dv * 19. / 720. + (R[5] - L[5]) * c1 * 19. / 240.);
+    tp[0] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 + (R[2] - L[2]) * dv * K12 + (R[5] - L[5]) * c1 * 0.25);
+    tp[1] -= 0.5 * dv3 * ((R[0] + 0.5 * ur + L[0] + 0.5 * ul) * c1 + (R[2] + L[2]) * dv * K12 + (R[5] + L[5]) * c1 * 0.25);
+    tp[2] -= dv2 * (((R[0] - L[0]) * dv2 + (ur - ul) * 0.5 * dv2 + (R[2] - L[2]) * dv * c1) * K12 + (R[5] - L[5]) * dv2 * (19. / 720.));
+    tp[3] -= (R[3] - L[3]) * c1 * dv3 * K12;
+    tp[4] -= (R[4] - L[4]) * c1 * dv3 * K12;
+    tp[5] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 * 0.25 + (R[2] - L[2]) * dv * (19. / 720.) + (R[5] - L[5]) * c1 * (19. / 240.));
   }
   // I5: v1 faces, upwind on the sign of the cell-integrated field; no flux through |v1| = Lv
   {
@@ -205,27 +213,27 @@ __global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin
         ul = 0.;
       }
     }
-    const double gR = R[0] + 0.5 * ur + R[5] * 5. / 12., gL = L[0] + 0.5 * ul + L[5] * 5. / 12.;
+    const double gR = R[0] + 0.5 * ur + R[5] * (5. / 12.), gL = L[0] + 0.5 * ul + L[5] * (5. / 12.);
     tp[0] += dv2 * (gR - gL) * E + dv2 * (R[1] - L[1]) * E1;
     tp[1] += dv2 * ((gR - gL) * E1 + (R[1] - L[1]) * E2);
     tp[2] += 0.5 * (dv2 * (gR + gL) * E + dv2 * (R[1] + L[1]) * E1);
-    tp[3] += (R[3] - L[3]) * E * dv2 / 12.;
-    tp[4] += (R[4] - L[4]) * E * dv2 / 12.;
-    tp[5] += dv2 * (((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * 5. / 12. + (R[5] - L[5]) * 133. / 720.) * E + (R[1] - L[1]) * E1 * 5. / 12.);
+    tp[3] += (R[3] - L[3]) * E * dv2 * K12;
+    tp[4] += (R[4] - L[4]) * E * dv2 * K12;
+    tp[5] += dv2 * (((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * (5. / 12.) + (R[5] - L[5]) * (133. / 720.)) * E + (R[1] - L[1]) * E1 * (5. / 12.));
   }
-  const double dxs = P.dx * P.scalev;
+  const double idxs = P.inv_dxs;   // 1/(dx scalev)
   double H[6];
-  H[0] = (19 * tp[0] / 4. - 15 * tp[5]) / dxs;
-  H[5] = (60 * tp[5] - 15 * tp[0]) / dxs;
+  H[0] = (19 * tp[0] * 0.25 - 15 * tp[5]) * idxs;
+  H[5] = (60 * tp[5] - 15 * tp[0]) * idxs;
   #pragma unroll
-  for (int l = 1; l < 5; l++) H[l] = tp[l] * 12. / dxs;
+  for (int l = 1; l < 5; l++) H[l] = tp[l] * (12. * idxs);
   #pragma unroll
   for (int c = 0; c < 6; c++) {
     const long long o = own + (long long)c * sv;
     double r;
     if (STAGE == 0) r = u[c] + P.dt * H[c];
     else if (STAGE == 1) r = 0.75 * U0[o] + 0.25 * u[c] + 0.25 * P.dt * H[c];
-    else r = U0[o] / 3. + u[c] * 2. / 3. + P.dt * H[c] * 2. / 3.;
+    else r = U0[o] * (1. / 3.) + u[c] * (2. / 3.) + P.dt * H[c] * (2. / 3.);
     Uout[o] = r;
   }
 }
@@ -233,7 +241,7 @@ int lp_launch_dg_stage(lpgpu_ctx *c, int stage)
 {
   DgParams P;
   P.Nv = c->p.Nv; P.sv = c->sv; P.ncell = c->ncell; P.dv = c->tab.dv; P.dx = c->p.Lx / c->p.Nx; P.dt = c->p.dt;
-  P.scalev = c->tab.scalev; P.Lv = c->p.Lv;
+  P.scalev = c->tab.scalev; P.Lv = c->p.Lv; P.inv_dxs = 1. / (P.dx * P.scalev);
   const long long n = (long long)c->ncell * c->sv;
   const unsigned grid = (unsigned)((n + 255) / 256);
   // buffers: stage 0 reads U -> writes U1; stage 1 reads U1 (+U) -> U2; stage 2 reads U2 (+U) -> U

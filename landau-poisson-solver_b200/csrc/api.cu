@@ -100,7 +100,7 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   }
   A_(dev_alloc(&c->d_aos, plane * c->ncell));
   A_(dev_alloc(&c->d_ms_local, (size_t)2 * c->ncell));
-  A_(dev_alloc(&c->d_ms_part, (size_t)2 * 8 * c->ncell));
+  A_(dev_alloc(&c->d_ms_part, (size_t)2 * 32 * c->ncell));   // LP_FR_CH partials per cell
   A_(dev_alloc(&c->d_ms_all, (size_t)2 * c->p.Nx));
   A_(dev_alloc(&c->d_fld, (size_t)1 + 4 * c->ncell));
   A_(dev_alloc(&c->d_mom, (size_t)5));

@@ -671,6 +671,125 @@ __global__ void __launch_bounds__(256) k_project_final(const double2 *__restrict
   u[2LL * sv] = t2; u[3LL * sv] = t3; u[4LL * sv] = t4;      // U[6k+1] is not touched by collisions
 }
 
+// ---- register-tiled projection (N % 4 == 0, Nv % 8 == 0).  The simple kernels above issue one or more loads per
+// complex multiply-add and are bound by the L1/shared-memory pipe; here every loaded table entry / intermediate
+// feeds four (slab) or eight (final) outputs held in registers, so the FP64 pipe is the limit.
+__global__ void __launch_bounds__(256, 2) k_project_slab_t(const double2 *__restrict__ q0, const double2 *__restrict__ q1,
+                                                        const double2 *__restrict__ q2, const double2 *__restrict__ q3,
+                                                        double2 *__restrict__ Bbuf, const double2 *__restrict__ tT,
+                                                        const double2 *__restrict__ tM, const double2 *__restrict__ tS,
+                                                        int N, int Nv, double nu)
+{
+  extern __shared__ double2 sm2[];
+  const int P = N + 1, PV = Nv + 1;
+  double2 *Xs = sm2;                 // [N][P]
+  double2 *As = Xs + N * P;          // [3][N][PV]
+  const long long slab = blockIdx.x; // cell*N + k1
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < N * N; t += nt) {
+    const long long g = slab * N * N + t;
+    const double2 a = q0[g], b = q1[g], c = q2[g], d = q3[g];
+    Xs[(t / N) * P + (t % N)] = make_double2(nu * (0.5 * a.x + (b.x + c.x + d.x) * (1. / 6.)), nu * (0.5 * a.y + (b.y + c.y + d.y) * (1. / 6.)));
+  }
+  __syncthreads();
+  // contract k3: As[tab][k2][j3], thread = (j3, four consecutive k2)
+  for (int it = tid; it < (N / 4) * Nv; it += nt) {
+    const int j3 = it % Nv, k20 = 4 * (it / Nv);
+    double2 aT[4], aM[4], aS[4];
+    #pragma unroll
+    for (int kk = 0; kk < 4; kk++) aT[kk] = aM[kk] = aS[kk] = make_double2(0., 0.);
+    #pragma unroll 2
+    for (int k3 = 0; k3 < N; k3++) {
+      const double2 T3 = tT[k3 * Nv + j3], M3 = tM[k3 * Nv + j3], S3 = tS[k3 * Nv + j3];
+      #pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const double2 x = Xs[(k20 + kk) * P + k3];
+        cfma(aT[kk], T3, x); cfma(aM[kk], M3, x); cfma(aS[kk], S3, x);
+      }
+    }
+    #pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      As[(0 * N + k20 + kk) * PV + j3] = aT[kk]; As[(1 * N + k20 + kk) * PV + j3] = aM[kk]; As[(2 * N + k20 + kk) * PV + j3] = aS[kk];
+    }
+  }
+  __syncthreads();
+  // contract k2: thread = (j3, four consecutive j2)
+  const int Pq = Nv * Nv;
+  for (int it = tid; it < (Nv / 4) * Nv; it += nt) {
+    const int j3 = it % Nv, j20 = 4 * (it / Nv);
+    double2 bTT[4], bMT[4], bTM[4], bS[4];
+    #pragma unroll
+    for (int jj = 0; jj < 4; jj++) bTT[jj] = bMT[jj] = bTM[jj] = bS[jj] = make_double2(0., 0.);
+    #pragma unroll 2
+    for (int k2 = 0; k2 < N; k2++) {
+      const double2 at = As[(0 * N + k2) * PV + j3], am = As[(1 * N + k2) * PV + j3], as = As[(2 * N + k2) * PV + j3];
+      #pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const double2 T2 = tT[k2 * Nv + j20 + jj], M2 = tM[k2 * Nv + j20 + jj], S2 = tS[k2 * Nv + j20 + jj];
+        cfma(bTT[jj], T2, at); cfma(bMT[jj], M2, at); cfma(bTM[jj], T2, am); cfma(bS[jj], S2, at); cfma(bS[jj], T2, as);
+      }
+    }
+    #pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      double2 *o = Bbuf + slab * 4 * Pq + (j20 + jj) * Nv + j3;
+      o[0] = bTT[jj]; o[Pq] = bMT[jj]; o[2 * Pq] = bTM[jj]; o[3 * Pq] = bS[jj];
+    }
+  }
+}
+// contract k1 and apply the DG update (divisions by scalev, scaleL, scale3, 4, 240 of collisionRoutines_1.cpp:973-983
+// folded into correctly rounded factors).  CTA = (cell, 32 consecutive p = (j2, j3)); the whole [k1][4][32] tile of
+// the intermediate is fetched with one burst of cp.async (64 KB in flight, read exactly once), then warp w contracts
+// k1 for its eight j1 values: lanes read the tile from shared memory, the table entries are warp-uniform loads.
+__global__ void __launch_bounds__(128) k_project_final_t(const double2 *__restrict__ Bbuf, double *__restrict__ planes,
+                                                         const double2 *__restrict__ tT, const double2 *__restrict__ tM,
+                                                         const double2 *__restrict__ tS, int N, int Nv, int sv, double fac)
+{
+  extern __shared__ double2 Bs[];          // [k1][4][32]
+  const int Pq = Nv * Nv;
+  const long long cell = blockIdx.y; const int p0 = 32 * blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int idx = tid; idx < N * 4 * 32; idx += blockDim.x) {
+    const int k1 = idx >> 7, w = (idx >> 5) & 3, pp = idx & 31;
+    fc3::cp16(Bs + idx, Bbuf + ((cell * N + k1) * 4 + w) * Pq + p0 + pp);
+  }
+  fc3::cp_wait_all();
+  __syncthreads();
+  const int p = p0 + lane;
+  for (int j10 = 8 * warp; j10 < Nv; j10 += 8 * nw) {
+    double tp0[8], tp2[8], tp3[8], tp4[8], tp5[8];
+    #pragma unroll
+    for (int a = 0; a < 8; a++) tp0[a] = tp2[a] = tp3[a] = tp4[a] = tp5[a] = 0.;
+    #pragma unroll 2
+    for (int k1 = 0; k1 < N; k1++) {
+      const double2 *b = Bs + k1 * 128 + lane;
+      const double2 btt = b[0], bmt = b[32], btm = b[64], bs = b[96];
+      #pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const double2 T1 = tT[k1 * Nv + j10 + a], M1 = tM[k1 * Nv + j10 + a], S1 = tS[k1 * Nv + j10 + a];
+        tp0[a] = fma(T1.x, btt.x, tp0[a]); tp0[a] = fma(-T1.y, btt.y, tp0[a]);
+        tp2[a] = fma(M1.x, btt.x, tp2[a]); tp2[a] = fma(-M1.y, btt.y, tp2[a]);
+        tp3[a] = fma(T1.x, bmt.x, tp3[a]); tp3[a] = fma(-T1.y, bmt.y, tp3[a]);
+        tp4[a] = fma(T1.x, btm.x, tp4[a]); tp4[a] = fma(-T1.y, btm.y, tp4[a]);
+        tp5[a] = fma(S1.x, btt.x, tp5[a]); tp5[a] = fma(-S1.y, btt.y, tp5[a]);
+        tp5[a] = fma(T1.x, bs.x, tp5[a]); tp5[a] = fma(-T1.y, bs.y, tp5[a]);
+      }
+    }
+    #pragma unroll
+    for (int a = 0; a < 8; a++) {
+      double *u = planes + ((cell + 1) * 6) * (long long)sv + (long long)(j10 + a) * Pq + p;
+      const double U0 = u[0], U2 = u[2LL * sv], U3 = u[3LL * sv], U4 = u[4LL * sv], U5 = u[5LL * sv];
+      const double t0 = U0 + U5 * 0.25 + tp0[a] * fac;
+      const double t2 = U2 + tp2[a] * (12. * fac);
+      const double t3 = U3 + tp3[a] * (12. * fac);
+      const double t4 = U4 + tp4[a] * (12. * fac);
+      const double t5 = U0 * 0.25 + U5 * (19. / 240.) + tp5[a] * fac;
+      u[0] = 19 * t0 * 0.25 - 15 * t5;
+      u[5LL * sv] = 60 * t5 - 15 * t0;
+      u[2LL * sv] = t2; u[3LL * sv] = t3; u[4LL * sv] = t4;      // U[6k+1] is not touched by collisions
+    }
+  }
+}
+
 int lp_launch_project(lpgpu_ctx *c, double *planes, int B)
 {
   const int N = c->p.N, Nv = c->p.Nv;
@@ -680,6 +799,21 @@ int lp_launch_project(lpgpu_ctx *c, double *planes, int B)
   LP_CUDA(cudaFuncSetAttribute(k_project_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const double2 *T = reinterpret_cast<const double2 *>(c->d_T), *M = reinterpret_cast<const double2 *>(c->d_M),
                 *S = reinterpret_cast<const double2 *>(c->d_S);
+  static const bool simple_only = getenv("LPGPU_PROJECT_SIMPLE") != nullptr;   // developer knob
+  if (!simple_only && N % 4 == 0 && Nv % 8 == 0) {
+    LP_CUDA(cudaFuncSetAttribute(k_project_slab_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_project_slab_t<<<B * N, 256, smem, c->stream>>>(
+        reinterpret_cast<const double2 *>(c->d_q[0]), reinterpret_cast<const double2 *>(c->d_q[1]),
+        reinterpret_cast<const double2 *>(c->d_q[2]), reinterpret_cast<const double2 *>(c->d_q[3]),
+        reinterpret_cast<double2 *>(c->d_B), T, M, S, N, Nv, c->p.nu);
+    LP_LAUNCHED(c);
+    const double fac = c->p.dt / c->tab.scalev / c->tab.scaleL / c->tab.scale3;
+    const size_t smemf = (size_t)N * 4 * 32 * sizeof(double2);
+    LP_CUDA(cudaFuncSetAttribute(k_project_final_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
+    k_project_final_t<<<dim3(Nv * Nv / 32, B), 128, smemf, c->stream>>>(reinterpret_cast<const double2 *>(c->d_B), planes, T, M, S, N, Nv, c->sv, fac);
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
   k_project_slab<<<B * N, threads, smem, c->stream>>>(
       reinterpret_cast<const double2 *>(c->d_q[0]), reinterpret_cast<const double2 *>(c->d_q[1]),
       reinterpret_cast<const double2 *>(c->d_q[2]), reinterpret_cast<const double2 *>(c->d_q[3]),
