@@ -744,14 +744,16 @@ __global__ void __launch_bounds__(128) k_project_final_t(const double2 *__restri
                                                          const double2 *__restrict__ tT, const double2 *__restrict__ tM,
                                                          const double2 *__restrict__ tS, int N, int Nv, int sv, double fac)
 {
-  extern __shared__ double2 Bs[];          // [k1][4][32]
+  extern __shared__ double2 Bs[];          // [k1][4][32] | T, M, S [k1][Nv]
   const int Pq = Nv * Nv;
   const long long cell = blockIdx.y; const int p0 = 32 * blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  double2 *sT = Bs + N * 128, *sM = sT + N * Nv, *sS = sM + N * Nv;
   for (int idx = tid; idx < N * 4 * 32; idx += blockDim.x) {
     const int k1 = idx >> 7, w = (idx >> 5) & 3, pp = idx & 31;
     fc3::cp16(Bs + idx, Bbuf + ((cell * N + k1) * 4 + w) * Pq + p0 + pp);
   }
+  for (int idx = tid; idx < N * Nv; idx += blockDim.x) { fc3::cp16(sT + idx, tT + idx); fc3::cp16(sM + idx, tM + idx); fc3::cp16(sS + idx, tS + idx); }
   fc3::cp_wait_all();
   __syncthreads();
   const int p = p0 + lane;
@@ -765,7 +767,7 @@ __global__ void __launch_bounds__(128) k_project_final_t(const double2 *__restri
       const double2 btt = b[0], bmt = b[32], btm = b[64], bs = b[96];
       #pragma unroll
       for (int a = 0; a < 8; a++) {
-        const double2 T1 = tT[k1 * Nv + j10 + a], M1 = tM[k1 * Nv + j10 + a], S1 = tS[k1 * Nv + j10 + a];
+        const double2 T1 = sT[k1 * Nv + j10 + a], M1 = sM[k1 * Nv + j10 + a], S1 = sS[k1 * Nv + j10 + a];
         tp0[a] = fma(T1.x, btt.x, tp0[a]); tp0[a] = fma(-T1.y, btt.y, tp0[a]);
         tp2[a] = fma(M1.x, btt.x, tp2[a]); tp2[a] = fma(-M1.y, btt.y, tp2[a]);
         tp3[a] = fma(T1.x, bmt.x, tp3[a]); tp3[a] = fma(-T1.y, bmt.y, tp3[a]);
@@ -808,7 +810,7 @@ int lp_launch_project(lpgpu_ctx *c, double *planes, int B)
         reinterpret_cast<double2 *>(c->d_B), T, M, S, N, Nv, c->p.nu);
     LP_LAUNCHED(c);
     const double fac = c->p.dt / c->tab.scalev / c->tab.scaleL / c->tab.scale3;
-    const size_t smemf = (size_t)N * 4 * 32 * sizeof(double2);
+    const size_t smemf = ((size_t)N * 4 * 32 + (size_t)3 * N * Nv) * sizeof(double2);
     LP_CUDA(cudaFuncSetAttribute(k_project_final_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
     k_project_final_t<<<dim3(Nv * Nv / 32, B), 128, smemf, c->stream>>>(reinterpret_cast<const double2 *>(c->d_B), planes, T, M, S, N, Nv, c->sv, fac);
     LP_LAUNCHED(c);

@@ -344,7 +344,8 @@ struct F2 {
   static LP_HD void issue_loads(int tid, int cell, int kz, int p, const double2 *Z, double2 *IN)
   {
     const double2 *su = plane(Z, cell, p, kz), *sv = plane(Z, cell, 7 + zpow_of(p), kz);
-    for (int idx = tid; idx < 2 * N * N; idx += NT) {
+    const int lim = (p == 1) ? N * N : 2 * N * N;      // p = 1 reuses the y-transformed v of p = 0
+    for (int idx = tid; idx < lim; idx += NT) {
       const int arr = idx / (N * N), e = idx % (N * N);
       cp16(IN + idx, (arr ? sv : su) + e);
     }
@@ -352,6 +353,14 @@ struct F2 {
   static LP_HD void ystage(int tid, int p, const double2 *IN, const double *sE, double2 *Y)
   {
     const int x = tid % N, r = (tid / N) % 3, arr = tid / (3 * N);
+    if (arr == 1 && p == 1) {
+      // v_1 = -E(x)^2 fhat has the y transform of v_0 = fhat, which this thread stored at p = 0: rescale in place
+      const double sx = -ipow(sE[x], 2);
+      double2 *dst = Y + N * PY + x * PY + r * L;
+      #pragma unroll
+      for (int q = 0; q < L; q++) { const double2 v = dst[q]; dst[q] = make_double2(v.x * sx, v.y * sx); }
+      return;
+    }
     const double2 *src = IN + arr * N * N + x;
     double2 a0[L], a1[L], yv[L];
     #pragma unroll
