@@ -188,7 +188,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    g.profile_computeQ(True)
+    g.profile_computeQ(2)
     l0 = g.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -218,10 +218,12 @@ def main():
            "d2h_bytes_per_step": int(back.numel() * 8 * world), "steps": e2e_steps, "timesteps_per_s": e2e_steps / t_e2e}
 
     # ---- roofline of the dominant kernels --------------------------------------------------------
-    # (1) the step's ComputeQ = seven zero-padded FFT convolutions (k_fc_fwd_yz + k_fc_x + k_fc_inv_yz, timed
-    #     together by the library's events).  Bound: HBM.  Algorithmic bytes of this formulation per cell:
-    #     fhat in + 14 transformed y-z plane sets written and read once + the x-reduced array written and read
-    #     once + Qhat out.
+    # (1) the step's dominant kernel: k_fc3_f2_tmem, the y/x-transform + product + inverse kernel of ComputeQ's
+    #     FFT-convolution pipeline (~52 % of a step; its launches were bracketed by CUDA events inside the timed
+    #     region, profile mode 2).  Bound: the FP64 pipe (ncu: FP64 pipe 45 % busy, DRAM 13 %), so the roofline is
+    #     quoted in FP64 TFLOP/s against the DFMA rate measured live on this GPU.  Algorithmic flops of that kernel
+    #     (DESIGN.md section 4.1): per cell and per kz plane 14 x (N + M) forward and (M + N) inverse length-M line
+    #     transforms at the textbook 5 M log2 M, plus 7 M^2 complex multiply-adds at 8 flop; M = 3N/2 planes.
     # (2) the north star's direct O(N^6) sum (k_computeQ_tiled, computeq_variant = 3), timed here on the same
     #     cells outside the step: FP64-pipe bound, 10 flop per (xi, omega) pair.
     roof = roof_direct = None
@@ -230,23 +232,28 @@ def main():
     ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(ppath):
         peaks = json.load(open(ppath))
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s fallback of B200_PROFILING.md (of fallback)"
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "computeq_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
+    fp64_src = ("DFMA micro-benchmark run live on this GPU (lpgpu_fp64_peak); MEASURED_PEAKS.json holds only HBM and bf16 peaks; "
+                "nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s")
     if cq_n > 0:
-        Mpad = 3 * NSPEC // 2                      # cyclic transform size per dimension (fftconv.cu)
-        bytes_per_cell = 16 * (NSPEC ** 3 + 2 * 14 * NSPEC * Mpad * Mpad + 2 * NSPEC * Mpad * Mpad + NSPEC ** 3)
+        Mpad = 3 * NSPEC // 2                      # cyclic transform size per dimension (fc3.cuh)
+        line_flop = 5. * Mpad * np.log2(Mpad)
+        f2_flop_per_cell = Mpad * ((14 + 1) * (NSPEC + Mpad) * line_flop + 7 * Mpad * Mpad * 8.)
         avg_s = cq_ms * 1e-3 / cq_n
-        achieved = bytes_per_cell * s.x_count / avg_s / 1e9
-        roof = {"bound": "hbm", "kernel": "ComputeQ as FFT convolutions: k_fc_fwd_yz + k_fc_x + k_fc_inv_yz", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic.get("fftconv_dram_bytes_per_launch"),
-                "avg_launch_ms": avg_s * 1e3, "launches": cq_n, "share_of_step": cq_ms * 1e-3 / t_dev, "peak_source": hbm_src,
-                "algorithmic_bytes_per_launch": bytes_per_cell * s.x_count,
+        achieved = f2_flop_per_cell * s.x_count / avg_s / 1e12
+        chain_bytes_per_cell = 16 * (NSPEC ** 3 + 2 * 10 * NSPEC * NSPEC * Mpad + 2 * NSPEC * NSPEC * Mpad + NSPEC ** 3)
+        roof = {"bound": "fp64", "kernel": "k_fc3_f2_tmem (ComputeQ as FFT convolutions: y/x line transforms + products + inverse x/y of one kz plane per CTA, accumulators in TMEM)",
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": traffic.get("fc3_f2_dram_bytes_per_launch"),
+                "avg_launch_ms": avg_s * 1e3, "launches": cq_n, "share_of_step": cq_ms * 1e-3 / t_dev, "peak_source": fp64_src,
+                "algorithmic_flop_per_launch": f2_flop_per_cell * s.x_count,
+                "hbm_view": {"algorithmic_bytes_per_launch_whole_chain": chain_bytes_per_cell * s.x_count, "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                             "note": "F1+F2+F3 move 10+1 arrays of N^2 M complex once each way; at the measured HBM peak that is ~0.08 ms per launch chain, well under the FP64 time"},
                 "direct_form_equivalent_tflops": flop_per_eval(NSPEC) * s.x_count / avg_s / 1e12,
-                "note": "direct_form_equivalent_tflops counts the 10 flop/pair of the O(N^6) sum this kernel replaces; it exceeds the FP64 peak because the FFT form executes ~13x fewer flops for the same result (parity-tested)"}
+                "note": "bound is the FP64 vector pipe (not hbm/tensor): the contraction is not dense, see DESIGN.md 4.1; direct_form_equivalent_tflops counts the 10 flop/pair of the O(N^6) sum this kernel replaces and exceeds the FP64 peak because the FFT form executes ~50x fewer flops for the same result (parity-tested)"}
     try:
         d = pkg.LPGpu(Nx, NV, NSPEC, homogeneous=False, x_begin=s.x_begin, x_count=s.x_count, device=local, computeq_variant=3, **PHYS)
         d.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -264,7 +271,7 @@ def main():
         roof_direct = {"bound": "fp64", "kernel": "k_computeQ_tiled (computeq_variant=3, the reference's O(N^6) form)", "achieved": ach,
                        "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic.get("dram_bytes_per_launch"),
                        "avg_launch_ms": avg_d * 1e3, "launches": dq_n, "evals_per_s": s.x_count / avg_d,
-                       "peak_source": "DFMA micro-benchmark run live on this GPU (lpgpu_fp64_peak); MEASURED_PEAKS.json holds only HBM and bf16 peaks; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
+                       "peak_source": fp64_src,
                        "algorithmic_flop_per_launch": flop_per_eval(NSPEC) * s.x_count}
     except Exception as e:
         roof_direct = {"error": repr(e)}
@@ -272,7 +279,7 @@ def main():
     line = None
     if rank == 0:
         ws_mb = (3 * (s.x_count + 2) * 6 * NV ** 3 * 8 + s.x_count * NSPEC ** 3 * 8 * (3 + 2 * 6) + s.x_count * NSPEC * 4 * NV * NV * 16
-                 + s.x_count * 15 * NSPEC * (3 * NSPEC // 2) ** 2 * 16) / 2 ** 20
+                 + s.x_count * 11 * NSPEC * NSPEC * (3 * NSPEC // 2) * 16) / 2 ** 20
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -288,13 +295,11 @@ def main():
         h = solver.ShardedSolver(1, NV, NSPEC, homogeneous=True, device=local, **PHYS)
         h.g.set_stream(torch.cuda.current_stream().cuda_stream)
         h.upload(solver.set_init_4h_homo(NV, PHYS["Lv"]))
-        for _ in range(3):
-            h.step(1)
+        h.step(4)                  # the library replays a CUDA graph of the timestep from the second step on
         torch.cuda.synchronize()
         e0.record()
-        nh = 20
-        for _ in range(nh):
-            h.step(1)
+        nh = 40
+        h.step(nh)
         e1.record()
         torch.cuda.synchronize()
         th = e0.elapsed_time(e1) * 1e-3

@@ -40,7 +40,8 @@ typedef struct lpgpu_params {
   int x_begin, x_count;
   int device;       /* CUDA device ordinal */
   int computeq_variant; /* which ComputeQ kernel evaluates the weighted spectral convolution (same result to round-off):
-                           0 = fastest validated: seven zero-padded FFT convolutions when N is a power of two,
+                           0 = fastest validated: seven zero-padded FFT convolutions when 3N/2 = 2^a 3^b (N = 8, 16, 24, 32
+                               run the register-resident pipeline fused with fft3D/conserveMoments/FS),
                                otherwise the register-tiled direct sum;
                            1 = simple one-thread-per-xi direct kernel (on-device cross-check);
                            2 = FFT convolutions; 3 = register-tiled direct sum (the O(N^6) form of the reference) */
@@ -116,8 +117,10 @@ int lpgpu_get_stage_spectrum(lpgpu_ctx *c, int which, double *out /* x_count*N^3
 int lpgpu_field(lpgpu_ctx *c, double *out);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
-/* Bracket every ComputeQ kernel launch with CUDA events on the context's stream; read returns the
- * summed device time and the number of launches since enable (synchronises the stream). */
+/* Bracket ComputeQ with CUDA events on the context's stream: enable = 1 around the whole ComputeQ chain of
+ * kernels, 2 around its dominant kernel only (the y/x-transform + product kernel of the FFT-convolution
+ * pipeline), 0 off; read returns the summed device time and the number of bracketed launches since enable
+ * (synchronises the stream). */
 int lpgpu_profile_computeQ(lpgpu_ctx *c, int enable);
 int lpgpu_profile_read(lpgpu_ctx *c, double *total_ms, long long *launches);
 /* DFMA micro-benchmark: sustained FP64 FMA rate of `device` in TFLOP/s (roofline denominator). */

@@ -132,6 +132,8 @@ int lpgpu_finalize(lpgpu_ctx *c)
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
+  if (c->gexec) cudaGraphExecDestroy(c->gexec);
+  if (c->gstream) cudaStreamDestroy(c->gstream);
   delete c;
   return LPGPU_OK;
 }
@@ -264,13 +266,56 @@ int lpgpu_collide_step(lpgpu_ctx *c)
   LP_CUDA(cudaStreamSynchronize(c->stream));
   return LPGPU_OK;
 }
+static int one_step_async(lpgpu_ctx *c)
+{
+  if (!c->p.homogeneous) LP_TRY(advect_rk3_async(c));
+  if (c->p.nu > 0.) LP_TRY(collide_async(c));
+  return LPGPU_OK;
+}
+// Capture one timestep (about 40 dependent launches) into a CUDA graph.  A single homogeneous cell is launch-latency
+// bound (each kernel runs a few microseconds); replaying the graph removes the per-launch gaps.
+static void capture_step_graph(lpgpu_ctx *c)
+{
+  if (!c->gstream && cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->graph_failed = true; return; }
+  cudaStream_t user = c->stream;
+  const long long before = c->launches;
+  c->stream = c->gstream;
+  cudaGraph_t graph = nullptr;
+  int rc = LPGPU_ECUDA;
+  if (cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    rc = one_step_async(c);
+    if (cudaStreamEndCapture(c->gstream, &graph) != cudaSuccess) rc = LPGPU_ECUDA;
+  }
+  c->stream = user;
+  c->graph_launches = c->launches - before;
+  c->launches = before;                      // captured, not executed
+  if (rc == LPGPU_OK && graph && cudaGraphInstantiate(&c->gexec, graph, 0) == cudaSuccess) {
+    cudaGraphDestroy(graph);
+    return;
+  }
+  if (graph) cudaGraphDestroy(graph);
+  cudaGetLastError();
+  c->gexec = nullptr;
+  c->graph_failed = true;
+}
 int lpgpu_step(lpgpu_ctx *c, int nsteps)
 {
   LP_ENTER(c);
-  for (int s = 0; s < nsteps; s++) {
-    if (!c->p.homogeneous) LP_TRY(advect_rk3_async(c));
-    if (c->p.nu > 0.) LP_TRY(collide_async(c));
+  static const bool no_graph = getenv("LPGPU_NO_GRAPH") != nullptr;   // developer knob
+  int done = 0;
+  if (!no_graph && c->prof_on == 0 && !c->graph_failed && nsteps >= 2) {
+    if (!c->gexec) {
+      LP_TRY(one_step_async(c));             // eager first step: lazy allocations and function attributes happen here
+      done = 1;
+      capture_step_graph(c);
+    }
+    if (c->gexec)
+      for (; done < nsteps; done++) {
+        LP_CUDA(cudaGraphLaunch(c->gexec, c->stream));
+        c->launches += c->graph_launches;
+      }
   }
+  for (; done < nsteps; done++) LP_TRY(one_step_async(c));
   LP_CUDA(cudaStreamSynchronize(c->stream));
   return LPGPU_OK;
 }
@@ -389,7 +434,7 @@ int lpgpu_profile_computeQ(lpgpu_ctx *c, int enable)
     c->prof_ev.resize(8192);
     for (auto &e : c->prof_ev) LP_CUDA(cudaEventCreate(&e));
   }
-  c->prof_on = enable != 0;
+  c->prof_on = enable;
   c->prof_used = 0;
   return LPGPU_OK;
 }

@@ -253,7 +253,7 @@ static int launch_tiled(lpgpu_ctx *c, const double *fhat, double *q, int B)
   }
   double2 *out = reinterpret_cast<double2 *>(SL > 1 ? c->d_qpart : q);
   dim3 grid(N * B, SL, 1);
-  const bool prof = c->prof_on && c->prof_used + 2 <= c->prof_ev.size();
+  const bool prof = c->prof_on == 1 && c->prof_used + 2 <= c->prof_ev.size();
   if (prof) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   kern<<<grid, C::NT, C::SMEM, c->stream>>>(reinterpret_cast<const double2 *>(fhat), out, c->d_G, c->d_eta, c->d_Etab, SL);
   LP_LAUNCHED(c);

@@ -678,9 +678,12 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   else k_fc3_f1<L, false><<<dim3(N, nb), fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
   LP_LAUNCHED(c);
   static const bool no_tmem = getenv("LPGPU_FC_NO_TMEM") != nullptr;   // developer knob: accumulators in registers, 1 CTA per SM
+  const bool prof2 = c->prof_on == 2 && c->prof_used + 2 <= c->prof_ev.size();
+  if (prof2) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   if (L == 16 && !no_tmem) k_fc3_f2_tmem<<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
   else k_fc3_f2<L><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
   LP_LAUNCHED(c);
+  if (prof2) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
   k_fc3_f3<L><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo, c->d_C5, part);
   LP_LAUNCHED(c);
   return LPGPU_OK;
@@ -748,7 +751,7 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     LP_CUDA(cudaFuncSetAttribute(k_fc_inv_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
   const double2 *tw = reinterpret_cast<const double2 *>(c->d_fctw);
-  const bool prof = c->prof_on && c->prof_used + 2 <= c->prof_ev.size();
+  const bool prof = c->prof_on == 1 && c->prof_used + 2 <= c->prof_ev.size();
   if (prof) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   for (int b0 = 0; b0 < B; b0 += c->fc_chunk) {
     const int nb = B - b0 < c->fc_chunk ? B - b0 : c->fc_chunk;

@@ -58,7 +58,12 @@ struct lpgpu_ctx {
   bool fc3_attr;
   int fc_chunk;
   // ---- optional CUDA-event timing of the ComputeQ launches (bench.py roofline)
-  bool prof_on;
+  // ---- CUDA graph of one timestep (lpgpu_step with nsteps >= 2): captured once on gstream, replayed on `stream`
+  cudaStream_t gstream;
+  cudaGraphExec_t gexec;
+  bool graph_failed;
+  long long graph_launches;   // kernels per replay
+  int prof_on;            // 0 off, 1 events around the whole ComputeQ chain, 2 around its dominant kernel (F2) only
   std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
   size_t prof_used;        // events used so far
 };

@@ -224,7 +224,7 @@ class LPGpu:
 
     # -- measurement helpers
     def profile_computeQ(self, enable=True):
-        self._check(self.L.lpgpu_profile_computeQ(self.h, int(bool(enable))))
+        self._check(self.L.lpgpu_profile_computeQ(self.h, int(enable)))   # 0 off, 1 whole ComputeQ chain, 2 its dominant kernel
 
     def profile_read(self):
         ms, n = C.c_double(), C.c_longlong()

@@ -156,6 +156,24 @@ def test_full_step_small(small):
     assert np.all(np.abs(mg[1:4] - mo[1:4]) <= 1e-10)     # momentum: absolute, as moment_differ.sh does
 
 
+def test_graph_replay_matches_eager_steps(small, pkg):
+    """lpgpu_step(n >= 2) replays a CUDA graph of the timestep after one eager step: same bits as n single steps."""
+    ora, g = small
+    U = _perturbed(ora, 5)
+    g.upload_U(U)
+    for _ in range(4):
+        g.step(1)                                         # eager
+    want = g.download_U()
+    g2 = pkg.LPGpu(**SMALL)
+    g2.upload_U(U)
+    g2.step(3)                                            # 1 eager + capture + 2 replays
+    g2.step(1)
+    got = g2.download_U()
+    g2.close()
+    assert np.array_equal(got, want)
+    assert relerr(got, ora.step(ora.step(ora.step(ora.step(U))))) < TOL_U
+
+
 def test_entropy_and_negativity_diagnostics(small, pkg):
     """computeEntropy / FindNegVals / computeKiEratio (LP_ompi.cpp:819,829,846) on the GPU."""
     ora, g = small
