@@ -32,6 +32,7 @@ NV = 32
 NSPEC = 32
 PHYS = dict(Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)     # [TwoStream] section of the reference input deck
 A_AMP, K_WAVE = 0.5, 2 * np.pi / 4.
+OUT = sys.stdout
 METRIC, UNIT = "collision_cell_evals_per_s", "evals/s"
 
 
@@ -120,7 +121,7 @@ def run_reference(args, rank):
             "config": {"workload": "two-stream Landau-Poisson step, %d x-cells per GPU, Nv=%d, N=%d" % (CELLS_PER_GPU, NV, NSPEC),
                        "sample": "each step = one ComputeQ + conserveMoments on one cell (the metric's unit)"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def main():
@@ -131,6 +132,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: whatever a library prints there (NCCL's version banner ...)
+    # is sent to stderr
+    global OUT
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -314,7 +320,7 @@ def main():
     else:
         s.close()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

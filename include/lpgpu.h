@@ -73,6 +73,9 @@ int lpgpu_advect_rk3(lpgpu_ctx *c);
 /* setInit_spectral + for every local cell ComputeQ, conserveMoments, RK4 + the scatter of the 5
  * updated coefficients into U: LP_ompi.cpp:671-754. */
 int lpgpu_collide_step(lpgpu_ctx *c);
+/* Same work, enqueued only: the sharded driver queues the next stage's exchange behind it instead of stalling the
+ * host once per phase.  lpgpu_synchronize (or any synchronous call) before reading results. */
+int lpgpu_collide_step_async(lpgpu_ctx *c);
 /* nsteps passes of the while(t<nT) body without diagnostics (single shard). */
 int lpgpu_step(lpgpu_ctx *c, int nsteps);
 

@@ -298,6 +298,12 @@ static void capture_step_graph(lpgpu_ctx *c)
   c->gexec = nullptr;
   c->graph_failed = true;
 }
+int lpgpu_collide_step_async(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  if (!(c->p.nu > 0.)) return LPGPU_OK;
+  return collide_async(c);
+}
 int lpgpu_step(lpgpu_ctx *c, int nsteps)
 {
   LP_ENTER(c);

@@ -38,7 +38,7 @@ class Exchange(C.Structure):
 EXPORTS = [
     "lpgpu_last_error", "lpgpu_device_count", "lpgpu_init", "lpgpu_finalize", "lpgpu_set_stream",
     "lpgpu_synchronize", "lpgpu_launch_count", "lpgpu_upload_U", "lpgpu_download_U",
-    "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_step", "lpgpu_advect_exchange_info",
+    "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_step", "lpgpu_advect_exchange_info",
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
@@ -62,7 +62,7 @@ def load_library():
     L.lpgpu_launch_count.restype = C.c_longlong
     L.lpgpu_launch_count.argtypes = [C.c_void_p]
     L.lpgpu_init.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
-    for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_sample_device"):
+    for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_sample_device"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.lpgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial"):
@@ -160,8 +160,8 @@ class LPGpu:
     def advect_rk3(self):
         self._check(self.L.lpgpu_advect_rk3(self.h))
 
-    def collide_step(self):
-        self._check(self.L.lpgpu_collide_step(self.h))
+    def collide_step(self, wait=True):
+        self._check(self.L.lpgpu_collide_step(self.h) if wait else self.L.lpgpu_collide_step_async(self.h))
 
     def step(self, nsteps=1):
         self._check(self.L.lpgpu_step(self.h, int(nsteps)))

@@ -303,7 +303,8 @@ class ShardedSolver:
         for _ in range(nsteps):
             self.advect()
             if self.nu > 0:
-                self.g.collide_step()
+                self.g.collide_step(wait=False)      # enqueue only: the host runs ahead into the next exchange
+        self.g.synchronize()
 
     def moments(self):
         """Global mass, P1..3, KiE, EleE (LP_ompi.cpp:820-827) on every rank."""
