@@ -140,6 +140,10 @@ int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host);
  * out4[2]/out4[1] after summing over shards, MomentCalculations.cpp:133-199), number of cells FindNegVals
  * flags (NegativityChecks.cpp:24-160). */
 int lpgpu_diagnostics_partial(lpgpu_ctx *c, double *out4);
+/* PrintMarginal (LP_ompi.cpp:649, :870; MarginalCreation.cpp:16-67): the sums over the velocity directions that are
+ * integrated out, per output cell: x_count*Nv rows of (sum U0, U1, U2, U5 over j2, j3) or, homogeneous, Nv*Nv rows of
+ * (sum U0, U2, U3, U5 over j3).  The host evaluates the marginal at its 4 x 4 sub-grid points from them. */
+int lpgpu_marginal_sums(lpgpu_ctx *c, double *out);
 /* computeEleE (MomentCalculations.cpp:201-230) from the gathered per-cell sums; host-only. */
 int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms_all, double *EleE);
 

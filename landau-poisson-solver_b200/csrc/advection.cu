@@ -359,6 +359,39 @@ int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev)
   return LPGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// PrintMarginal (MarginalCreation.cpp:16-67, 160-219) needs only four sums per output cell:
+//   inhomogeneous: per (x cell, j1)  sum over (j2, j3) of U0, U1, U2, U5   (f_marg_Inhomo)
+//   homogeneous:   per (j1, j2)      sum over j3       of U0, U2, U3, U5   (f_marg_Homo)
+// One warp per output cell, fixed-order tree; the host evaluates the 4 x 4 sub-grid points from them.
+__global__ void __launch_bounds__(256) k_marginal_sums(const double *__restrict__ planes, double *__restrict__ out, int Nv, int sv, int ncell,
+                                                       int homogeneous)
+{
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nout = homogeneous ? Nv * Nv : ncell * Nv;
+  if (warp >= nout) return;
+  const int cmap_in[4] = {0, 1, 2, 5}, cmap_ho[4] = {0, 2, 3, 5};
+  long long base; int count;
+  if (homogeneous) { base = 6LL * sv + (long long)warp * Nv; count = Nv; }                       // (j1, j2) -> j3 run
+  else { const int cell = warp / Nv, j1 = warp % Nv; base = ((long long)(cell + 1) * 6) * sv + (long long)j1 * Nv * Nv; count = Nv * Nv; }
+  double v[4] = {0., 0., 0., 0.};
+  for (int t = lane; t < count; t += 32)
+    #pragma unroll
+    for (int a = 0; a < 4; a++) v[a] += planes[base + (long long)(homogeneous ? cmap_ho[a] : cmap_in[a]) * sv + t];
+  #pragma unroll
+  for (int a = 0; a < 4; a++) {
+    for (int o = 16; o > 0; o >>= 1) v[a] += __shfl_down_sync(0xffffffffu, v[a], o);
+    if (lane == 0) out[4LL * warp + a] = v[a];
+  }
+}
+int lp_launch_marginal_sums(lpgpu_ctx *c, const double *planes, double *out_dev)
+{
+  const int nout = c->p.homogeneous ? c->p.Nv * c->p.Nv : c->ncell * c->p.Nv;
+  k_marginal_sums<<<(nout * 32 + 255) / 256, 256, 0, c->stream>>>(planes, out_dev, c->p.Nv, c->sv, c->ncell, c->p.homogeneous);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
 int lp_launch_moments(lpgpu_ctx *c, const double *planes)
 {
   // d_B is free outside the projection: use its head for the per-cell partials

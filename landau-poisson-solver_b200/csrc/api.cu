@@ -484,6 +484,20 @@ int lpgpu_diagnostics_partial(lpgpu_ctx *c, double *out4)
   return LPGPU_OK;
 }
 
+// the four sums per output cell PrintMarginal needs (see k_marginal_sums); out: x_count*Nv*4 doubles
+// (U0, U1, U2, U5 summed over j2, j3) or, homogeneous, Nv*Nv*4 (U0, U2, U3, U5 summed over j3)
+int lpgpu_marginal_sums(lpgpu_ctx *c, double *out)
+{
+  LP_ENTER(c);
+  if (!out) return LPGPU_EINVAL;
+  const size_t n = (size_t)4 * (c->p.homogeneous ? c->p.Nv * c->p.Nv : c->ncell * c->p.Nv);
+  double *dev = c->d_B;                      // free outside the projection
+  LP_TRY(lp_launch_marginal_sums(c, c->d_U[0], dev));
+  LP_CUDA(cudaMemcpyAsync(out, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
 // computeEleE (MomentCalculations.cpp:201-230) written in terms of the per-cell sums
 // m_i = scalev sum (U0 + U5/4), s_i = scalev sum U1.  Pure host arithmetic on 2*Nx numbers.
 int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms, double *EleE)

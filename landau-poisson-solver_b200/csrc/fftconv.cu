@@ -477,14 +477,44 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
   const int y = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
   K::issue_g(tid, y, Gt, Gs);
   if (FUSED) {
-    if (tid < N) {
-      double2 v[N];
+    // the N lines along i of this slab, four threads per line: thread (j, k) forms the decimated sequence
+    // y_j[n] = (sum_s x[n + s N/4] (-i)^(j s)) w_N^(j n) and transforms it (N/4 points): X[4q + j]
+    if (tid < 4 * N) {
+      constexpr int Q = N / 4;
+      const int j = tid / N, k = tid % N;
+      const double2 *src = in + (((long long)cell * N) * N + y) * N + k;
+      double2 v[Q];
       #pragma unroll
-      for (int i = 0; i < N; i++) v[i] = in[(((long long)cell * N + i) * N + y) * N + tid];
-      fc3::fftN<N, -1, N>(v);
+      for (int n = 0; n < Q; n++) {
+        const double2 x0 = src[(long long)n * N * N], x1 = src[(long long)(n + Q) * N * N], x2 = src[(long long)(n + 2 * Q) * N * N],
+                      x3 = src[(long long)(n + 3 * Q) * N * N];
+        double2 t;
+        if (j == 0) t = fc3::cadd(fc3::cadd(x0, x2), fc3::cadd(x1, x3));
+        else if (j == 2) t = fc3::csub(fc3::cadd(x0, x2), fc3::cadd(x1, x3));
+        else {
+          const double2 a = fc3::csub(x0, x2), b = fc3::csub(x1, x3);       // j = 1: a - i b,  j = 3: a + i b
+          t = (j == 1) ? make_double2(a.x + b.y, a.y - b.x) : make_double2(a.x - b.y, a.y + b.x);
+        }
+        v[n] = t;
+      }
+      if (j == 1) {
+        #pragma unroll
+        for (int n = 0; n < Q; n++) v[n] = fc3::mul_tw<N, -1>(v[n], n);
+      } else if (j == 2) {
+        #pragma unroll
+        for (int n = 0; n < Q; n++) v[n] = fc3::mul_tw<N, -1>(v[n], 2 * n);
+      } else if (j == 3) {
+        #pragma unroll
+        for (int n = 0; n < Q; n++) v[n] = fc3::mul_tw<N, -1>(v[n], 3 * n);
+      }
+      fc3::fftN<Q, -1, N>(v);
       #pragma unroll
-      for (int i = 0; i < N; i++) FS[i * K::P + tid] = phase_mul(post[(i * N + y) * N + tid], v[i]);
-    } else if (tid < 2 * N) sE[tid - N] = E[tid - N];
+      for (int q = 0; q < Q; q++) {
+        const int i = 4 * q + j;
+        FS[i * K::P + k] = phase_mul(post[(i * N + y) * N + k], v[q]);
+      }
+    }
+    for (int t = tid; t < N; t += K::NT) sE[t] = E[t];
   } else {
     K::load(tid, cell, y, in, E, FS, sE);
   }

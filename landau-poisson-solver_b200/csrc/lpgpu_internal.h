@@ -126,4 +126,5 @@ int lp_launch_field_scan(lpgpu_ctx *c);
 int lp_launch_dg_stage(lpgpu_ctx *c, int stage);
 int lp_launch_local_halo(lpgpu_ctx *c, double *planes);
 int lp_launch_moments(lpgpu_ctx *c, const double *planes);
+int lp_launch_marginal_sums(lpgpu_ctx *c, const double *planes, double *out_dev);
 int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev);

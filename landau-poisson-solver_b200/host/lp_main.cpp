@@ -204,6 +204,12 @@ int main(int argc, char **argv)
   const std::string fu_name = name;
   snprintf(name, sizeof name, "Data/EntropyVals_%s", tail);
   const std::string fent_name = name;
+  snprintf(name, sizeof name, "Data/Marginals_%s", tail);
+  const std::string fmarg_name = name;
+  snprintf(name, sizeof name, "Data/PhiVals_%s", tail);
+  const std::string fphi_name = name;
+  snprintf(name, sizeof name, "Data/FieldVals_%s", tail);
+  const std::string fE_name = name;
 
   const int sv = p.Nv * p.Nv * p.Nv, ncell = p.x_count;
   std::vector<double> U((size_t)6 * sv * ncell);
@@ -249,16 +255,82 @@ int main(int argc, char **argv)
       fprintf(fmom, "%11.8g %11.8g %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g \n", m5[0], m5[1], m5[2], m5[3], m5[4], ele, t, log(t), m5[4] + ele);
     }
   };
+  // ---- Marginals_*.dc / PhiVals_*.dc / FieldVals_*.dc: first the evaluation points, then one row for the initial state
+  // and one every 20 steps (LP_ompi.cpp:648-655, :868-875).  The GPU reduces over the integrated-out velocity
+  // directions (lpgpu_marginal_sums) and over whole velocity space ((m_i, s_i) of lpgpu_moments_partial); the host
+  // evaluates the reference's closed forms at its 4 sub-points per cell.
+  FILE *fmarg = fopen(fmarg_name.c_str(), "w"), *fphi = fopen(fphi_name.c_str(), "w"), *fE = fopen(fE_name.c_str(), "w");
+  if (!fmarg || !fphi || !fE) die("cannot open the Marginals/PhiVals/FieldVals files under Data/");
+  const int np = 4, Nv = p.Nv;
+  const double dv = g.dv, dx = g.dx, ddv = dv / np, ddx = dx / np;
+  auto gridv = [&](double j) { return -p.Lv + (j + 0.5) * dv; };     // Gridv / Gridx, advection_1.cpp:15-21
+  auto gridx = [&](double i) { return (i + 0.5) * dx; };
+  if (p.homogeneous) {                                               // PrintMarginalLoc_Homo, MarginalCreation.cpp:118-158
+    for (int row = 0; row < 2; row++) {
+      for (int j1 = 0; j1 < Nv; j1++) for (int n1 = 0; n1 < np; n1++) for (int j2 = 0; j2 < Nv; j2++) for (int n2 = 0; n2 < np; n2++)
+        fprintf(fmarg, "%11.8g  ", row == 0 ? gridv(j1 - 0.5) + n1 * ddv : gridv(j2 - 0.5) + n2 * ddv);
+      fprintf(fmarg, "\n");
+    }
+  } else {                                                           // PrintMarginalLoc_Inhomo :81-116, PrintFieldLoc FieldCalculations.cpp:40-58
+    for (int row = 0; row < 2; row++) {
+      for (int i = 0; i < p.Nx; i++) for (int nx = 0; nx < np; nx++) for (int j1 = 0; j1 < Nv; j1++) for (int nv = 0; nv < np; nv++)
+        fprintf(fmarg, "%11.8g  ", row == 0 ? gridx(i - 0.5) + nx * ddx : gridv(j1 - 0.5) + nv * ddv);
+      fprintf(fmarg, "\n");
+    }
+    for (int i = 0; i < p.Nx; i++) for (int nx = 0; nx < np; nx++) {
+      fprintf(fphi, "%11.8g  ", gridx(i - 0.5) + nx * ddx);
+      fprintf(fE, "%11.8g  ", gridx(i - 0.5) + nx * ddx);
+    }
+    fprintf(fphi, "\n"); fprintf(fE, "\n");
+  }
+  std::vector<double> msum((size_t)4 * (p.homogeneous ? Nv * Nv : ncell * Nv));
+  auto print_marginal_and_field = [&]() {
+    CHECK(lpgpu_marginal_sums(ctx, msum.data()));
+    if (p.homogeneous) {                                             // PrintMarginal_Homo :196-219 with f_marg_Homo :43-59
+      for (int j1 = 0; j1 < Nv; j1++) for (int n1 = 0; n1 < np; n1++) for (int j2 = 0; j2 < Nv; j2++) for (int n2 = 0; n2 < np; n2++) {
+        const double d1 = gridv(j1 - 0.5) + n1 * ddv - gridv(j1), d2 = gridv(j2 - 0.5) + n2 * ddv - gridv(j2);
+        const double *q = &msum[(size_t)4 * (j1 * Nv + j2)];
+        fprintf(fmarg, "%11.8g  ", dv * q[0] + q[1] * d1 + q[2] * d2 + q[3] * ((d1 * d1 + d2 * d2) / dv + dv / 12));
+      }
+      fprintf(fmarg, "\n");
+      return;
+    }
+    for (int i = 0; i < p.Nx; i++) for (int nx = 0; nx < np; nx++) for (int j1 = 0; j1 < Nv; j1++) for (int nv = 0; nv < np; nv++) {
+      const double xd = gridx(i - 0.5) + nx * ddx - gridx(i), vd = gridv(j1 - 0.5) + nv * ddv - gridv(j1);   // PrintMarginal_Inhomo :162-194
+      const double *q = &msum[(size_t)4 * (i * Nv + j1)];
+      fprintf(fmarg, "%11.8g  ", dv * dv * q[0] + dv * dv * q[1] * xd / dx + dv * q[2] * vd + q[3] * (vd * vd + dv * dv / 6));
+    }
+    fprintf(fmarg, "\n");
+    // PrintFieldData_Normal (FieldCalculations.cpp:331-355): phi at 4 points per cell; computePhi_Normal (:244-329) in
+    // terms of m_q = scalev sum(U0 + U5/4), s_q = scalev sum U1 and computePhi_x_0 (:223-243)
+    double m5[5];
+    std::vector<double> ms((size_t)2 * ncell);
+    CHECK(lpgpu_moments_partial(ctx, m5, ms.data()));
+    double P = 0., acc = 0.;
+    std::vector<double> Pq(p.Nx), Sq(p.Nx);                           // P_q = sum_{q' < q} m_q',  S_q = sum_{q' < q} (P_q' + m_q'/2 - s_q'/12)
+    for (int q = 0; q < p.Nx; q++) { Pq[q] = P; Sq[q] = acc; acc += P + 0.5 * ms[2 * q] - ms[2 * q + 1] / 12.; P += ms[2 * q]; }
+    const double ce = 0.5 * p.Lx - acc * dx * dx / p.Lx;
+    for (int i = 0; i < p.Nx; i++) for (int nx = 0; nx < np; nx++) {
+      const double x = gridx(i - 0.5) + nx * ddx, xd = x - gridx(i - 0.5), xm = x - gridx(i);
+      const double xe = xm * xm * xm / (6. * dx) - dx * xm / 8. - dx * dx / 24.;
+      const double phi = Sq[i] * dx * dx + Pq[i] * dx * xd + ms[2 * i] * xd * xd / 2. + ms[2 * i + 1] * xe - x * x / 2 - ce * x;
+      fprintf(fphi, "%11.8g ", phi);
+    }
+    fprintf(fphi, "\n");
+  };
   diagnostics(0);
+  print_marginal_and_field();
   const auto t0 = std::chrono::steady_clock::now();
   for (int t = 0; t < nT; t++) {
     CHECK(lpgpu_step(ctx, 1));
     diagnostics(t + 1);
+    if (t % 20 == 0) print_marginal_and_field();                     // after steps 1, 21, 41, ...: the reference tests its 0-based counter (LP_ompi.cpp:79, :868)
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("\nTime duration for %d time steps is %gs\n\n", nT, secs);
   fclose(fmom);
   fclose(fent);
+  fclose(fmarg); fclose(fphi); fclose(fE);
   CHECK(lpgpu_download_U(ctx, U.data()));
   FILE *fu = fopen(fu_name.c_str(), "wb");
   if (fu) { fwrite(U.data(), sizeof(double), U.size(), fu); fclose(fu); }

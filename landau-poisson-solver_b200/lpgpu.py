@@ -42,7 +42,7 @@ EXPORTS = [
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
-    "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak", "lpgpu_diagnostics_partial",
+    "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums",
 ]
 
 _lib = None
@@ -65,7 +65,7 @@ def load_library():
     for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_sample_device"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.lpgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
-    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial"):
+    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
     for name in ("lpgpu_step", "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_eval_device"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_int]
@@ -237,6 +237,13 @@ class LPGpu:
         ms = np.zeros(2 * self.ncell)
         self._check(self.L.lpgpu_moments_partial(self.h, _ptr(out), _ptr(ms)))
         return out, ms
+
+    def marginal_sums(self):
+        """[rows, 4] sums PrintMarginal needs: rows = (x cell, j1) or, homogeneous, (j1, j2)."""
+        rows = self.Nv * self.Nv if self.homogeneous else self.ncell * self.Nv
+        out = np.empty((rows, 4))
+        self._check(self.L.lpgpu_marginal_sums(self.h, _ptr(out)))
+        return out
 
     def eleE_from_ms(self, ms_all):
         ms_all = _f64(ms_all)
