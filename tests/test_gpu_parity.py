@@ -222,15 +222,17 @@ def test_two_stream_step(pkg):
     g.close()
 
 
-@pytest.mark.parametrize("N", [24, 32])
-def test_full_size_step_two_algorithms_and_conservation(pkg, N):
-    """BASELINE sizes (N = Nv = 24 and 32), where the oracle is too slow for a whole step: the fused FFT-convolution
-    chain (variant 0) and the direct O(N^6) kernel with the unfused transforms/conservation (variant 3) are two
-    independent implementations of the same timestep and must agree to round-off; the step conserves mass, and
-    the collision part momentum and energy, as the reference's does."""
+@pytest.mark.parametrize("N,Nv", [(16, 24), (32, 32)])
+def test_full_size_step_two_algorithms_and_conservation(pkg, N, Nv):
+    """BASELINE sizes (Nv = 24 with the reference's own pairing N = 16, and N = Nv = 32), where the oracle is too slow
+    for a whole step: the fused FFT-convolution chain (variant 0) and the direct O(N^6) kernel with the unfused
+    transforms/conservation (variant 3) are two independent implementations of the same timestep and must agree to
+    round-off; the step conserves mass, and the collision part momentum and energy, as the reference's does.
+    (N = 24 is left out on purpose: the unmodified reference itself blows up there -- max|dU| = 2.4e10 after one
+    homogeneous step, reproduced by the GPU path to 1e-13)"""
     from lpsolver_b200 import solver
-    cfg = dict(Nx=2, Nv=N, N=N, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
-    U = solver.set_init_ld(cfg["Nx"], N, cfg["Lv"], cfg["Lx"], 0.5, 2 * np.pi / 4., True)
+    cfg = dict(Nx=2, Nv=Nv, N=N, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
+    U = solver.set_init_ld(cfg["Nx"], Nv, cfg["Lv"], cfg["Lx"], 0.5, 2 * np.pi / 4., True)
     out, mom = {}, {}
     for variant in (0, 3):
         g = pkg.LPGpu(computeq_variant=variant, **cfg)
@@ -249,7 +251,7 @@ def test_full_size_step_two_algorithms_and_conservation(pkg, N):
     assert abs((m1[4] + m1[5]) - (m0[4] + m0[5])) < 1e-4 * abs(m0[4] + m0[5])   # total energy drifts only at O(dt) splitting level
     # collision-only (homogeneous) step: mass, momentum and energy of the DG solution are kept
     h = pkg.LPGpu(homogeneous=True, **dict(cfg, Nx=1))
-    h.upload_U(solver.set_init_4h_homo(N, cfg["Lv"]))
+    h.upload_U(solver.set_init_4h_homo(Nv, cfg["Lv"]))
     a = h.moments()
     h.step(2)
     b = h.moments()
