@@ -45,6 +45,9 @@ typedef struct lpgpu_params {
                                otherwise the register-tiled direct sum;
                            1 = simple one-thread-per-xi direct kernel (on-device cross-check);
                            2 = FFT convolutions; 3 = register-tiled direct sum (the O(N^6) form of the reference) */
+  int full_and_linear;  /* reference flag FullandLinear (test 3): electron-ion term next to Q(f,f) -- ComputeQ_FandL,
+                           conserveAllMoments_FandL, RK4_FandL (collisionRoutines_1.cpp:605-689, 800-901, 987-1085;
+                           conservationRoutines.cpp:102-129).  Runs through the direct-sum kernel (correct, not tuned). */
 } lpgpu_params;
 
 const char *lpgpu_last_error(void);

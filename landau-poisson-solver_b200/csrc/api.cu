@@ -75,6 +75,11 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
 #define A_(x) if (rc == LPGPU_OK) rc = (x)
   A_(dev_upload(&c->d_eta, t.eta));
   A_(dev_upload(&c->d_G, t.G));
+  if (p->full_and_linear) {
+    A_(dev_upload(&c->d_Gl, t.Gl));
+    std::vector<double> cl(t.CCt_lin, t.CCt_lin + 4);
+    A_(dev_upload(&c->d_CCt_lin, cl));
+  }
   A_(dev_upload(&c->d_C5, t.C5));
   { std::vector<double> cct(t.CCt, t.CCt + 25); A_(dev_upload(&c->d_CCt, cct)); }
   A_(dev_upload(&c->d_Wfwd, t.Wfwd));
@@ -113,7 +118,8 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_alloc(&c->d_tmp, 2 * n3));
   for (int s = 0; s < 4; s++) A_(dev_alloc(&c->d_q[s], 2 * n3));
   A_(dev_alloc(&c->d_lam, (size_t)5 * 8 * c->cap_cells + 8));
-  A_(dev_alloc(&c->d_cpart, (size_t)5 * p->N * c->cap_cells));   // conservation partials: 8 chunks x 5 per cell
+  A_(dev_alloc(&c->d_cpart, (size_t)5 * p->N * c->cap_cells));
+  if (p->full_and_linear) A_(dev_alloc(&c->d_ql, 2 * n3));   // conservation partials: 8 chunks x 5 per cell
   A_(dev_alloc(&c->d_B, (size_t)2 * c->cap_cells * p->N * 4 * p->Nv * p->Nv));
 #undef A_
   if (rc != LPGPU_OK) { lpgpu_finalize(c); return rc; }
@@ -128,7 +134,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   cudaDeviceSynchronize();
   double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
-                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart};
+                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart, c->d_Gl, c->d_ql, c->d_CCt_lin};
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
@@ -238,6 +244,18 @@ static int eval_async(lpgpu_ctx *c, const double *f, double *q, int B)
 static int collide_async(lpgpu_ctx *c)
 {
   const int B = c->ncell;
+  if (c->p.full_and_linear) {
+    // RK4_FandL_Inhomo / _Homo (collisionRoutines_1.cpp:800-901, 987-1085): every stage spectrum is qHat + qHat_linear
+    // after conserveAllMoments_FandL; both later stage vectors carry dt (:842, :858), unlike RK4_Inhomo's third
+    LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, B));
+    for (int s = 0; s <= 3; s++) {
+      LP_TRY(lp_launch_fft3d(c, s == 0 ? c->d_f : c->d_f1, true, c->d_fhat, B));
+      LP_TRY(lp_launch_computeQ_fandl(c, c->d_fhat, c->d_q[s], c->d_ql, B));
+      LP_TRY(lp_launch_conserve_fandl(c, c->d_q[s], c->d_ql, B));
+      if (s < 3) LP_TRY(lp_launch_fs(c, c->d_q[s], s == 0 ? 1 : 2, nullptr, B));
+    }
+    return lp_launch_project(c, c->d_U[0], B);
+  }
   if (lp_fc3_available(c)) {
     // fused chain: per stage  fft3D(j,k) -> [fft3D(i) + z-lines] -> F2 -> [inverse z + conservation dots]
     //                         -> [conservation correction + FS(i)] -> FS(j,k) + RK stage update

@@ -523,6 +523,99 @@ int lp_launch_conserve(lpgpu_ctx *c, double *q, int B)
   return LPGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// FullandLinear variant (reference test 3).  ComputeQ_FandL (collisionRoutines_1.cpp:605-689): next to the
+// quadratic sum, qHat_linear[xi] = sum_w h_eta^3 wt(w) scale3 gHat3_linear(xi, w) fhat[xi + N/2 - w]; qHat receives
+// both.  One thread per xi (the direct form; this variant is a parity row, not a tuned path).
+__global__ void __launch_bounds__(128) k_computeQ_fandl(const double2 *__restrict__ fhat, double2 *__restrict__ q, double2 *__restrict__ ql,
+                                                        const double *__restrict__ G, const double *__restrict__ Gl,
+                                                        const double *__restrict__ eta, int N, double scale3, long long total)
+{
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int N3 = N * N * N, H = N / 2;
+  const long long cell = t / N3; const int xi = (int)(t % N3);
+  const int k = xi % N, j = (xi / N) % N, i = xi / (N * N);
+  const double2 *fh = fhat + cell * N3;
+  int si, ei, sj, ej, sk, ek;
+  lp_window(N, i, si, ei); lp_window(N, j, sj, ej); lp_window(N, k, sk, ek);
+  double t0 = 0., t1 = 0., t01 = 0., t11 = 0.;
+  for (int l = si; l < ei; l++) {
+    const int x = i + H - l; const double e1 = eta[i] - eta[l];
+    for (int m = sj; m < ej; m++) {
+      const int y = j + H - m; const double e2 = eta[j] - eta[m];
+      for (int n = sk; n < ek; n++) {
+        const int z = k + H - n; const double e3 = eta[k] - eta[n];
+        const int w = n + N * (m + N * l);
+        const double *g = G + 7LL * w, *gl = Gl + 3LL * w;
+        const double quad = g[1] * e1 * e1 + g[2] * e2 * e2 + g[3] * e3 * e3 + g[4] * e1 * e2 + g[5] * e1 * e3 + g[6] * e2 * e3;
+        const double W = g[0] - quad, W1 = -(scale3 * quad + gl[0] * e1 + gl[1] * e2 + gl[2] * e3);
+        const double2 a = fh[w], b = fh[z + N * (y + N * x)];
+        const double l0 = W1 * b.x, l1 = W1 * b.y;
+        t0 += W * (a.x * b.x - a.y * b.y) + l0;
+        t1 += W * (a.x * b.y + a.y * b.x) + l1;
+        t01 += l0; t11 += l1;
+      }
+    }
+  }
+  q[t] = make_double2(t0, t1);
+  ql[t] = make_double2(t01, t11);
+}
+int lp_launch_computeQ_fandl(lpgpu_ctx *c, const double *fhat, double *q, double *ql, int B)
+{
+  const long long total = (long long)B * c->N3;
+  k_computeQ_fandl<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(
+      reinterpret_cast<const double2 *>(fhat), reinterpret_cast<double2 *>(q), reinterpret_cast<double2 *>(ql), c->d_G, c->d_Gl, c->d_eta,
+      c->p.N, c->tab.scale3, total);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+// conserveAllMoments_FandL (conservationRoutines.cpp:102-129): five rows on qHat, mass and energy rows on qHat_linear,
+// then qHat += qHat_linear (first loop of RK4_FandL_*, collisionRoutines_1.cpp:806-810).  One block per cell.
+__global__ void __launch_bounds__(512) k_conserve_fandl(double2 *__restrict__ q, double2 *__restrict__ ql, const double *__restrict__ C5,
+                                                        const double *__restrict__ CCt, const double *__restrict__ CCt_lin, int N3)
+{
+  __shared__ double red[7][16];
+  __shared__ double lam[7];
+  double2 *qc = q + (long long)blockIdx.x * N3, *qlc = ql + (long long)blockIdx.x * N3;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  double s[7] = {0., 0., 0., 0., 0., 0., 0.};
+  for (int idx = tid; idx < N3; idx += blockDim.x) {
+    const double2 v = qc[idx], u = qlc[idx];
+    s[0] += v.x * C5[idx]; s[1] += v.y * C5[N3 + idx]; s[2] += v.y * C5[2 * N3 + idx];
+    s[3] += v.y * C5[3 * N3 + idx]; s[4] += v.x * C5[4 * N3 + idx];
+    s[5] += u.x * C5[idx]; s[6] += u.x * C5[4 * N3 + idx];
+  }
+  #pragma unroll
+  for (int m = 0; m < 7; m++) {
+    double v = s[m];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[m][wid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot[7];
+    for (int m = 0; m < 7; m++) { double v = 0.; for (int w = 0; w < nw; w++) v += red[m][w]; tot[m] = v; }
+    for (int a = 0; a < 5; a++) { double v = 0.; for (int b = 0; b < 5; b++) v += CCt[b + a * 5] * tot[b]; lam[a] = v; }
+    for (int a = 0; a < 2; a++) lam[5 + a] = CCt_lin[0 + a * 2] * tot[5] + CCt_lin[1 + a * 2] * tot[6];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N3; idx += blockDim.x) {
+    double2 v = qc[idx], u = qlc[idx];
+    v.x -= (C5[idx] * lam[0] + C5[4 * N3 + idx] * lam[4]);
+    v.y -= (C5[N3 + idx] * lam[1] + C5[2 * N3 + idx] * lam[2] + C5[3 * N3 + idx] * lam[3]);
+    u.x -= (C5[idx] * lam[5] + C5[4 * N3 + idx] * lam[6]);
+    qlc[idx] = u;
+    qc[idx] = make_double2(v.x + u.x, v.y + u.y);
+  }
+}
+int lp_launch_conserve_fandl(lpgpu_ctx *c, double *q, double *ql, int B)
+{
+  k_conserve_fandl<<<B, 512, 0, c->stream>>>(reinterpret_cast<double2 *>(q), reinterpret_cast<double2 *>(ql), c->d_C5, c->d_CCt, c->d_CCt_lin, c->N3);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
 int lp_launch_conserve_from_parts(lpgpu_ctx *c, double *q, const double *part, int B)
 {
   k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, part, c->N3, c->p.N);

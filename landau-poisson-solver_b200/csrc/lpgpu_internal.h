@@ -13,6 +13,8 @@ struct LpTables {
   double Lv, dv, scalev, scaleL, scale3, L_eta, h_v, h_eta;
   std::vector<double> v, eta, wt;          // N
   std::vector<double> G;                   // 7*N^3  folded kernel symbols, [w*7 + t]
+  std::vector<double> Gl;                  // 3*N^3  FullandLinear: h_eta^3 wt scale3 sum_i S_ij(w) w_i, [w*3 + j]
+  double CCt_lin[4];                       // (C C^T)^-1 of the mass and energy rows
   std::vector<double> C5;                  // 5*N^3  conservation rows, [q*5 + m] (interleaved)
   double CCt[25];                          // (C C^T)^-1
   std::vector<double> Wfwd, Winv;          // N*N complex: DFT twiddle matrices exp(-/+ 2 pi i jk/N)
@@ -50,6 +52,7 @@ struct lpgpu_ctx {
   double *d_fhat, *d_tmp;                  // complex N^3
   double *d_q[4];                          // complex N^3: qHat, Q1_fft..Q3_fft
   double *d_lam;                           // 5 per cell
+  double *d_Gl, *d_ql, *d_CCt_lin;          // FullandLinear: linear symbols, qHat_linear work array, 2x2 inverse
   double *d_cpart;                         // [cell][N][5] partial conservation dots written by the fused ComputeQ
   double *d_B;                             // projection intermediate: ncell*N*4*Nv^2 complex
   size_t cap_cells;        // capacity (in cells) of the collision work arrays
@@ -119,6 +122,9 @@ int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mod
 int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B);
 int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B);
 int lp_launch_conserve(lpgpu_ctx *c, double *q, int B);
+// FullandLinear: ComputeQ_FandL and conserveAllMoments_FandL followed by qHat += qHat_linear (RK4_FandL's first loop)
+int lp_launch_computeQ_fandl(lpgpu_ctx *c, const double *fhat, double *q, double *ql, int B);
+int lp_launch_conserve_fandl(lpgpu_ctx *c, double *q, double *ql, int B);
 int lp_launch_project(lpgpu_ctx *c, double *planes, int B);
 // ---- advection.cu
 int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes);

@@ -84,6 +84,7 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
 
   // ---- folded kernel symbols G[w][0..6] = h_eta^3 wt^3 * {A, S11, S22, S33, 2 S12, 2 S13, 2 S23}
   t.G.assign((size_t)7 * N3, 0.);
+  t.Gl.assign((size_t)3 * N3, 0.);
   const double R = p.Lv, pref = t.h_eta * t.h_eta * t.h_eta;
   for (int l = 0; l < N; l++)
     for (int m = 0; m < N; m++)
@@ -98,6 +99,13 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
         double *g = &t.G[(size_t)7 * (n + N * (m + N * l))];
         g[0] = w * A; g[1] = w * S11; g[2] = w * S22; g[3] = w * S33;
         g[4] = w * 2. * S12; g[5] = w * 2. * S13; g[6] = w * 2. * S23;
+        // FullandLinear (gHat3_linear, collisionRoutines_1.cpp:193-218): -sum_ij S_ij xi_i (xi_j - w_j) with xi = e + w is
+        // -sum_ij S_ij e_i e_j - sum_j (sum_i S_ij w_i) e_j; the second symbol, folded with h_eta^3 wt scale3 (:662)
+        double *gl = &t.Gl[(size_t)3 * (n + N * (m + N * l))];
+        const double ws = w * t.scale3;
+        gl[0] = ws * (S11 * k1 + S12 * k2 + S13 * k3);
+        gl[1] = ws * (S12 * k1 + S22 * k2 + S23 * k3);
+        gl[2] = ws * (S13 * k1 + S23 * k2 + S33 * k3);
       }
 
   // ---- conservation rows, planar [m*N^3 + q]: m = 0 mass (real), 1..3 momentum (imag), 4 energy (real)
@@ -127,6 +135,13 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
       t.CCt[i * 5 + j] = s;
     }
   invert_in_place(t.CCt, 5);
+  {
+    // CCt_linear (conservationRoutines.cpp:222-238): mass and energy rows only
+    double a = 0., b = 0., d = 0.;
+    for (int q = 0; q < N3; q++) { a += t.C5[q] * t.C5[q]; b += t.C5[q] * t.C5[(size_t)4 * N3 + q]; d += t.C5[(size_t)4 * N3 + q] * t.C5[(size_t)4 * N3 + q]; }
+    t.CCt_lin[0] = a; t.CCt_lin[1] = b; t.CCt_lin[2] = b; t.CCt_lin[3] = d;
+    invert_in_place(t.CCt_lin, 2);
+  }
 
   // ---- shifted transforms (collisionRoutines_1.cpp:285-319 fft3D, :363-398 FS).  The reference multiplies
   // by a pre-phase, runs an unnormalised DFT and multiplies by a post-phase; its phase angles are rounded

@@ -174,7 +174,7 @@ int main(int argc, char **argv)
   if (nic == 0) die("No initial condition has been chosen.");
   if (nic > 1) die("Please ONLY set ONE of Damping, TwoStream, FourHump or TwoHump to true.");
   if (d.flag("First") == d.flag("Second")) die("Need to choose if this is a first run or a subsequent one (First / Second).");
-  for (const char *n : {"FullandLinear", "LinearLandau", "MassConsOnly"})
+  for (const char *n : {"LinearLandau", "MassConsOnly"})
     if (d.flag(n)) die(std::string(n) + " is not part of the GPU hot path.");
   if (ic == "Doping" || ic == "TwoHump") die(ic + " initial/boundary conditions are not part of the GPU hot path.");
   if (!d.has("flag")) die("Please set the name of 'flag' in the input file.");
@@ -193,6 +193,7 @@ int main(int argc, char **argv)
   else p.Lx = d.num(ic + "/Lx", 2 * M_PI / k_wave);
   if (p.homogeneous && ic != "FourHump") die("Trying to run the space homogeneous code, but current IC is not available (only FourHump).");
   p.x_begin = 0; p.x_count = p.homogeneous ? 1 : p.Nx; p.device = device; p.computeq_variant = 0;
+  p.full_and_linear = d.flag("FullandLinear");
 
   char name[512], tail[400];
   const std::string flag = d.str("flag");

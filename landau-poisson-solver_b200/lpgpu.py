@@ -23,7 +23,7 @@ class Params(C.Structure):
                 ("Lv", C.c_double), ("Lx", C.c_double), ("nu", C.c_double), ("dt", C.c_double),
                 ("gamma", C.c_int), ("homogeneous", C.c_int),
                 ("x_begin", C.c_int), ("x_count", C.c_int), ("device", C.c_int),
-                ("computeq_variant", C.c_int)]
+                ("computeq_variant", C.c_int), ("full_and_linear", C.c_int)]
 
 
 class Exchange(C.Structure):
@@ -106,12 +106,12 @@ class LPGpu:
     function names (RK3 -> advect_rk3, ComputeQ, conserveMoments, FS, fft3D, setInit_spectral)."""
 
     def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, gamma=-3, x_begin=0, x_count=None,
-                 device=0, computeq_variant=0):
+                 device=0, computeq_variant=0, full_and_linear=False):
         self.L = load_library()
         if x_count is None:
             x_count = 1 if homogeneous else Nx
         self.params = Params(Nx, Nv, N, Lv, Lx, nu, dt, gamma, int(bool(homogeneous)), x_begin, x_count, device,
-                             computeq_variant)
+                             computeq_variant, int(bool(full_and_linear)))
         self.Nx, self.Nv, self.N = Nx, Nv, N
         self.homogeneous = bool(homogeneous)
         self.ncell = 1 if homogeneous else x_count

@@ -71,7 +71,8 @@ class RunConfig:
         self.second = _bool(kv, "Second")
         self.second_name = kv.get("Second/Name")
         self.homogeneous = _bool(kv, "Homogeneous")
-        for unsupported in ("FullandLinear", "LinearLandau", "MassConsOnly"):
+        self.full_and_linear = _bool(kv, "FullandLinear")
+        for unsupported in ("LinearLandau", "MassConsOnly"):
             if _bool(kv, unsupported):
                 raise NotImplementedError("%s is outside the GPU hot path (SURVEY.md section 8f.4)" % unsupported)
         if self.ic in ("Doping", "TwoHump"):
@@ -254,7 +255,7 @@ class _DeviceBuffer:
 class ShardedSolver:
     """One rank of the x-sharded solver.  world == 1 needs no process group."""
 
-    def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None):
+    def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None, full_and_linear=False):
         self.rank, self.world, self.dist = rank, world, dist
         self.homogeneous = bool(homogeneous)
         if homogeneous:
@@ -262,7 +263,7 @@ class ShardedSolver:
         else:
             self.x_begin, self.x_count = shard_range(Nx, world, rank)
         self.g = lpgpu.LPGpu(Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=homogeneous, x_begin=self.x_begin,
-                             x_count=self.x_count, device=device)
+                             x_count=self.x_count, device=device, full_and_linear=full_and_linear)
         self.nu = nu
         self._ex = None
         if world > 1 and not homogeneous:
@@ -329,7 +330,8 @@ def run_from_input_file(path="LPsolver-input.txt", outdir=".", device=0, quiet=F
     """Single-GPU equivalent of running the reference's `solver` in a directory holding
     LPsolver-input.txt: writes Data/Moments_*.dc with one row per step (row 1 = initial state)."""
     cfg = RunConfig.from_file(path)
-    s = ShardedSolver(cfg.Nx, cfg.Nv, cfg.N, cfg.Lv, cfg.Lx, cfg.nu, cfg.dt, homogeneous=cfg.homogeneous, device=device)
+    s = ShardedSolver(cfg.Nx, cfg.Nv, cfg.N, cfg.Lv, cfg.Lx, cfg.nu, cfg.dt, homogeneous=cfg.homogeneous, device=device,
+                      full_and_linear=cfg.full_and_linear)
     s.upload(cfg.initial_condition())
     out = os.path.join(outdir, cfg.moments_filename())
     os.makedirs(os.path.dirname(out), exist_ok=True)

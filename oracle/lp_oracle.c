@@ -19,6 +19,8 @@
 
 struct lpo_ctx {
   int Nx, Nv, N, homogeneous, gamma, direct_intmodes;
+  int fandl;                      /* FullandLinear: electron-ion term Q(f, ions) next to Q(f,f) */
+  double CCt_lin[4];              /* (C C^T)^-1 of the mass and energy rows (conservationRoutines.cpp:222-238) */
   int size_v, size_ft, ncell;
   double Lv, Lx, nu, dt, dv, dx, scalev, scaleL, scale3;
   double L_eta, h_v, h_eta;
@@ -160,6 +162,11 @@ static void build_conservation(lpo_ctx *c)
       c->CCt[i * 5 + j] = t;
     }
   invert_small(c->CCt, 5);
+  /* CCt_linear: rows C1_5[0], C1_5[4] only (conservationRoutines.cpp:222-238) */
+  double a = 0., b = 0., d = 0.;
+  for (int q = 0; q < N3; q++) { a += c->C5[q] * c->C5[q]; b += c->C5[q] * c->C5[4 * N3 + q]; d += c->C5[4 * N3 + q] * c->C5[4 * N3 + q]; }
+  c->CCt_lin[0] = a; c->CCt_lin[1] = b; c->CCt_lin[2] = b; c->CCt_lin[3] = d;
+  invert_small(c->CCt_lin, 2);
 }
 void lpo_get_conservation(const lpo_ctx *c, double *C5, double *CCt25)
 {
@@ -566,6 +573,112 @@ void lpo_RK4(const lpo_ctx *c, const double *f, int cell, const double *qHat, co
   free(out); free(Q); free(Q1); free(f1); free(q1); free(q2); free(q3); free(tp);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* FullandLinear variant (reference test 3): ComputeQ_FandL collisionRoutines_1.cpp:605-689,
+ * gHat3_linear :193-218, conserveAllMoments_FandL conservationRoutines.cpp:102-129,
+ * RK4_FandL_Inhomo/_Homo collisionRoutines_1.cpp:800-901 / 987-1085. */
+void lpo_set_fandl(lpo_ctx *c, int on) { c->fandl = on; }
+static double weight_lin_at(const lpo_ctx *c, int i, int j, int k, int l, int m, int n)
+{
+  const int N3 = c->size_ft, w = n + c->N * (m + c->N * l);
+  double S[3][3];
+  S[0][0] = c->Sh[1 * N3 + w]; S[1][1] = c->Sh[2 * N3 + w]; S[2][2] = c->Sh[3 * N3 + w];
+  S[0][1] = S[1][0] = c->Sh[4 * N3 + w];
+  S[0][2] = S[2][0] = c->Sh[5 * N3 + w];
+  S[1][2] = S[2][1] = c->Sh[6 * N3 + w];
+  double z[3] = {c->eta[i], c->eta[j], c->eta[k]}, kk[3] = {c->eta[l], c->eta[m], c->eta[n]};
+  double res = 0.;
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) res += S[a][b] * z[a] * (z[b] - kk[b]);
+  return -res;
+}
+void lpo_ComputeQ_FandL(const lpo_ctx *c, const double *f, double *qHat, double *qLin)
+{
+  const int N = c->N, N3 = c->size_ft;
+  double *in = (double *)malloc(sizeof(double) * 2 * N3), *fh = (double *)malloc(sizeof(double) * 2 * N3);
+  for (int q = 0; q < N3; q++) { in[2 * q] = f[q]; in[2 * q + 1] = 0.; }
+  lpo_fft3D(c, in, fh);
+  const double pref = c->h_eta * c->h_eta * c->h_eta, *wt = c->wt, s3 = c->scale3;
+  #pragma omp parallel for collapse(2) schedule(dynamic)
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++)
+      for (int k = 0; k < N; k++) {
+        int si, ei, sj, ej, sk, ek;
+        window(N, i, &si, &ei); window(N, j, &sj, &ej); window(N, k, &sk, &ek);
+        double t0 = 0., t1 = 0., t01 = 0., t11 = 0.;
+        for (int l = si; l < ei; l++)
+          for (int m = sj; m < ej; m++)
+            for (int n = sk; n < ek; n++) {
+              int x = i + N / 2 - l, y = j + N / 2 - m, z = k + N / 2 - n;
+              int a = n + N * (m + N * l), b = z + N * (y + N * x);
+              double W = weight_at(c, i, j, k, l, m, n), W1 = weight_lin_at(c, i, j, k, l, m, n);
+              double pw = pref * wt[l] * wt[m] * wt[n];
+              t0 += pw * (W * (fh[2 * a] * fh[2 * b] - fh[2 * a + 1] * fh[2 * b + 1]) + s3 * W1 * fh[2 * b]);
+              t1 += pw * (W * (fh[2 * a] * fh[2 * b + 1] + fh[2 * a + 1] * fh[2 * b]) + s3 * W1 * fh[2 * b + 1]);
+              t01 += pw * s3 * W1 * fh[2 * b];
+              t11 += pw * s3 * W1 * fh[2 * b + 1];
+            }
+        int q = k + N * (j + N * i);
+        qHat[2 * q] = t0; qHat[2 * q + 1] = t1;
+        qLin[2 * q] = t01; qLin[2 * q + 1] = t11;
+      }
+  free(in); free(fh);
+}
+void lpo_conserveMoments_FandL(const lpo_ctx *c, double *qHat, double *qLin)
+{
+  const int N3 = c->size_ft;
+  double tp[2] = {0., 0.}, b[2];
+  for (int q = 0; q < N3; q++) { tp[0] += qLin[2 * q] * c->C5[q]; tp[1] += qLin[2 * q] * c->C5[4 * N3 + q]; }
+  lpo_conserveMoments(c, qHat);
+  for (int i = 0; i < 2; i++) { b[i] = 0.; for (int j = 0; j < 2; j++) b[i] += c->CCt_lin[j + i * 2] * tp[j]; }
+  for (int q = 0; q < N3; q++) qLin[2 * q] -= (c->C5[q] * b[0] + c->C5[4 * N3 + q] * b[1]);
+}
+static void project_update(const lpo_ctx *c, const double *Qc, int cell, const double *U, double *dU)
+{
+  const double dt = c->dt, sc = c->scalev, sL = c->scaleL, s3 = c->scale3;
+  double *tp = (double *)malloc(sizeof(double) * 5 * c->size_v);
+  if (c->direct_intmodes) project_direct(c, Qc, tp); else project_separable(c, Qc, tp);
+  for (int kt = 0; kt < c->size_v; kt++) {
+    size_t kv = (size_t)cell * c->size_v + kt;
+    double t0 = U[kv * 6 + 0] + U[kv * 6 + 5] / 4. + dt * tp[5 * kt + 0] / sc / sL / s3;
+    double t2 = U[kv * 6 + 2] + dt * tp[5 * kt + 1] * 12. / sc / sL / s3;
+    double t3 = U[kv * 6 + 3] + dt * tp[5 * kt + 2] * 12. / sc / sL / s3;
+    double t4 = U[kv * 6 + 4] + dt * tp[5 * kt + 3] * 12. / sc / sL / s3;
+    double t5 = U[kv * 6 + 0] / 4. + U[kv * 6 + 5] * 19. / 240. + dt * tp[5 * kt + 4] / sc / sL / s3;
+    dU[5 * kt + 0] = 19 * t0 / 4. - 15 * t5;
+    dU[5 * kt + 4] = 60 * t5 - 15 * t0;
+    dU[5 * kt + 1] = t2; dU[5 * kt + 2] = t3; dU[5 * kt + 3] = t4;
+  }
+  free(tp);
+}
+/* qHat, qLin: conserved first-stage spectra; qHat is overwritten by qHat + qLin as in the reference */
+void lpo_RK4_FandL(const lpo_ctx *c, const double *f, int cell, double *qHat, const double *qLin, const double *U, double *dU)
+{
+  const int N3 = c->size_ft;
+  const double dt = c->dt, nu = c->nu;
+  double *out = (double *)malloc(sizeof(double) * 2 * N3);
+  double *Q = (double *)malloc(sizeof(double) * N3), *Q1 = (double *)malloc(sizeof(double) * N3), *f1 = (double *)malloc(sizeof(double) * N3);
+  double *q[3], *ql = (double *)malloc(sizeof(double) * 2 * N3);
+  for (int s = 0; s < 3; s++) q[s] = (double *)malloc(sizeof(double) * 2 * N3);
+  for (int i = 0; i < 2 * N3; i++) qHat[i] += qLin[i];
+  lpo_FS(c, qHat, out);
+  for (int i = 0; i < N3; i++) { Q[i] = out[2 * i]; f1[i] = f[i] + dt * Q[i] * nu; }
+  for (int s = 0; s < 3; s++) {
+    lpo_ComputeQ_FandL(c, f1, q[s], ql);
+    lpo_conserveMoments_FandL(c, q[s], ql);
+    for (int i = 0; i < 2 * N3; i++) q[s][i] += ql[i];
+    if (s < 2) {
+      lpo_FS(c, q[s], out);
+      /* both later stage vectors carry dt here (:842, :858), unlike RK4_Inhomo's third stage */
+      for (int i = 0; i < N3; i++) { Q1[i] = out[2 * i]; f1[i] = f[i] + 0.5 * dt * Q[i] * nu + 0.5 * dt * Q1[i] * nu; }
+    }
+  }
+  for (int i = 0; i < 2 * N3; i++) out[i] = nu * (0.5 * qHat[i] + (q[0][i] + q[1][i] + q[2][i]) / 6.);
+  project_update(c, out, cell, U, dU);
+  free(out); free(Q); free(Q1); free(f1); free(ql);
+  for (int s = 0; s < 3; s++) free(q[s]);
+}
+
 /* collision branch of the time loop incl. the scatter into U: LP_ompi.cpp:669-754 */
 void lpo_collide_step(const lpo_ctx *c, double *U)
 {
@@ -575,6 +688,14 @@ void lpo_collide_step(const lpo_ctx *c, double *U)
   double *dU = (double *)malloc(sizeof(double) * 5 * (size_t)c->ncell * sv);
   lpo_setInit_spectral(c, U, f);
   for (int cell = 0; cell < c->ncell; cell++) {
+    if (c->fandl) {
+      double *ql = (double *)malloc(sizeof(double) * 2 * N3);
+      lpo_ComputeQ_FandL(c, f + (size_t)cell * N3, q, ql);
+      lpo_conserveMoments_FandL(c, q, ql);
+      lpo_RK4_FandL(c, f + (size_t)cell * N3, cell, q, ql, U, dU + 5 * (size_t)cell * sv);
+      free(ql);
+      continue;
+    }
     lpo_ComputeQ(c, f + (size_t)cell * N3, q);
     lpo_conserveMoments(c, q);
     lpo_RK4(c, f + (size_t)cell * N3, cell, q, U, dU + 5 * (size_t)cell * sv, NULL);

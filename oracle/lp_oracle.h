@@ -45,6 +45,12 @@ void lpo_conserveMoments(const lpo_ctx *c, double *qHat);
 void lpo_RK4(const lpo_ctx *c, const double *f, int cell, const double *qHat, const double *U,
              double *dU, double *q123);
 void lpo_collide_step(const lpo_ctx *c, double *U);
+/* FullandLinear variant (reference test 3): switches lpo_collide_step / lpo_step to ComputeQ_FandL,
+ * conserveAllMoments_FandL and RK4_FandL (collisionRoutines_1.cpp:605-689, 800-901, 987-1085;
+ * conservationRoutines.cpp:102-129) */
+void lpo_set_fandl(lpo_ctx *c, int on);
+void lpo_ComputeQ_FandL(const lpo_ctx *c, const double *f, double *qHat, double *qLin);
+void lpo_conserveMoments_FandL(const lpo_ctx *c, double *qHat, double *qLin);
 
 /* advection path */
 void lpo_field(const lpo_ctx *c, const double *U, double *out /* 1 + 4*Nx */);

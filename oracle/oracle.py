@@ -94,6 +94,20 @@ class PortOracle:
     def set_direct_intmodes(self, on):
         self._call("lpo_set_direct_intmodes", int(on))
 
+    def set_fandl(self, on=True):
+        """FullandLinear = True (reference test 3): collide_step / step use the *_FandL routines."""
+        self._call("lpo_set_fandl", int(on))
+
+    def ComputeQ_FandL(self, f):
+        q, ql = np.empty((self.N3, 2)), np.empty((self.N3, 2))
+        self._call("lpo_ComputeQ_FandL", _f64(f), q, ql)
+        return q, ql
+
+    def conserveMoments_FandL(self, q, ql):
+        q, ql = _f64(q).copy(), _f64(ql).copy()
+        self._call("lpo_conserveMoments_FandL", q, ql)
+        return q, ql
+
     def grids(self):
         v, e, w = (np.empty(self.N) for _ in range(3))
         self._call("lpo_get_grids", v, e, w)

@@ -77,6 +77,26 @@ def test_port_reproduces_Moments_Test0():
         U = P.step(U)
 
 
+def test_port_reproduces_Moments_Test3_full_and_linear():
+    """FullandLinear = True (ComputeQ_FandL, conserveAllMoments_FandL, RK4_FandL): every printed digit of the
+    non-noise columns of all six rows of tests/Moments_Test3.dc -- the reference's own golden pins this variant."""
+    gold = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test3.dc"]
+    P = PortOracle(**TEST0)
+    P.set_fandl(True)
+    U = P.SetInit_LD(0.2, 0.5)
+    for step in range(6):
+        m = P.moments(U)
+        row = [m[0], m[1], m[2], m[3], m[4], m[5], np.sqrt(m[5]), np.log(np.sqrt(m[5])), m[4] + m[5]]
+        for col in (0, 4, 5, 6, 7, 8):
+            assert abs(row[col] - gold[step][col]) <= 6e-8 * max(1.0, abs(gold[step][col])), (step, col)
+        if step == 5:
+            _gate(row, gold[5])
+        U = P.step(U)
+    # and it differs from the plain operator (Test0) where the golden files differ
+    gold0 = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test0.dc"]
+    assert abs(gold[5][4] - gold0[5][4]) > 5e-6
+
+
 def test_port_reproduces_Moments_Test4():
     gold = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test4.dc"]
     P = PortOracle(homogeneous=True, **TEST0)
