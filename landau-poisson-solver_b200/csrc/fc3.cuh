@@ -289,11 +289,13 @@ struct F1 {
     }
   }
   // Gs + a*astride + z*N + x: the slab of array a (shared: astride = N*N; straight from Gt + y*N*N: astride = N^3)
-  static LP_HD void lines(int tid, int cell, int y, const double *Gs, long long astride, const double2 *FS, const double *sE, double2 *Z)
+  // rounds [round_begin, round_end) of the five (two arrays each): a launch with few cells gives every round its own CTA
+  static LP_HD void lines(int tid, int cell, int y, const double *Gs, long long astride, const double2 *FS, const double *sE, double2 *Z,
+                          int round_begin = 0, int round_end = 5)
   {
     const int x = tid % N, r = (tid / N) % 3, slot = tid / (3 * N);
     #pragma unroll 1
-    for (int round = 0; round < 5; round++) {
+    for (int round = round_begin; round < round_end; round++) {
       const int a = round * 2 + slot;
       double2 a0[L], a1[L], yv[L];
       if (a < 7) {
@@ -339,6 +341,13 @@ struct F2 {
   {
     if (L == 16) { const int w = tid >> 5, lane = tid & 31; r = w >> 1; ky = (w & 1) * 24 + lane; return lane < 24; }
     r = tid / M; ky = tid % M; return tid < 3 * M;
+  }
+  // product range [p_begin, p_end) of split sp of nsplit (p = 0 and 1 stay together: p = 1 reuses p = 0's y transform)
+  static LP_HD void psplit(int sp, int nsplit, int &p_begin, int &p_end)
+  {
+    if (nsplit <= 1) { p_begin = 0; p_end = 7; return; }
+    p_begin = sp == 0 ? 0 : sp == 1 ? 3 : 5;
+    p_end = sp == 0 ? 3 : sp == 1 ? 5 : 7;
   }
   static LP_HD const double2 *plane(const double2 *Z, int cell, int a, int kz) { return Z + (((long long)cell * 10 + a) * M + kz) * (N * N); }
   static LP_HD void issue_loads(int tid, int cell, int kz, int p, const double2 *Z, double2 *IN)
@@ -440,12 +449,21 @@ template <int L>
 struct F3 {
   static constexpr int N = 2 * L, M = 3 * L, PN = N + 1, NT = 3 * N;
   static constexpr int SMEM_C2 = 3 * L * PN;
-  static LP_HD void zinverse(int tid, int cell, int xo, const double2 *C, double2 *T3)
+  // nsplit partial C arrays (split_stride apart) are summed on the way in: F2 may split its seven products over
+  // nsplit CTAs per (cell, kz) when few cells are in flight (the inverse transforms are linear)
+  template <int NSPLIT>
+  static LP_HD void zinverse(int tid, int cell, int xo, const double2 *C, double2 *T3, long long split_stride)
   {
     const int yo = tid % N, rz = tid / N;
     double2 c[L];
     #pragma unroll
-    for (int q = 0; q < L; q++) c[q] = C[(((long long)cell * M + rz * L + q) * N + xo) * N + yo];
+    for (int q = 0; q < L; q++) {
+      const double2 *src = C + (((long long)cell * M + rz * L + q) * N + xo) * N + yo;
+      double2 v = src[0];
+      #pragma unroll
+      for (int sp = 1; sp < NSPLIT; sp++) v = cadd(v, src[sp * split_stride]);
+      c[q] = v;
+    }
     inv_third<L>(c, rz);
     #pragma unroll
     for (int l = 0; l < L; l++) T3[(rz * L + l) * PN + yo] = c[l];

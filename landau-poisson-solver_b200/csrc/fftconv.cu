@@ -483,7 +483,9 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
       constexpr int Q = N / 4;
       const int j = tid / N, k = tid % N;
       const double2 *src = in + (((long long)cell * N) * N + y) * N + k;
-      double2 v[Q];
+      double2 v[Q], ph[Q];
+      #pragma unroll
+      for (int q = 0; q < Q; q++) ph[q] = post[((4 * q + j) * N + y) * N + k];     // issued with the data loads, not after the transform
       #pragma unroll
       for (int n = 0; n < Q; n++) {
         const double2 x0 = src[(long long)n * N * N], x1 = src[(long long)(n + Q) * N * N], x2 = src[(long long)(n + 2 * Q) * N * N],
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
       #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int i = 4 * q + j;
-        FS[i * K::P + k] = phase_mul(post[(i * N + y) * N + k], v[q]);
+        FS[i * K::P + k] = phase_mul(ph[q], v[q]);
       }
     }
     for (int t = tid; t < N; t += K::NT) sE[t] = E[t];
@@ -520,28 +522,33 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
   }
   fc3::cp_wait_all();
   __syncthreads();
-  K::lines(tid, cell, y, Gs, N * N, FS, sE, Z);
+  if (gridDim.z == 1) K::lines(tid, cell, y, Gs, N * N, FS, sE, Z);
+  else K::lines(tid, cell, y, Gs, N * N, FS, sE, Z, blockIdx.z, blockIdx.z + 1);     // few cells: one round per CTA
 }
 template <int L>
-__global__ void __launch_bounds__(fc3::F2<L>::NT, 1) k_fc3_f2(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
+__global__ void __launch_bounds__(fc3::F2<L>::NT, 1) k_fc3_f2(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C,
+                                                              long long split_stride)
 {
   typedef fc3::F2<L> K;
   extern __shared__ double2 smf[];
   double2 *IN = smf, *Y = IN + K::IN_C2;
   double *sE = reinterpret_cast<double *>(Y + K::Y_C2);
   const int kz = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
-  K::issue_loads(tid, cell, kz, 0, Z, IN);
+  int p_begin, p_end;
+  K::psplit(blockIdx.z, gridDim.z, p_begin, p_end);       // gridDim.z = 3: the seven products split over three CTAs
+  C += blockIdx.z * split_stride;
+  K::issue_loads(tid, cell, kz, p_begin, Z, IN);
   for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
   double2 acc[L];
   #pragma unroll
   for (int q = 0; q < L; q++) acc[q] = make_double2(0., 0.);
   #pragma unroll 1
-  for (int p = 0; p < 7; p++) {
+  for (int p = p_begin; p < p_end; p++) {
     fc3::cp_wait_all();
     __syncthreads();                       // planes of p landed; every x-stage read of Y from p-1 is done
     K::ystage(tid, p, IN, sE, Y);
     __syncthreads();                       // Y complete; IN consumed
-    if (p < 6) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
+    if (p + 1 < p_end) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
     K::xstage(tid, Y, acc);
   }
   __syncthreads();
@@ -587,8 +594,9 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // PARK: also park the u transform of the x stage in TMEM while the v transform runs (128 instead of 64 columns per thread)
 #define LP_F2TM_PER (PARK ? 128 : 64)
 #define LP_F2TM_COLS (2 * LP_F2TM_PER)   // 6 warps: lane quarters 0..3 twice -> two column groups
-template <bool PARK>
-__global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
+template <bool PARK, int NSPLIT>
+__global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C,
+                                                        long long split_stride)
 {
   constexpr int L = 16;
   typedef fc3::F2<L> K;
@@ -602,7 +610,10 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(dst), "r"((unsigned)LP_F2TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  K::issue_loads(tid, cell, kz, 0, Z, IN);
+  int p_begin, p_end;
+  K::psplit(blockIdx.z, NSPLIT, p_begin, p_end);       // gridDim.z = 3: the seven products split over three CTAs
+  C += blockIdx.z * split_stride;
+  K::issue_loads(tid, cell, kz, p_begin, Z, IN);
   for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -614,12 +625,12 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   const bool xok = K::xtask(tid, r, ky);
   if (ky > K::M - 1) ky = K::M - 1;
   #pragma unroll 1
-  for (int p = 0; p < 7; p++) {
+  for (int p = p_begin; p < p_end; p++) {
     fc3::cp_wait_all();
     __syncthreads();                       // planes of p landed; every x-stage read of Y from p-1 is done
     K::ystage(tid, p, IN, sE, Y);
     __syncthreads();                       // Y complete; IN consumed
-    if (p < 6) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
+    if (p + 1 < p_end) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
     {
       double2 a0[L], a1[L], uh[L], vh[L];
       #pragma unroll
@@ -636,7 +647,7 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
       #pragma unroll
       for (int c4 = 0; c4 < L / 4; c4++) {
         double2 a[4];
-        if (p > 0) tmem_ld4c(tacc + 16 * c4, a);
+        if (p > p_begin) tmem_ld4c(tacc + 16 * c4, a);
         else { a[0] = a[1] = a[2] = a[3] = make_double2(0., 0.); }
         double2 u4[4];
         if constexpr (PARK) tmem_ld4c(tacc + 64 + 16 * c4, u4);
@@ -677,15 +688,15 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
 }
 // part (nullable): per (cell, xo) partial dot products of the conservation rows with the stored spectrum,
 // [cell][xo][5]; folded in a fixed order by the kernels that apply the correction (collision.cu)
-template <int L>
+template <int L, int NSPLIT>
 __global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__restrict__ C, double2 *__restrict__ q,
-                                                           const double *__restrict__ C5, double *__restrict__ part)
+                                                           const double *__restrict__ C5, double *__restrict__ part, long long split_stride)
 {
   typedef fc3::F3<L> K;
   __shared__ double2 T3[K::SMEM_C2];
   __shared__ double red[5][4];
   const int xo = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
-  K::zinverse(tid, cell, xo, C, T3);
+  K::template zinverse<NSPLIT>(tid, cell, xo, C, T3, split_stride);
   __syncthreads();
   double s[5] = {0., 0., 0., 0., 0.};
   K::store(tid, cell, xo, T3, q, part ? C5 : nullptr, s);
@@ -713,26 +724,35 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
     LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     LP_CUDA(cudaFuncSetAttribute(k_fc3_f2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     if (L == 16) {
-      LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     }
     c->fc3_attr = true;
   }
   const double *E = c->d_Etab + LP_ETAB_PAD;
   const double2 *post = reinterpret_cast<const double2 *>(c->d_post_fwd);
-  if (fused_i) k_fc3_f1<L, true><<<dim3(N, nb), fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
-  else k_fc3_f1<L, false><<<dim3(N, nb), fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
+  const dim3 g1(N, nb, nb * N * 2 <= 148 ? 5 : 1);
+  if (fused_i) k_fc3_f1<L, true><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
+  else k_fc3_f1<L, false><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
   LP_LAUNCHED(c);
   static const bool no_tmem = getenv("LPGPU_FC_NO_TMEM") != nullptr;   // developer knob: accumulators in registers, 1 CTA per SM
   const bool prof2 = c->prof_on == 2 && c->prof_used + 2 <= c->prof_ev.size();
   if (prof2) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   static const bool park_uh = getenv("LPGPU_F2_NO_PARK_UH") == nullptr;   // developer knob: keep the u transform in registers (6 % slower)
-  if (L == 16 && !no_tmem && park_uh) k_fc3_f2_tmem<true><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
-  else if (L == 16 && !no_tmem) k_fc3_f2_tmem<false><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
-  else k_fc3_f2<L><<<dim3(M, nb), K2::NT, smem2, c->stream>>>(Z, E, C);
+  // few cells in flight (the homogeneous single cell: M CTAs on 148 SMs): split the seven products over three CTAs per
+  // (cell, kz); each writes its partial C and F3 sums them (the inverse transforms are linear)
+  const int nsplit = (nb * M * 2 <= 148) ? 3 : 1;
+  const long long split_stride = (long long)nb * M * N * N;
+  const dim3 g2(M, nb, nsplit);
+  if (L == 16 && !no_tmem && nsplit == 3) k_fc3_f2_tmem<true, 3><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
+  else if (L == 16 && !no_tmem && park_uh) k_fc3_f2_tmem<true, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
+  else if (L == 16 && !no_tmem) k_fc3_f2_tmem<false, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
+  else k_fc3_f2<L><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   LP_LAUNCHED(c);
   if (prof2) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
-  k_fc3_f3<L><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo, c->d_C5, part);
+  if (nsplit == 3) k_fc3_f3<L, 3><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo, c->d_C5, part, split_stride);
+  else k_fc3_f3<L, 1><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo, c->d_C5, part, split_stride);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -780,7 +800,7 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     if (chunk > c->cap_cells) chunk = c->cap_cells;
     c->fc_chunk = (int)chunk;
     LP_CUDA(cudaMalloc((void **)&c->d_fc1, per_cell * chunk));
-    LP_CUDA(cudaMalloc((void **)&c->d_fc2, (size_t)N * M * M * sizeof(double2) * chunk));
+    LP_CUDA(cudaMalloc((void **)&c->d_fc2, (size_t)N * M * M * sizeof(double2) * 2 * chunk));   // room for the three partial C arrays of a split launch (3 N^2 M = 2 N M^2)
     std::vector<double> tw(2 * M);   // exp(-2 pi i t / M), t < M
     for (int t = 0; t < M; t++) { const long double a = 2.0L * M_PIl * t / M; tw[2 * t] = (double)cosl(a); tw[2 * t + 1] = (double)(-sinl(a)); }
     LP_CUDA(cudaMalloc((void **)&c->d_fctw, 2 * M * sizeof(double)));

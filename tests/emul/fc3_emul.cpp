@@ -8,7 +8,7 @@
 #include "../../landau-poisson-solver_b200/csrc/fc3.cuh"
 
 template <int L>
-static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q)
+static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit)
 {
   using namespace fc3;
   constexpr int N = 2 * L, M = 3 * L;
@@ -17,7 +17,8 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
     for (int x = 0; x < N; x++)
       for (int y = 0; y < N; y++)
         for (int z = 0; z < N; z++) Gt[(((size_t)a * N + y) * N + z) * N + x] = G7[(size_t)7 * (z + N * (y + N * x)) + a];
-  std::vector<double2> Z((size_t)B * 10 * M * N * N), C((size_t)B * M * N * N);
+  const long long split_stride = (long long)B * M * N * N;
+  std::vector<double2> Z((size_t)B * 10 * M * N * N), C((size_t)nsplit * split_stride);
   {
     typedef F1<L> K;
     std::vector<double2> FS(K::SMEM_C2);
@@ -36,42 +37,53 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
     struct Acc { double2 a[L]; };
     std::vector<Acc> acc(K::NT);
     for (int cell = 0; cell < B; cell++)
-      for (int kz = 0; kz < M; kz++) {
-        std::memset(acc.data(), 0, sizeof(Acc) * acc.size());
-        for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, 0, Z.data(), IN.data());
-        for (int p = 0; p < 7; p++) {
-          for (int t = 0; t < K::NT; t++) K::ystage(t, p, IN.data(), sE.data(), Y.data());
-          if (p < 6) for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, p + 1, Z.data(), IN.data());
-          for (int t = 0; t < K::NT; t++) K::xstage(t, Y.data(), acc[t].a);
+      for (int kz = 0; kz < M; kz++)
+        for (int sp = 0; sp < nsplit; sp++) {
+          int p0, p1;
+          K::psplit(sp, nsplit, p0, p1);
+          std::memset(acc.data(), 0, sizeof(Acc) * acc.size());
+          for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, p0, Z.data(), IN.data());
+          for (int p = p0; p < p1; p++) {
+            for (int t = 0; t < K::NT; t++) K::ystage(t, p, IN.data(), sE.data(), Y.data());
+            if (p + 1 < p1) for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, p + 1, Z.data(), IN.data());
+            for (int t = 0; t < K::NT; t++) K::xstage(t, Y.data(), acc[t].a);
+          }
+          for (int t = 0; t < K::NT; t++) K::xinverse(t, acc[t].a, Y.data());
+          for (int t = 0; t < K::NT; t++) K::yinverse(t, Y.data(), IN.data());
+          for (int t = 0; t < K::NT; t++) K::store(t, cell, kz, IN.data(), C.data() + sp * split_stride);
         }
-        for (int t = 0; t < K::NT; t++) K::xinverse(t, acc[t].a, Y.data());
-        for (int t = 0; t < K::NT; t++) K::yinverse(t, Y.data(), IN.data());
-        for (int t = 0; t < K::NT; t++) K::store(t, cell, kz, IN.data(), C.data());
-      }
   }
   {
     typedef F3<L> K;
     std::vector<double2> T3(K::SMEM_C2);
     for (int cell = 0; cell < B; cell++)
       for (int xo = 0; xo < N; xo++) {
-        for (int t = 0; t < K::NT; t++) K::zinverse(t, cell, xo, C.data(), T3.data());
+        for (int t = 0; t < K::NT; t++) {
+          if (nsplit == 3) K::template zinverse<3>(t, cell, xo, C.data(), T3.data(), split_stride);
+          else K::template zinverse<1>(t, cell, xo, C.data(), T3.data(), split_stride);
+        }
         double dummy[5] = {0., 0., 0., 0., 0.};
         for (int t = 0; t < K::NT; t++) K::store(t, cell, xo, T3.data(), q, nullptr, dummy);
       }
   }
 }
 
-extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+extern "C" int fc3_emulate_split(int N, int B, const double *fhat, const double *G7, const double *E, double *q, int nsplit)
 {
   const double2 *f = reinterpret_cast<const double2 *>(fhat);
   double2 *o = reinterpret_cast<double2 *>(q);
   switch (N) {
-    case 8: emulate<4>(B, f, G7, E, o); return 0;
-    case 16: emulate<8>(B, f, G7, E, o); return 0;
-    case 24: emulate<12>(B, f, G7, E, o); return 0;
-    case 32: emulate<16>(B, f, G7, E, o); return 0;
+    case 8: emulate<4>(B, f, G7, E, o, nsplit); return 0;
+    case 16: emulate<8>(B, f, G7, E, o, nsplit); return 0;
+    case 24: emulate<12>(B, f, G7, E, o, nsplit); return 0;
+    case 32: emulate<16>(B, f, G7, E, o, nsplit); return 0;
   }
   return 1;
+}
+
+extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+{
+  return fc3_emulate_split(N, B, fhat, G7, E, q, 1);
 }
 
 extern "C" int fc3_direct(int N, int B, const double *fhat, const double *G7, const double *E, double *q)

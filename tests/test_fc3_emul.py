@@ -37,6 +37,19 @@ def test_pipeline_matches_direct_sum(emul, N, B):
     assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
 
 
+def test_product_split_over_three_ctas(emul):
+    """F2 may split its seven products over three CTAs per (cell, kz) when few cells are in flight; F3 sums the parts."""
+    N, B = 16, 1
+    rng = np.random.default_rng(3)
+    fh = rng.standard_normal((B, N ** 3, 2))
+    G = rng.standard_normal((N ** 3, 7))
+    E = (np.arange(N) - N / 2) * 0.37
+    got, want = np.zeros_like(fh), np.zeros_like(fh)
+    assert emul.fc3_emulate_split(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), got.ctypes.data_as(P), 3) == 0
+    assert emul.fc3_direct(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), want.ctypes.data_as(P)) == 0
+    assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
+
+
 def test_unsupported_size_is_refused(emul):
     z = np.zeros(8)
     assert emul.fc3_emulate(10, 1, z.ctypes.data_as(P), z.ctypes.data_as(P), z.ctypes.data_as(P), z.ctypes.data_as(P)) == 1
