@@ -98,8 +98,8 @@ def cpu_eval_rate(reps, warm):
     if ora is None:
         ora = PortOracle(**cfg)
     t_init = time.time() - t_init
-    from lpsolver_b200 import solver
-    f = (PortOracle(**cfg).setInit_spectral(solver.set_init_4h_homo(NV, PHYS["Lv"])))[0]
+    po = PortOracle(**cfg)                            # input data from the oracle side only: nothing of the product on this path
+    f = po.setInit_spectral(po.SetInit_4H_Homo())[0]
     for _ in range(warm):
         ora.conserveMoments(ora.ComputeQ(f))
     t = time.time()
@@ -110,6 +110,14 @@ def cpu_eval_rate(reps, warm):
                 sample="%d x (ComputeQ + conserveMoments) on 1 cell, N=%d, OpenMP on %d threads; init %.0f s excluded" % (reps, NSPEC, ora.num_threads, t_init)), dt
 
 
+def workload_config(world):
+    """config of the JSON line, shared by both arms"""
+    Nx = CELLS_PER_GPU * world
+    return {"workload": "two-stream Landau-Poisson timestep (SSP-RK3 DG advection + RK4 spectral Landau collision), %d x-cells per GPU, Nv=%d, N=%d "
+                        "(BASELINE config Nx=256,Nv=32^3 on 8 GPUs, per-GPU shard)" % (CELLS_PER_GPU, NV, NSPEC),
+            "Nx": Nx, "Nv": NV, "N": NSPEC, "evals_per_step": 4 * Nx, "parallelism": "x-cells sharded over %d GPU(s)" % world}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the metric's unit, timed on the host."""
     if rank != 0:
@@ -118,8 +126,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "two-stream Landau-Poisson step, %d x-cells per GPU, Nv=%d, N=%d" % (CELLS_PER_GPU, NV, NSPEC),
-                       "sample": "each step = one ComputeQ + conserveMoments on one cell (the metric's unit)"},
+            "config": dict(workload_config(args.gpus), sample="each step = one ComputeQ + conserveMoments on one cell (the metric's unit) "
+                                                              "by the reference's own CPU code on this box's host cores"),
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=OUT, flush=True)
 
@@ -287,9 +295,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "two-stream Landau-Poisson timestep (SSP-RK3 DG advection + RK4 spectral Landau collision), %d x-cells per GPU, Nv=%d, N=%d (BASELINE config Nx=256,Nv=32^3 on 8 GPUs, per-GPU shard)" % (CELLS_PER_GPU, NV, NSPEC),
-                           "Nx": Nx, "Nv": NV, "N": NSPEC, "evals_per_step": 4 * Nx, "parallelism": "x-cells sharded over %d GPU(s)" % world,
-                           "l2": "per-GPU working set %.0f MB > 126 MB L2; no flush between steps" % ws_mb},
+                "config": dict(workload_config(world), l2="per-GPU working set %.0f MB > 126 MB L2; no flush between steps" % ws_mb),
                 "timesteps_per_s": args.steps / t_dev, "roofline": roof, "roofline_direct": roof_direct, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks}
 
