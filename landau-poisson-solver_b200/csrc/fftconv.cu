@@ -1,21 +1,15 @@
 // ComputeQ as seven zero-padded linear convolutions (computeq_variant 0/2) -- the O(N^3 log N) form of the
-// same sum (identity checked against the reference's table to 1.5e-16):
+// same sum (identity checked against the reference's table to 1.5e-16); the algebra is in fc3.cuh.
 //
-//   Wt(xi,omega) = G0(omega) - sum_{p=1..6} G_p(omega) mono_p(E(beta)),   beta = xi + N/2 - omega,
-//   mono = {e1^2, e2^2, e3^2, e1 e2, e1 e3, e2 e3},  e_a = E(beta_a) = eta[beta_a] - eta[N/2]
-//   => Qhat[xi] = sum_p ( u_p (*) v_p )[xi + N/2],   u_p = G_p fhat,  v_p = h_p(E) fhat   (linear convolution)
-//
-// computed with cyclic transforms of size M = 3N/2 per dimension.  The linear convolution lives on
-// [0, 2N-2]; only s = xi + N/2 in [N/2, 3N/2) is wanted, and with period M the indices that alias onto
-// that window would be s + M >= 2N (outside the support) -- so 1.5 N points suffice instead of 2N
-// (2.4x fewer points in 3-D).  M = 12, 24, 36, 48 for N = 8, 16, 24, 32: radix-2 and radix-3 stages.
-//   F1  per (cell, x, p): build the padded y-z plane of u_p / v_p, transform along z (N non-zero rows) and y
-//   F2  per (cell, ky, 8 kz): transform the 14 x-lines, sum_p u_p v_p, inverse transform along x, keep N outputs
-//   F3  per (cell, x'): inverse transform along y and z, scale by M^-3, extract the N x N window
-// Forward transforms are decimation-in-frequency (natural in, digit-reversed out), inverse transforms are
-// the conjugate-transposed stages in reverse order (digit-reversed in, natural out), so no permutation pass
-// exists anywhere: products are formed position-wise.  Butterflies run on shared-memory lines with
-// correctly rounded twiddles from the host.  Sizes whose M has another prime factor use the tiled direct kernel.
+// Two implementations live here:
+//  * the register-resident pipeline of fc3.cuh (N = 8, 16, 24, 32; the default path): kernels k_fc3_f1 / k_fc3_f2 /
+//    k_fc3_f2_tmem / k_fc3_f3, fused with fft3D's last pass, the conservation dot products, and -- for N = 32 -- with
+//    the product accumulators and the waiting u transform parked in tensor memory;
+//  * a generic shared-memory version for any other even N whose M = 3N/2 is 2^a 3^b (k_fc_fwd_yz / k_fc_x /
+//    k_fc_inv_yz): decimation-in-frequency stages on shared-memory lines (natural in, digit-reversed out; the
+//    inverse runs the conjugate-transposed stages in reverse order, so products are formed position-wise and no
+//    permutation pass exists), 14 arrays of N M^2 through HBM between the y-z and the x kernel.
+// Sizes whose M has another prime factor use the tiled direct kernel (computeq.cu).
 #include "lpgpu_internal.h"
 #include "fc3.cuh"
 
@@ -235,229 +229,6 @@ __global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ C
     const double2 v = plane[(t / N + H) * P + (t % N) + H];
     o[t] = make_double2(v.x * sc, v.y * sc);
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Register/shuffle lines for M = 3 * LPL, LPL = 4, 8, 16 (N = 8, 16, 32): a group of LPL lanes owns one line;
-// lane l holds the elements l, l+LPL, l+2 LPL.  The radix-3 stage is in registers, the log2(LPL) radix-2 stages
-// exchange partners with __shfl_xor -- no shared-memory traffic inside a transform, no integer divisions.
-// The element layout after the forward transform (value of sub-block k, position l at index k*LPL + l) is the
-// same digit-reversed layout the generic stages produce, so forward and inverse pair up position-wise.
-template <int LPL>
-struct LaneTw {
-  static constexpr int NS = (LPL == 16) ? 4 : (LPL == 8) ? 3 : 2;
-  double2 w3a, w3b;      // tw[l], tw[2l]: radix-3 stage twiddles
-  double2 ws[NS];        // stage s (span h = LPL >> (s+1)): twiddle of the upper partner, 1 for the lower
-  double sg[NS];         // -1 upper, +1 lower
-  __device__ __forceinline__ void init(int l, const double2 *tw)
-  {
-    constexpr int M = 3 * LPL;
-    w3a = tw[l]; w3b = tw[2 * l];
-    #pragma unroll
-    for (int s = 0; s < NS; s++) {
-      const int h = LPL >> (s + 1);
-      const bool up = (l & h) != 0;
-      ws[s] = up ? tw[(l & (h - 1)) * (M / (2 * h))] : make_double2(1., 0.);
-      sg[s] = up ? -1. : 1.;
-    }
-  }
-};
-__device__ __forceinline__ double2 shfl_xor_c(double2 v, int h)
-{ return make_double2(__shfl_xor_sync(0xffffffffu, v.x, h), __shfl_xor_sync(0xffffffffu, v.y, h)); }
-
-template <int LPL>
-__device__ __forceinline__ void line_fwd_regs(double2 &a0, double2 &a1, double2 &a2, const LaneTw<LPL> &T)
-{
-  const double2 t1 = cxadd(a1, a2), t2 = make_double2(a0.x - 0.5 * t1.x, a0.y - 0.5 * t1.y);
-  const double2 d = cxsub(a1, a2), t3 = make_double2(LP_SQRT3_2 * d.x, LP_SQRT3_2 * d.y);
-  double2 y[3];
-  y[0] = cxadd(a0, t1);
-  y[1] = cxmul(make_double2(t2.x + t3.y, t2.y - t3.x), T.w3a);
-  y[2] = cxmul(make_double2(t2.x - t3.y, t2.y + t3.x), T.w3b);
-  #pragma unroll
-  for (int s = 0; s < LaneTw<LPL>::NS; s++) {
-    const int h = LPL >> (s + 1);
-    #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const double2 o = shfl_xor_c(y[k], h);
-      y[k] = cxmul(make_double2(fma(T.sg[s], y[k].x, o.x), fma(T.sg[s], y[k].y, o.y)), T.ws[s]);   // lower: a+b, upper: (a-b) w
-    }
-  }
-  a0 = y[0]; a1 = y[1]; a2 = y[2];
-}
-template <int LPL>
-__device__ __forceinline__ void line_inv_regs(double2 &a0, double2 &a1, double2 &a2, const LaneTw<LPL> &T)
-{
-  double2 y[3] = {a0, a1, a2};
-  #pragma unroll
-  for (int s = LaneTw<LPL>::NS - 1; s >= 0; s--) {
-    const int h = LPL >> (s + 1);
-    #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const double2 m = cxmulc(y[k], T.ws[s]);                  // upper: y conj(w), lower: y
-      const double2 o = shfl_xor_c(m, h);
-      y[k] = make_double2(fma(T.sg[s], m.x, o.x), fma(T.sg[s], m.y, o.y));   // lower: y0 + t, upper: y0 - t
-    }
-  }
-  const double2 y1 = cxmulc(y[1], T.w3a), y2 = cxmulc(y[2], T.w3b);
-  const double2 t1 = cxadd(y1, y2), t2 = make_double2(y[0].x - 0.5 * t1.x, y[0].y - 0.5 * t1.y);
-  const double2 d = cxsub(y1, y2), t3 = make_double2(LP_SQRT3_2 * d.x, LP_SQRT3_2 * d.y);
-  a0 = cxadd(y[0], t1);
-  a1 = make_double2(t2.x - t3.y, t2.y + t3.x);
-  a2 = make_double2(t2.x + t3.y, t2.y - t3.x);
-}
-
-// F1 (register lines): plane of u_p / v_{p-7}; rows y < N along z, then all M columns along y.  The padded
-// halves are never materialised: the third element of every line is zero on input.
-template <int LPL>
-__global__ void __launch_bounds__(256) k_fr_fwd_yz(const double2 *__restrict__ fhat, double2 *__restrict__ Fxy, const double *__restrict__ G,
-                                                   const double *__restrict__ Etab, const double2 *__restrict__ twg)
-{
-  constexpr int N = 2 * LPL, M = 3 * LPL, P = M + 1, SLOTS = 8 * (32 / LPL);
-  __shared__ double2 plane[M * P];
-  __shared__ double2 tw[M];
-  const int x = blockIdx.x, p = blockIdx.y; const long long cell = blockIdx.z;
-  const int tid = threadIdx.x, l = tid % LPL, slot = tid / LPL;
-  for (int t = tid; t < M; t += 256) tw[t] = twg[t];
-  const double *E = Etab + LP_ETAB_PAD;
-  const double ex = E[x];
-  for (int t = tid; t < N * N; t += 256) {
-    const int y = t / N, z = t % N;
-    const long long w = ((long long)x * N + y) * N + z;
-    const double2 f = fhat[cell * N * N * N + w];
-    double m;
-    if (p < 7) m = G[7 * w + p];
-    else {
-      const double ey = E[y], ez = E[z];
-      switch (p - 7) {
-        case 0: m = 1.; break;
-        case 1: m = -ex * ex; break;
-        case 2: m = -ey * ey; break;
-        case 3: m = -ez * ez; break;
-        case 4: m = -ex * ey; break;
-        case 5: m = -ex * ez; break;
-        default: m = -ey * ez; break;
-      }
-    }
-    plane[y * P + z] = make_double2(m * f.x, m * f.y);
-  }
-  __syncthreads();
-  LaneTw<LPL> T; T.init(l, tw);
-  // every lane runs every round (the shuffles are warp-wide); rounds past the end work on zeros and store nothing
-  for (int base = 0; base < N; base += SLOTS) {
-    const int y = base + slot; const bool ok = y < N;
-    double2 a0 = ok ? plane[y * P + l] : make_double2(0., 0.), a1 = ok ? plane[y * P + l + LPL] : make_double2(0., 0.), a2 = make_double2(0., 0.);
-    line_fwd_regs<LPL>(a0, a1, a2, T);
-    if (ok) { plane[y * P + l] = a0; plane[y * P + l + LPL] = a1; plane[y * P + l + 2 * LPL] = a2; }
-  }
-  __syncthreads();
-  for (int base = 0; base < M; base += SLOTS) {
-    const int cidx = base + slot; const bool ok = cidx < M;
-    double2 a0 = ok ? plane[l * P + cidx] : make_double2(0., 0.), a1 = ok ? plane[(l + LPL) * P + cidx] : make_double2(0., 0.), a2 = make_double2(0., 0.);
-    line_fwd_regs<LPL>(a0, a1, a2, T);
-    if (ok) { plane[l * P + cidx] = a0; plane[(l + LPL) * P + cidx] = a1; plane[(l + 2 * LPL) * P + cidx] = a2; }
-  }
-  __syncthreads();
-  double2 *o = Fxy + ((cell * 14 + p) * N + x) * (long long)(M * M);
-  for (int t = tid; t < M * M; t += 256) o[t] = plane[(t / M) * P + (t % M)];
-}
-
-// F2 (register lines): a warp owns LP = 16/LPL lines; for each, the lower lane group transforms u_p, the upper
-// group v_p; products are accumulated over p on the lower group, which then runs the inverse transform.
-template <int LPL>
-__global__ void __launch_bounds__(256) k_fr_x(const double2 *__restrict__ Fxy, double2 *__restrict__ Cx, const double2 *__restrict__ twg)
-{
-  constexpr int N = 2 * LPL, M = 3 * LPL, H = N / 2, NL = 8 * (16 / LPL), P = N + 1;   // NL lines (consecutive kz) per block
-  __shared__ double2 U[NL * P], V[NL * P];
-  __shared__ double2 tw[M];
-  const int kz0 = blockIdx.x * NL, ky = blockIdx.y; const long long cell = blockIdx.z;
-  const int tid = threadIdx.x, l = tid % LPL, grp = tid / LPL;       // grp: even = u of line grp/2, odd = v of the same line
-  const int line = grp >> 1; const bool isv = grp & 1;
-  const int nkz = (M - kz0 < NL) ? M - kz0 : NL;
-  for (int t = tid; t < M; t += 256) tw[t] = twg[t];
-  __syncthreads();
-  LaneTw<LPL> T; T.init(l, tw);
-  double2 acc0 = make_double2(0., 0.), acc1 = acc0, acc2 = acc0;
-  const long long MM = (long long)M * M;
-  for (int p = 0; p < 7; p++) {
-    __syncthreads();
-    const double2 *su = Fxy + ((cell * 14 + p) * N) * MM + (long long)ky * M + kz0;
-    const double2 *sv = Fxy + ((cell * 14 + p + 7) * N) * MM + (long long)ky * M + kz0;
-    for (int t = tid; t < NL * N; t += 256) {
-      const int x = t / NL, kzi = t % NL;
-      const bool live = kzi < nkz;
-      U[kzi * P + x] = live ? su[x * MM + kzi] : make_double2(0., 0.);
-      V[kzi * P + x] = live ? sv[x * MM + kzi] : make_double2(0., 0.);
-    }
-    __syncthreads();
-    const double2 *src = (isv ? V : U) + line * P;
-    double2 a0 = src[l], a1 = src[l + LPL], a2 = make_double2(0., 0.);
-    line_fwd_regs<LPL>(a0, a1, a2, T);
-    // bring v (upper group) next to u (lower group) and accumulate the products on the lower group
-    const double2 b0 = make_double2(__shfl_down_sync(0xffffffffu, a0.x, LPL), __shfl_down_sync(0xffffffffu, a0.y, LPL));
-    const double2 b1 = make_double2(__shfl_down_sync(0xffffffffu, a1.x, LPL), __shfl_down_sync(0xffffffffu, a1.y, LPL));
-    const double2 b2 = make_double2(__shfl_down_sync(0xffffffffu, a2.x, LPL), __shfl_down_sync(0xffffffffu, a2.y, LPL));
-    const double2 p0 = cxmul(a0, b0), p1 = cxmul(a1, b1), p2 = cxmul(a2, b2);
-    acc0 = cxadd(acc0, p0); acc1 = cxadd(acc1, p1); acc2 = cxadd(acc2, p2);
-  }
-  line_inv_regs<LPL>(acc0, acc1, acc2, T);          // natural order: x = l, l+LPL, l+2LPL; wanted x in [H, H+N) = [LPL, 3 LPL)
-  __syncthreads();
-  if (!isv) { U[line * P + l] = acc1; U[line * P + l + LPL] = acc2; }
-  __syncthreads();
-  double2 *o = Cx + (cell * N) * MM + (long long)ky * M + kz0;
-  for (int t = tid; t < NL * N; t += 256) {
-    const int xo = t / NL, kzi = t % NL;
-    if (kzi < nkz) o[xo * MM + kzi] = U[kzi * P + xo];
-  }
-}
-
-// F3 (register lines): inverse along y (all columns, rows [H, H+N) kept), then along z for those rows; scale; write Qhat
-template <int LPL>
-__global__ void __launch_bounds__(256) k_fr_inv_yz(const double2 *__restrict__ Cx, double2 *__restrict__ q, const double2 *__restrict__ twg)
-{
-  constexpr int N = 2 * LPL, M = 3 * LPL, P = M + 1, SLOTS = 8 * (32 / LPL);
-  __shared__ double2 plane[M * P];
-  __shared__ double2 tw[M];
-  const int xo = blockIdx.x; const long long cell = blockIdx.y;
-  const int tid = threadIdx.x, l = tid % LPL, slot = tid / LPL;
-  for (int t = tid; t < M; t += 256) tw[t] = twg[t];
-  const double2 *s = Cx + (cell * N + xo) * (long long)(M * M);
-  for (int t = tid; t < M * M; t += 256) plane[(t / M) * P + (t % M)] = s[t];
-  __syncthreads();
-  LaneTw<LPL> T; T.init(l, tw);
-  const double2 zero = make_double2(0., 0.);
-  for (int base = 0; base < M; base += SLOTS) {
-    const int cidx = base + slot; const bool ok = cidx < M;
-    double2 a0 = ok ? plane[l * P + cidx] : zero, a1 = ok ? plane[(l + LPL) * P + cidx] : zero, a2 = ok ? plane[(l + 2 * LPL) * P + cidx] : zero;
-    line_inv_regs<LPL>(a0, a1, a2, T);
-    if (ok) { plane[(l + LPL) * P + cidx] = a1; plane[(l + 2 * LPL) * P + cidx] = a2; }   // rows y' = l+LPL, l+2LPL (the kept window)
-  }
-  __syncthreads();
-  const double sc = 1.0 / ((double)M * M * M);
-  double2 *o = q + (cell * N + xo) * (long long)(N * N);
-  for (int base = 0; base < N; base += SLOTS) {
-    const int yy = base + slot; const bool ok = yy < N;
-    const int y = yy + LPL;                                                     // H = N/2 = LPL
-    double2 a0 = ok ? plane[y * P + l] : zero, a1 = ok ? plane[y * P + l + LPL] : zero, a2 = ok ? plane[y * P + l + 2 * LPL] : zero;
-    line_inv_regs<LPL>(a0, a1, a2, T);
-    if (ok) {
-      o[yy * N + l] = make_double2(a1.x * sc, a1.y * sc);
-      o[yy * N + l + LPL] = make_double2(a2.x * sc, a2.y * sc);
-    }
-  }
-}
-
-template <int LPL>
-int launch_regs(lpgpu_ctx *c, const double2 *fh, double2 *F1, double2 *F2, double2 *qo, const double2 *tw, int nb)
-{
-  constexpr int N = 2 * LPL, M = 3 * LPL, NL = 8 * (16 / LPL);
-  k_fr_fwd_yz<LPL><<<dim3(N, 14, nb), 256, 0, c->stream>>>(fh, F1, c->d_G, c->d_Etab, tw);
-  LP_LAUNCHED(c);
-  k_fr_x<LPL><<<dim3((M + NL - 1) / NL, M, nb), 256, 0, c->stream>>>(F1, F2, tw);
-  LP_LAUNCHED(c);
-  k_fr_inv_yz<LPL><<<dim3(N, nb), 256, 0, c->stream>>>(F2, qo, tw);
-  LP_LAUNCHED(c);
-  return LPGPU_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -772,7 +543,7 @@ bool make_plan(int M, FcPlan &pl)
 // returns -1 when M = 3N/2 is not of the form 2^a 3^b (caller uses the tiled direct kernel)
 static bool fc3_knobs_off()
 {
-  static const bool off = getenv("LPGPU_FFT_GENERIC") != nullptr || getenv("LPGPU_FC_OLD") != nullptr;
+  static const bool off = getenv("LPGPU_FFT_GENERIC") != nullptr;
   return off;
 }
 bool lp_fc3_available(const lpgpu_ctx *c)
@@ -790,14 +561,18 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
   const size_t plane_bytes = ((size_t)M * (M + 1) + M) * sizeof(double2);
   const size_t line_bytes = ((size_t)16 * (M + 1) + M) * sizeof(double2);
   if (!c->d_fc1) {
-    // chunk of cells whose 14 transformed arrays fit a fixed budget (12.4 MB per cell at N = 32)
-    const size_t per_cell = (size_t)14 * N * M * M * sizeof(double2);
+    // chunk of cells whose transformed arrays fit a fixed budget: 10 arrays of N^2 M for the register-resident pipeline
+    // (7.9 MB per cell at N = 32), 14 of N M^2 for the shared-memory fallback
+    const bool fc3_size = (N == 32 || N == 24 || N == 16 || N == 8) && !fc3_knobs_off();
+    const size_t per_cell = fc3_size ? (size_t)10 * N * N * M * sizeof(double2) : (size_t)14 * N * M * M * sizeof(double2);
     // 1 GB of transformed planes per chunk.  Measured: chunks small enough for F2 to read F1's output out of the
     // 126 MB L2 (96 MB) are 15 % slower than one big launch -- the kernels are not HBM-limited, launch tails are.
     const size_t budget_mb = getenv("LPGPU_FC_CHUNK_MB") ? (size_t)atoi(getenv("LPGPU_FC_CHUNK_MB")) : 1024;
     size_t chunk = (budget_mb << 20) / per_cell;
     if (chunk < 1) chunk = 1;
     if (chunk > c->cap_cells) chunk = c->cap_cells;
+    // equal chunks: a 2-cell tail after a 62-cell chunk would run nearly empty grids
+    { const size_t nchunks = (c->cap_cells + chunk - 1) / chunk; chunk = (c->cap_cells + nchunks - 1) / nchunks; }
     c->fc_chunk = (int)chunk;
     LP_CUDA(cudaMalloc((void **)&c->d_fc1, per_cell * chunk));
     LP_CUDA(cudaMalloc((void **)&c->d_fc2, (size_t)N * M * M * sizeof(double2) * 2 * chunk));   // room for the three partial C arrays of a split launch (3 N^2 M = 2 N M^2)
@@ -827,16 +602,10 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     double2 *qo = reinterpret_cast<double2 *>(q) + (size_t)b0 * c->N3;
     double2 *F1 = reinterpret_cast<double2 *>(c->d_fc1), *F2 = reinterpret_cast<double2 *>(c->d_fc2);
     static const bool generic_only = getenv("LPGPU_FFT_GENERIC") != nullptr;   // developer knob: force the shared-memory stages
-    static const bool old_regs = getenv("LPGPU_FC_OLD") != nullptr;            // developer knob: the shuffle-line kernels
-    if (!generic_only && !old_regs && (N == 32 || N == 24 || N == 16 || N == 8)) {
+    if (!generic_only && (N == 32 || N == 24 || N == 16 || N == 8)) {
       double *pp = part ? part + (size_t)b0 * N * 5 : nullptr;
       int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb, fused_i, pp) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb, fused_i, pp)
              : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb, fused_i, pp) : launch_fc3<4>(c, fh, F1, F2, qo, nb, fused_i, pp);
-      if (rc != LPGPU_OK) return rc;
-      continue;
-    }
-    if (!generic_only && (N == 32 || N == 16 || N == 8)) {
-      int rc = N == 32 ? launch_regs<16>(c, fh, F1, F2, qo, tw, nb) : N == 16 ? launch_regs<8>(c, fh, F1, F2, qo, tw, nb) : launch_regs<4>(c, fh, F1, F2, qo, tw, nb);
       if (rc != LPGPU_OK) return rc;
       continue;
     }
