@@ -68,6 +68,10 @@ long long lpgpu_launch_count(const lpgpu_ctx *c);
 /* U_host: this shard only, x_count*Nv^3*6 doubles, reference AoS layout. */
 int lpgpu_upload_U(lpgpu_ctx *c, const double *U_host);
 int lpgpu_download_U(lpgpu_ctx *c, double *U_host);
+/* Enqueue-only forms for pipelined callers (several contexts, one stream each: the copies of one overlap the
+ * kernels of another).  U_host must be page-locked and stay untouched until lpgpu_synchronize(c) returns. */
+int lpgpu_upload_U_async(lpgpu_ctx *c, const double *U_host);
+int lpgpu_download_U_async(lpgpu_ctx *c, double *U_host);
 
 /* ---- whole phases ----------------------------------------------------------------------- */
 /* RK3(U), LP_ompi.cpp:666 / advection_1.cpp:412-576.  Single-shard contexts only
@@ -81,6 +85,8 @@ int lpgpu_collide_step(lpgpu_ctx *c);
 int lpgpu_collide_step_async(lpgpu_ctx *c);
 /* nsteps passes of the while(t<nT) body without diagnostics (single shard). */
 int lpgpu_step(lpgpu_ctx *c, int nsteps);
+/* Same, enqueued only (lpgpu_synchronize before reading results). */
+int lpgpu_step_async(lpgpu_ctx *c, int nsteps);
 
 /* ---- sharded advection: one exchange per SSP-RK3 stage (stage = 0,1,2) ------------------- */
 /* Device addresses (in this context's memory) for the exchange of stage `stage`:

@@ -172,6 +172,25 @@ int lpgpu_download_U(lpgpu_ctx *c, double *U)
   LP_CUDA(cudaStreamSynchronize(c->stream));
   return LPGPU_OK;
 }
+// Enqueue-only forms: the copy and the layout kernel are ordered on the context's stream, the host returns at once.
+// The AoS staging buffer is shared by both directions; stream order keeps an upload behind the previous download.
+int lpgpu_upload_U_async(lpgpu_ctx *c, const double *U)
+{
+  LP_ENTER(c);
+  if (!U) { lp_set_error("lpgpu_upload_U_async: null U"); return LPGPU_EINVAL; }
+  const size_t n = (size_t)6 * c->sv * c->ncell;
+  LP_CUDA(cudaMemcpyAsync(c->d_aos, U, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return lp_launch_aos_to_planes(c, c->d_aos, c->d_U[0]);
+}
+int lpgpu_download_U_async(lpgpu_ctx *c, double *U)
+{
+  LP_ENTER(c);
+  if (!U) { lp_set_error("lpgpu_download_U_async: null U"); return LPGPU_EINVAL; }
+  const size_t n = (size_t)6 * c->sv * c->ncell;
+  LP_TRY(lp_launch_planes_to_aos(c, c->d_U[0], c->d_aos));
+  LP_CUDA(cudaMemcpyAsync(U, c->d_aos, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return LPGPU_OK;
+}
 
 // ---- advection ------------------------------------------------------------------------------
 static int check_stage(lpgpu_ctx *c, int stage)
@@ -322,9 +341,21 @@ int lpgpu_collide_step_async(lpgpu_ctx *c)
   if (!(c->p.nu > 0.)) return LPGPU_OK;
   return collide_async(c);
 }
+static int step_enqueue(lpgpu_ctx *c, int nsteps);
 int lpgpu_step(lpgpu_ctx *c, int nsteps)
 {
   LP_ENTER(c);
+  LP_TRY(step_enqueue(c, nsteps));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+int lpgpu_step_async(lpgpu_ctx *c, int nsteps)
+{
+  LP_ENTER(c);
+  return step_enqueue(c, nsteps);
+}
+static int step_enqueue(lpgpu_ctx *c, int nsteps)
+{
   static const bool no_graph = getenv("LPGPU_NO_GRAPH") != nullptr;   // developer knob
   int done = 0;
   if (!no_graph && c->prof_on == 0 && !c->graph_failed && nsteps >= 2) {
@@ -340,7 +371,6 @@ int lpgpu_step(lpgpu_ctx *c, int nsteps)
       }
   }
   for (; done < nsteps; done++) LP_TRY(one_step_async(c));
-  LP_CUDA(cudaStreamSynchronize(c->stream));
   return LPGPU_OK;
 }
 

@@ -38,6 +38,7 @@ class Exchange(C.Structure):
 EXPORTS = [
     "lpgpu_last_error", "lpgpu_device_count", "lpgpu_init", "lpgpu_finalize", "lpgpu_set_stream",
     "lpgpu_synchronize", "lpgpu_launch_count", "lpgpu_upload_U", "lpgpu_download_U",
+    "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_step_async",
     "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_step", "lpgpu_advect_exchange_info",
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
@@ -65,9 +66,9 @@ def load_library():
     for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_sample_device"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.lpgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
-    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums"):
+    for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
-    for name in ("lpgpu_step", "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_eval_device"):
+    for name in ("lpgpu_step", "lpgpu_step_async", "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_eval_device"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_int]
     L.lpgpu_advect_exchange_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(Exchange)]
     for name in ("lpgpu_fft3D", "lpgpu_FS", "lpgpu_ComputeQ"):
@@ -146,14 +147,16 @@ class LPGpu:
         return int(self.L.lpgpu_launch_count(self.h))
 
     # -- state
-    def upload_U(self, U):
+    def upload_U(self, U, wait=True):
+        """wait=False: enqueue only; U must then be page-locked and stay alive until synchronize()."""
         U = _f64(U)
         assert U.size == self.ncell * self.sv * 6, "U must hold this shard: x_count*Nv^3*6 doubles"
-        self._check(self.L.lpgpu_upload_U(self.h, _ptr(U)))
+        self._check((self.L.lpgpu_upload_U if wait else self.L.lpgpu_upload_U_async)(self.h, _ptr(U)))
 
-    def download_U(self, out=None):
+    def download_U(self, out=None, wait=True):
         U = np.empty(self.ncell * self.sv * 6) if out is None else out
-        self._check(self.L.lpgpu_download_U(self.h, _ptr(U)))
+        assert wait or out is not None, "an enqueue-only download needs the caller's page-locked buffer"
+        self._check((self.L.lpgpu_download_U if wait else self.L.lpgpu_download_U_async)(self.h, _ptr(U)))
         return U
 
     # -- phases
@@ -163,8 +166,8 @@ class LPGpu:
     def collide_step(self, wait=True):
         self._check(self.L.lpgpu_collide_step(self.h) if wait else self.L.lpgpu_collide_step_async(self.h))
 
-    def step(self, nsteps=1):
-        self._check(self.L.lpgpu_step(self.h, int(nsteps)))
+    def step(self, nsteps=1, wait=True):
+        self._check((self.L.lpgpu_step if wait else self.L.lpgpu_step_async)(self.h, int(nsteps)))
 
     def exchange_info(self, stage):
         ex = Exchange()

@@ -255,8 +255,13 @@ class _DeviceBuffer:
 class ShardedSolver:
     """One rank of the x-sharded solver.  world == 1 needs no process group."""
 
-    def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None, full_and_linear=False):
+    def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None, full_and_linear=False,
+                 stream=None):
+        """stream: a torch.cuda.Stream all work of this solver (kernels, copies, the NCCL exchange) is ordered on;
+        None = torch's current stream for sharded runs, the library's default otherwise.  Two solvers on two streams
+        pipeline: the host<->device copies of one overlap the kernels of the other."""
         self.rank, self.world, self.dist = rank, world, dist
+        self.stream = stream
         self.homogeneous = bool(homogeneous)
         if homogeneous:
             self.x_begin, self.x_count = 0, 1
@@ -266,10 +271,13 @@ class ShardedSolver:
                              x_count=self.x_count, device=device, full_and_linear=full_and_linear)
         self.nu = nu
         self._ex = None
+        if stream is not None:
+            self.g.set_stream(stream.cuda_stream)
         if world > 1 and not homogeneous:
             import torch
             self.torch = torch
-            self.g.set_stream(torch.cuda.current_stream().cuda_stream)
+            if stream is None:
+                self.g.set_stream(torch.cuda.current_stream().cuda_stream)
             self._ex = []
             for stage in range(3):
                 e = self.g.exchange_info(stage)
@@ -279,11 +287,14 @@ class ShardedSolver:
                                      send_left=wrap(e.send_left, n), send_right=wrap(e.send_right, n),
                                      recv_left=wrap(e.recv_left, n), recv_right=wrap(e.recv_right, n)))
 
-    def upload(self, U_shard):
-        self.g.upload_U(U_shard)
+    def upload(self, U_shard, wait=True):
+        self.g.upload_U(U_shard, wait=wait)
 
-    def download(self, out=None):
-        return self.g.download_U(out)
+    def download(self, out=None, wait=True):
+        return self.g.download_U(out, wait=wait)
+
+    def synchronize(self):
+        self.g.synchronize()
 
     def advect(self):
         if self.homogeneous:
@@ -293,19 +304,25 @@ class ShardedSolver:
             return
         for stage in range(3):
             self.g.advect_reduce(stage)
-            exchange_stage(self.dist, self.rank, self.world, **self._ex[stage])
+            if self.stream is not None:
+                with self.torch.cuda.stream(self.stream):
+                    exchange_stage(self.dist, self.rank, self.world, **self._ex[stage])
+            else:
+                exchange_stage(self.dist, self.rank, self.world, **self._ex[stage])
             self.g.advect_apply(stage)
 
-    def step(self, nsteps=1):
-        """nsteps passes of the while(t<nT) body (LP_ompi.cpp:662-813) without diagnostics."""
+    def step(self, nsteps=1, wait=True):
+        """nsteps passes of the while(t<nT) body (LP_ompi.cpp:662-813) without diagnostics.  wait=False only
+        enqueues (pipelined callers: synchronize() before touching host buffers)."""
         if self.world == 1 or self.homogeneous:
-            self.g.step(nsteps)
+            self.g.step(nsteps, wait=wait)
             return
         for _ in range(nsteps):
             self.advect()
             if self.nu > 0:
                 self.g.collide_step(wait=False)      # enqueue only: the host runs ahead into the next exchange
-        self.g.synchronize()
+        if wait:
+            self.g.synchronize()
 
     def moments(self):
         """Global mass, P1..3, KiE, EleE (LP_ompi.cpp:820-827) on every rank."""

@@ -174,6 +174,38 @@ def test_graph_replay_matches_eager_steps(small, pkg):
     assert relerr(got, ora.step(ora.step(ora.step(ora.step(U))))) < TOL_U
 
 
+def test_pipelined_contexts_match_synchronous_calls(pkg):
+    """Enqueue-only upload/step/download on two contexts, one stream each (bench.py's end-to-end loop): every batch
+    must come back exactly as the synchronous calls return it."""
+    import torch
+    ora = PortOracle(**SMALL)
+    U = [_perturbed(ora, seed=k) for k in range(2)]
+    g = pkg.LPGpu(**SMALL)
+    want = []
+    for k in range(2):
+        g.upload_U(U[k])
+        g.step(1)
+        want.append(g.download_U())
+    g.close()
+    assert relerr(want[0] - U[0], ora.step(U[0]) - U[0]) < TOL_DU
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ctx = [pkg.LPGpu(**SMALL) for _ in range(2)]
+    host = [torch.from_numpy(u.copy()).pin_memory() for u in U]
+    back = [torch.empty_like(h).pin_memory() for h in host]
+    for c, st in zip(ctx, streams):
+        c.set_stream(st.cuda_stream)
+    for rep in range(3):
+        for k in range(2):
+            ctx[k].synchronize()
+            ctx[k].upload_U(host[k].numpy(), wait=False)
+            ctx[k].step(1, wait=False)
+            ctx[k].download_U(back[k].numpy(), wait=False)
+    for k in range(2):
+        ctx[k].synchronize()
+        assert np.array_equal(back[k].numpy(), want[k])
+        ctx[k].close()
+
+
 def test_entropy_and_negativity_diagnostics(small, pkg):
     """computeEntropy / FindNegVals / computeKiEratio (LP_ompi.cpp:819,829,846) on the GPU."""
     ora, g = small
