@@ -20,6 +20,12 @@
 struct lpo_ctx {
   int Nx, Nv, N, homogeneous, gamma, direct_intmodes;
   int fandl;                      /* FullandLinear: electron-ion term Q(f, ions) next to Q(f,f) */
+  /* reference test 1: Doping = True (non-uniform background, Dirichlet walls), LinearLandau = True (Q(f,M)),
+   * MassConsOnly = True */
+  int doping, a_i, b_i, linear, mass_only;
+  double NL, NH, eps, T_L, T_R, CCt_mass;
+  double *dirL, *dirR;            /* DirichletBC coefficients at the left / right wall: 6 per velocity cell */
+  double *mhat;                   /* DFTMaxwell: ncell * N^3 complex */
   double CCt_lin[4];              /* (C C^T)^-1 of the mass and energy rows (conservationRoutines.cpp:222-238) */
   int size_v, size_ft, ncell;
   double Lv, Lx, nu, dt, dv, dx, scalev, scaleL, scale3;
@@ -167,6 +173,8 @@ static void build_conservation(lpo_ctx *c)
   for (int q = 0; q < N3; q++) { a += c->C5[q] * c->C5[q]; b += c->C5[q] * c->C5[4 * N3 + q]; d += c->C5[4 * N3 + q] * c->C5[4 * N3 + q]; }
   c->CCt_lin[0] = a; c->CCt_lin[1] = b; c->CCt_lin[2] = b; c->CCt_lin[3] = d;
   invert_small(c->CCt_lin, 2);
+  /* createCCtAndPivot_OnlyMass (conservationRoutines.cpp:311-349): M = 1, CCt = (sum C1_1^2)^-1 */
+  c->CCt_mass = 1. / a;
 }
 void lpo_get_conservation(const lpo_ctx *c, double *C5, double *CCt25)
 {
@@ -282,6 +290,7 @@ void lpo_destroy(lpo_ctx *c)
   if (!c) return;
   free(c->v); free(c->eta); free(c->wt); free(c->Sh); free(c->C5);
   free(c->T1); free(c->M1); free(c->S1); free(c->node_cell); free(c->node_xi);
+  free(c->dirL); free(c->dirR); free(c->mhat);
   free(c);
 }
 void lpo_set_direct_intmodes(lpo_ctx *c, int on) { c->direct_intmodes = on; }
@@ -423,10 +432,73 @@ void lpo_ComputeQ(const lpo_ctx *c, const double *f, double *qHat)
   free(in); free(fh);
 }
 
+/* ComputeQLinear (collisionRoutines_1.cpp:1185-1269): Q(f, M) -- the first factor of every pair is the stored
+ * transform of the initial Maxwellian, the second the transform of f */
+void lpo_ComputeQLinear(const lpo_ctx *c, const double *f, const double *mh, double *qHat)
+{
+  const int N = c->N, N3 = c->size_ft;
+  double *in = (double *)malloc(sizeof(double) * 2 * N3), *fh = (double *)malloc(sizeof(double) * 2 * N3);
+  for (int q = 0; q < N3; q++) { in[2 * q] = f[q]; in[2 * q + 1] = 0.; }
+  lpo_fft3D(c, in, fh);
+  const double pref = c->h_eta * c->h_eta * c->h_eta, *wt = c->wt;
+  #pragma omp parallel for collapse(2) schedule(dynamic)
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++)
+      for (int k = 0; k < N; k++) {
+        int si, ei, sj, ej, sk, ek;
+        window(N, i, &si, &ei); window(N, j, &sj, &ej); window(N, k, &sk, &ek);
+        double t0 = 0., t1 = 0.;
+        for (int l = si; l < ei; l++)
+          for (int m = sj; m < ej; m++)
+            for (int n = sk; n < ek; n++) {
+              int x = i + N / 2 - l, y = j + N / 2 - m, z = k + N / 2 - n;
+              int a = n + N * (m + N * l), b = z + N * (y + N * x);
+              double W = weight_at(c, i, j, k, l, m, n);
+              t0 += pref * wt[l] * wt[m] * wt[n] * (W * (mh[2 * a] * fh[2 * b] - mh[2 * a + 1] * fh[2 * b + 1]));
+              t1 += pref * wt[l] * wt[m] * wt[n] * (W * (mh[2 * a] * fh[2 * b + 1] + mh[2 * a + 1] * fh[2 * b]));
+            }
+        int q = k + N * (j + N * i);
+        qHat[2 * q] = t0; qHat[2 * q + 1] = t1;
+      }
+  free(in); free(fh);
+}
+/* the operator the time loop applies to cell `cell` (LP_ompi.cpp:692-703) */
+static void compute_q_cell(const lpo_ctx *c, const double *f, int cell, double *qHat)
+{
+  if (c->linear) lpo_ComputeQLinear(c, f, c->mhat + (size_t)cell * 2 * c->size_ft, qHat);
+  else lpo_ComputeQ(c, f, qHat);
+}
+/* ComputeDFTofMaxwellian (collisionRoutines_1.cpp:1169-1183): the transform of the state held in U when it is called
+ * (the initial condition), per cell.  The reference calls fft3D inside its fill loop; the last call wins. */
+void lpo_set_linear_landau(lpo_ctx *c, const double *U)
+{
+  const int N3 = c->size_ft;
+  free(c->mhat); c->mhat = NULL; c->linear = 0;
+  if (!U) return;
+  double *f = (double *)malloc(sizeof(double) * (size_t)c->ncell * N3), *in = (double *)malloc(sizeof(double) * 2 * N3);
+  c->mhat = (double *)malloc(sizeof(double) * (size_t)c->ncell * 2 * N3);
+  lpo_setInit_spectral(c, U, f);
+  for (int cell = 0; cell < c->ncell; cell++) {
+    for (int q = 0; q < N3; q++) { in[2 * q] = f[(size_t)cell * N3 + q]; in[2 * q + 1] = 0.; }
+    lpo_fft3D(c, in, c->mhat + (size_t)cell * 2 * N3);
+  }
+  free(f); free(in);
+  c->linear = 1;
+}
+void lpo_set_mass_cons_only(lpo_ctx *c, int on) { c->mass_only = on; }
+
 /* conserveAllMoments_Normal + solveWithCCt: conservationRoutines.cpp:131-156, 32-58 */
 void lpo_conserveMoments(const lpo_ctx *c, double *qHat)
 {
   const int N3 = c->size_ft;
+  if (c->mass_only) {
+    /* conserveMass_Normal: conservationRoutines.cpp:290-309 (C1_1 = C1_5[0]) */
+    double t = 0.;
+    for (int q = 0; q < N3; q++) t += qHat[2 * q] * c->C5[q];
+    const double lam0 = c->CCt_mass * t;
+    for (int q = 0; q < N3; q++) qHat[2 * q] -= (c->C5[q] * lam0);
+    return;
+  }
   double lam[5] = {0, 0, 0, 0, 0}, b[5];
   for (int q = 0; q < N3; q++) {
     lam[0] += qHat[2 * q] * c->C5[0 * N3 + q];
@@ -542,13 +614,13 @@ void lpo_RK4(const lpo_ctx *c, const double *f, int cell, const double *qHat, co
          *q3 = (double *)malloc(sizeof(double) * 2 * N3);
   lpo_FS(c, qHat, out);
   for (int i = 0; i < N3; i++) { Q[i] = out[2 * i]; f1[i] = f[i] + dt * Q[i] * nu; }
-  lpo_ComputeQ(c, f1, q1); lpo_conserveMoments(c, q1);
+  compute_q_cell(c, f1, cell, q1); lpo_conserveMoments(c, q1);   /* RK4Linear (:1272-1350) has the same stage logic */
   lpo_FS(c, q1, out);
   for (int i = 0; i < N3; i++) { Q1[i] = out[2 * i]; f1[i] = f[i] + 0.5 * dt * Q[i] * nu + 0.5 * dt * Q1[i] * nu; }
-  lpo_ComputeQ(c, f1, q2); lpo_conserveMoments(c, q2);
+  compute_q_cell(c, f1, cell, q2); lpo_conserveMoments(c, q2);
   lpo_FS(c, q2, out);
   for (int i = 0; i < N3; i++) { Q1[i] = out[2 * i]; f1[i] = f[i] + 0.5 * Q[i] * nu + 0.5 * Q1[i] * nu; }
-  lpo_ComputeQ(c, f1, q3); lpo_conserveMoments(c, q3);
+  compute_q_cell(c, f1, cell, q3); lpo_conserveMoments(c, q3);
   if (q123) {
     memcpy(q123, q1, sizeof(double) * 2 * N3);
     memcpy(q123 + 2 * N3, q2, sizeof(double) * 2 * N3);
@@ -696,7 +768,7 @@ void lpo_collide_step(const lpo_ctx *c, double *U)
       free(ql);
       continue;
     }
-    lpo_ComputeQ(c, f + (size_t)cell * N3, q);
+    compute_q_cell(c, f + (size_t)cell * N3, cell, q);
     lpo_conserveMoments(c, q);
     lpo_RK4(c, f + (size_t)cell * N3, cell, q, U, dU + 5 * (size_t)cell * sv, NULL);
   }
@@ -734,6 +806,27 @@ static void field_compute(const lpo_ctx *c, const double *U, field_t *F)
   }
   double P = 0., acc = 0.;
   for (int i = 0; i < Nx; i++) { F->cp[i] = dx * P; acc += P + 0.5 * F->m[i] - F->s[i] / 12.; P += F->m[i]; }
+  if (c->doping) {
+    /* computePhi_x_0_Doping, Int_E_Doping, Int_E1st_Doping, Int_E2nd_Doping: FieldCalculations.cpp:427-450, 585-676 */
+    const double NL = c->NL, NH = c->NH, eps = c->eps, a_val = (c->a_i + 1) * dx, b_val = (c->b_i + 1) * dx, Phi_Lx = 1;
+    const double tmp = acc * dx * dx;
+    F->ce = Phi_Lx / Lx + 0.5 * NH * Lx / eps + (NL - NH) * (b_val - a_val) / eps - (0.5 * (NL - NH) * (b_val * b_val - a_val * a_val) + tmp) / (Lx * eps);
+    P = 0.;
+    for (int i = 0; i < Nx; i++) {
+      const double ND = (i <= c->a_i || i > c->b_i) ? NH : NL, xi = gridx(c, (double)i), c2 = F->s[i] * dx / 2.;
+      double r = -(P + 0.5 * F->m[i] - F->s[i] / 12.) * dx * dx + ND * xi * dx;
+      if (i > c->a_i) r += (NH - NL) * a_val * dx;
+      if (i > c->b_i) r += (NL - NH) * b_val * dx;
+      F->iE[i] = r / eps - F->ce * dx;
+      F->iE1[i] = (ND - F->m[i]) * dx * dx / (12. * eps);
+      r = (-F->cp[i] + (F->m[i] * gridx(c, i - 0.5) + 0.25 * c2)) * dx / 12. + (ND - F->m[i]) * dx * xi / 12. - c2 * dx / 80.;
+      if (i > c->a_i) r += (NH - NL) * a_val * dx / 12.;
+      if (i > c->b_i) r += (NL - NH) * b_val * dx / 12.;
+      F->iE2[i] = r / eps - F->ce * dx / 12.;
+      P += F->m[i];
+    }
+    return;
+  }
   F->ce = 0.5 * Lx - acc * dx * dx / Lx;
   P = 0.;
   for (int i = 0; i < Nx; i++) {
@@ -774,11 +867,15 @@ static void dg_rhs(const lpo_ctx *c, const double *U, const field_t *F, size_t k
   {
     const double *R, *L; double ur, ul;
     if (j1 < Nv / 2) {
-      int ir = i + 1; if (ir == Nx) ir = 0;
-      R = U + 6 * ((size_t)ir * sv + jm); L = u; ur = -R[1]; ul = -L[1];
+      int ir = i + 1;
+      if (ir == Nx && c->doping) R = c->dirR + 6 * (size_t)jm;       /* I3_Doping: DirichletBC at the right wall (advection_1.cpp:230-233) */
+      else { if (ir == Nx) ir = 0; R = U + 6 * ((size_t)ir * sv + jm); }
+      L = u; ur = -R[1]; ul = -L[1];
     } else {
-      int il = i - 1; if (il == -1) il = Nx - 1;
-      R = u; L = U + 6 * ((size_t)il * sv + jm); ur = R[1]; ul = L[1];
+      int il = i - 1;
+      if (il == -1 && c->doping) L = c->dirL + 6 * (size_t)jm;       /* DirichletBC at the left wall (:254-257) */
+      else { if (il == -1) il = Nx - 1; L = U + 6 * ((size_t)il * sv + jm); }
+      R = u; ur = R[1]; ul = L[1];
     }
     tp[0] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 + (R[2] - L[2]) * dv / 12. + (R[5] - L[5]) * c1 / 4.);
     tp[1] -= 0.5 * dv3 * ((R[0] + 0.5 * ur + L[0] + 0.5 * ul) * c1 + (R[2] + L[2]) * dv / 12. + (R[5] + L[5]) * c1 / 4.);
@@ -850,14 +947,19 @@ static double two_gauss(double v1, double v2, double v3)
 }
 static double maxwellian_x(double x) { double T = 0.4; return exp(-x * x / (2 * T)) / sqrt(2 * T * M_PI); }
 /* cell moments of a velocity profile against the DG test functions: tmp0..tmp4 of the reference */
+static void vcell_moments_T(const lpo_ctx *c, int kind, double T, double s1, double s2, double s3, int j1, int j2, int j3, double t[5]);
 static void vcell_moments(const lpo_ctx *c, int kind, double s1, double s2, double s3, int j1, int j2, int j3, double t[5])
+{
+  vcell_moments_T(c, kind, 0.4, s1, s2, s3, j1, j2, j3, t);
+}
+static void vcell_moments_T(const lpo_ctx *c, int kind, double T, double s1, double s2, double s3, int j1, int j2, int j3, double t[5])
 {
   const double dv = c->dv;
   for (int l = 0; l < 5; l++) t[l] = 0.;
   for (int m1 = 0; m1 < 5; m1++) for (int m2 = 0; m2 < 5; m2++) for (int m3 = 0; m3 < 5; m3++) {
     double a = gridv(c, (double)j1) + 0.5 * dv * GT[m1] + s1, b = gridv(c, (double)j2) + 0.5 * dv * GT[m2] + s2,
            d = gridv(c, (double)j3) + 0.5 * dv * GT[m3] + s3;
-    double tp = GW[m1] * GW[m2] * GW[m3] * (kind == 1 ? two_gauss(a, b, d) : maxwellian(a, b, d, 0.4));
+    double tp = GW[m1] * GW[m2] * GW[m3] * (kind == 1 ? two_gauss(a, b, d) : maxwellian(a, b, d, T));
     t[0] += tp; t[1] += tp * 0.5 * GT[m1]; t[2] += tp * 0.5 * GT[m2]; t[3] += tp * 0.5 * GT[m3];
     t[4] += tp * 0.25 * (GT[m1] * GT[m1] + GT[m2] * GT[m2] + GT[m3] * GT[m3]);
   }
@@ -879,6 +981,42 @@ void lpo_SetInit_LD(const lpo_ctx *c, double *U, double a, double kw, int twostr
       U[k * 6 + 2] = xf * t[1] * 12 / dx; U[k * 6 + 3] = xf * t[2] * 12 / dx; U[k * 6 + 4] = xf * t[3] * 12 / dx;
     }
   }
+}
+/* DG coefficients of ND * Maxwellian(T) on velocity cell (j1,j2,j3): the body shared by SetInit_ND
+ * (SetInit_1.cpp:125-173) and DirichletBC (advection_1.cpp:24-69) */
+static void nd_maxwellian_cell(const lpo_ctx *c, double ND, double T, int j1, int j2, int j3, double u[6])
+{
+  double t[5]; vcell_moments_T(c, 0, T, 0., 0., 0., j1, j2, j3, t);
+  const double tp0 = ND * t[0], tp5 = ND * t[4];
+  u[0] = 19 * tp0 / 4. - 15 * tp5;
+  u[5] = 60 * tp5 - 15 * tp0;
+  u[1] = 0;
+  u[2] = ND * t[1] * 12; u[3] = ND * t[2] * 12; u[4] = ND * t[3] * 12;
+}
+static double doping_profile(const lpo_ctx *c, int i) { return (i <= c->a_i || i > c->b_i) ? c->NH : c->NL; }   /* FieldCalculations.cpp:413-425 */
+/* Doping = True: LP_ompi.cpp:157-166 (a_i, b_i), ReadDopingParameters */
+void lpo_set_doping(lpo_ctx *c, double NL, double NH, double eps, double T_L, double T_R)
+{
+  const int Nv = c->Nv;
+  c->doping = 1; c->NL = NL; c->NH = NH; c->eps = eps; c->T_L = T_L; c->T_R = T_R;
+  c->a_i = c->Nx / 3 - 1; c->b_i = 2 * c->Nx / 3 - 1;
+  free(c->dirL); free(c->dirR);
+  c->dirL = (double *)malloc(sizeof(double) * 6 * c->size_v);
+  c->dirR = (double *)malloc(sizeof(double) * 6 * c->size_v);
+  for (int j1 = 0; j1 < Nv; j1++) for (int j2 = 0; j2 < Nv; j2++) for (int j3 = 0; j3 < Nv; j3++) {
+    const size_t j = (size_t)(j1 * Nv * Nv + j2 * Nv + j3);
+    nd_maxwellian_cell(c, doping_profile(c, 0), T_L, j1, j2, j3, c->dirL + 6 * j);
+    nd_maxwellian_cell(c, doping_profile(c, c->Nx - 1), T_R, j1, j2, j3, c->dirR + 6 * j);
+  }
+}
+void lpo_SetInit_ND(const lpo_ctx *c, double *U)
+{
+  const int Nv = c->Nv;
+  for (int j1 = 0; j1 < Nv; j1++) for (int j2 = 0; j2 < Nv; j2++) for (int j3 = 0; j3 < Nv; j3++)
+    for (int i = 0; i < c->Nx; i++) {
+      size_t k = (size_t)i * c->size_v + (j1 * Nv * Nv + j2 * Nv + j3);
+      nd_maxwellian_cell(c, doping_profile(c, i), c->T_R, j1, j2, j3, U + 6 * k);
+    }
 }
 void lpo_SetInit_4H(const lpo_ctx *c, double *U)
 {

@@ -7,7 +7,7 @@
  *
  * Parity status: PINNED.  tests/test_oracle.py checks this restatement element-wise against the
  * unmodified reference compiled from /root/reference (oracle/_ref/libref.so) and against the
- * reference's golden files tests/Moments_Test0.dc / Moments_Test4.dc (copied values in
+ * reference's golden files tests/Moments_Test0.dc / _Test1 / _Test3 / _Test4 (copied values in
  * tests/golden/).
  *
  * Layouts are the reference's: U is AoS, U[6*k+l], k = i*Nv^3 + j1*Nv^2 + j2*Nv + j3
@@ -51,6 +51,17 @@ void lpo_collide_step(const lpo_ctx *c, double *U);
 void lpo_set_fandl(lpo_ctx *c, int on);
 void lpo_ComputeQ_FandL(const lpo_ctx *c, const double *f, double *qHat, double *qLin);
 void lpo_conserveMoments_FandL(const lpo_ctx *c, double *qHat, double *qLin);
+
+/* reference test 1 flags.  Doping = True: SetInit_ND, the *_Doping field integrals, I3_Doping with DirichletBC
+ * (SetInit_1.cpp:125-173, FieldCalculations.cpp:413-676, advection_1.cpp:24-69, 214-282).  LinearLandau = True:
+ * ComputeQLinear / RK4Linear with the transform of the state passed here as the fixed Maxwellian
+ * (collisionRoutines_1.cpp:1169-1350); U = NULL switches back.  MassConsOnly = True: conserveMass_Normal
+ * (conservationRoutines.cpp:290-349). */
+void lpo_set_doping(lpo_ctx *c, double NL, double NH, double eps, double T_L, double T_R);
+void lpo_SetInit_ND(const lpo_ctx *c, double *U);
+void lpo_set_linear_landau(lpo_ctx *c, const double *U);
+void lpo_set_mass_cons_only(lpo_ctx *c, int on);
+void lpo_ComputeQLinear(const lpo_ctx *c, const double *f, const double *mhat, double *qHat);
 
 /* advection path */
 void lpo_field(const lpo_ctx *c, const double *U, double *out /* 1 + 4*Nx */);

@@ -98,6 +98,27 @@ class PortOracle:
         """FullandLinear = True (reference test 3): collide_step / step use the *_FandL routines."""
         self._call("lpo_set_fandl", int(on))
 
+    def set_doping(self, NL, NH, eps, T_L=0.4, T_R=0.4):
+        """Doping = True (reference test 1): non-uniform background, Dirichlet walls."""
+        self._call("lpo_set_doping", float(NL), float(NH), float(eps), float(T_L), float(T_R))
+
+    def SetInit_ND(self):
+        U = np.zeros(self.ncell * self.sv * 6)
+        self._call("lpo_SetInit_ND", U)
+        return U
+
+    def set_linear_landau(self, U):
+        """LinearLandau = True: Q(f, M) with M the state U (ComputeDFTofMaxwellian); None switches back."""
+        self._call("lpo_set_linear_landau", None if U is None else _f64(U))
+
+    def set_mass_cons_only(self, on=True):
+        self._call("lpo_set_mass_cons_only", int(on))
+
+    def ComputeQLinear(self, f, mhat):
+        q = np.empty((self.N3, 2))
+        self._call("lpo_ComputeQLinear", _f64(f), _f64(mhat), q)
+        return q
+
     def ComputeQ_FandL(self, f):
         q, ql = np.empty((self.N3, 2)), np.empty((self.N3, 2))
         self._call("lpo_ComputeQ_FandL", _f64(f), q, ql)

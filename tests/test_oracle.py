@@ -97,6 +97,37 @@ def test_port_reproduces_Moments_Test3_full_and_linear():
     assert abs(gold[5][4] - gold0[5][4]) > 5e-6
 
 
+TEST1_DOPING = dict(NL=0.001, NH=1., eps=0.1, T_L=0.4, T_R=0.4)      # [Doping] section of LPsolver-input-test1.txt
+
+
+def test_port_reproduces_Moments_Test1_doping_linear_massonly():
+    """Reference test 1: Doping (SetInit_ND, *_Doping field integrals, Dirichlet walls in I3), LinearLandau
+    (ComputeQLinear / RK4Linear against the transform of the initial state) and MassConsOnly.  Every printed digit of
+    all six rows of tests/Moments_Test1.dc, and the final state the unmodified reference dumps (ref_test1.npz,
+    tests/golden/make_test1_golden.py) element by element."""
+    gold = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test1.dc"]
+    z = np.load(os.path.join(GOLD, "ref_test1.npz"))
+    P = PortOracle(**TEST0)
+    P.set_doping(**TEST1_DOPING)
+    U0 = P.SetInit_ND()
+    P.set_linear_landau(U0)
+    P.set_mass_cons_only(True)
+    U = U0
+    for step in range(6):
+        m = P.moments(U)
+        row = [m[0], m[1], m[2], m[3], m[4], m[5], np.sqrt(m[5]), np.log(np.sqrt(m[5])), m[4] + m[5]]
+        for col in (0, 1, 4, 5, 6, 7, 8):                   # P1 is a real signal here (walls), not round-off
+            assert abs(row[col] - gold[step][col]) <= 6e-8 * max(1.0, abs(gold[step][col])), (step, col)
+        if step == 5:
+            _gate([float("%.8g" % x) for x in row], gold[5])   # moment_differ.sh compares the printed files (%11.8g)
+        else:
+            U = P.step(U)
+    st = int(z["stride"])
+    assert relerr(U[::st], z["U_sample"]) < 1e-12
+    assert relerr((U - U0)[::st], z["U_sample"] - U0[::st]) < 1e-10
+    assert abs(U.sum() - float(z["U_sum"])) < 1e-10 * float(z["U_abs_sum"])
+
+
 def test_port_reproduces_Moments_Test4():
     gold = json.load(open(os.path.join(GOLD, "reference_moments.json")))["Moments_Test4.dc"]
     P = PortOracle(homogeneous=True, **TEST0)
