@@ -48,6 +48,14 @@ typedef struct lpgpu_params {
   int full_and_linear;  /* reference flag FullandLinear (test 3): electron-ion term next to Q(f,f) -- ComputeQ_FandL,
                            conserveAllMoments_FandL, RK4_FandL (collisionRoutines_1.cpp:605-689, 800-901, 987-1085;
                            conservationRoutines.cpp:102-129).  Runs through the direct-sum kernel (correct, not tuned). */
+  /* ---- reference test 1 options (appended: older callers that zero the struct keep their behaviour) ---- */
+  int doping;           /* reference flag Doping: step doping profile ND(x) (NH outside, NL inside the middle third,
+                           FieldCalculations.cpp:413-425), the *_Doping field integrals (:427-676) and Dirichlet walls in
+                           I3 (advection_1.cpp:24-69, 214-282) instead of the periodic neighbour */
+  double NL, NH, eps, T_L, T_R;   /* [Doping] section: densities, dielectric constant, wall temperatures */
+  int linear_landau;    /* reference flag LinearLandau: Q(f, M) -- ComputeQLinear / RK4Linear (collisionRoutines_1.cpp:
+                           1185-1350) against the transform of the state captured by lpgpu_set_maxwellian */
+  int mass_cons_only;   /* reference flag MassConsOnly: conserveMass_Normal (conservationRoutines.cpp:290-349) */
 } lpgpu_params;
 
 const char *lpgpu_last_error(void);
@@ -72,6 +80,11 @@ int lpgpu_download_U(lpgpu_ctx *c, double *U_host);
  * kernels of another).  U_host must be page-locked and stay untouched until lpgpu_synchronize(c) returns. */
 int lpgpu_upload_U_async(lpgpu_ctx *c, const double *U_host);
 int lpgpu_download_U_async(lpgpu_ctx *c, double *U_host);
+
+/* ComputeDFTofMaxwellian(U, f, DFTMaxwell) (LP_ompi.cpp:516, :541; collisionRoutines_1.cpp:1169-1183): capture the
+ * shifted transform of the state currently held on the device, cell by cell, as the fixed second argument M of the
+ * linear operator Q(f, M).  Needs linear_landau = 1; call once after uploading the initial condition. */
+int lpgpu_set_maxwellian(lpgpu_ctx *c);
 
 /* ---- whole phases ----------------------------------------------------------------------- */
 /* RK3(U), LP_ompi.cpp:666 / advection_1.cpp:412-576.  Single-shard contexts only

@@ -92,8 +92,11 @@ int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes)
 // intE2 = Int_E2nd (advection_1.cpp:419-429) from the gathered (m_q, s_q), q = 0..Nx-1.  The scan is
 // Nx long (<= a few hundred) and sequential on purpose: ce is a catastrophic cancellation
 // (Lx/2 - O(Lx/2)), so every GPU evaluates it in the same fixed order.
+// Doping = True: computePhi_x_0_Doping, Int_E_Doping, Int_E1st_Doping, Int_E2nd_Doping (FieldCalculations.cpp:427-450,
+// 585-676) with the step profile ND(i) = NH for i <= a_i or i > b_i, NL between (:413-425)
+struct DopingParams { int on, a_i, b_i; double NL, NH, eps; };
 __global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
-                                                    double dx, double Lx)
+                                                    double dx, double Lx, DopingParams D)
 {
   extern __shared__ double sms[];          // m[Nx] | s/12 [Nx] | prefix P[Nx]
   double *sm = sms, *s12 = sms + Nx, *sP = sms + 2 * Nx;
@@ -104,7 +107,13 @@ __global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ m
     // the serial part keeps the summation order of the one-thread scan: only additions are left on the chain
     double P = 0., acc = 0.;
     for (int q = 0; q < Nx; q++) { sP[q] = P; acc += P + 0.5 * sm[q] - s12[q]; P += sm[q]; }
-    s_ce = 0.5 * Lx - acc * dx * dx / Lx;
+    if (D.on) {
+      const double a_val = (D.a_i + 1) * dx, b_val = (D.b_i + 1) * dx, Phi_Lx = 1, tmp = acc * dx * dx;
+      s_ce = Phi_Lx / Lx + 0.5 * D.NH * Lx / D.eps + (D.NL - D.NH) * (b_val - a_val) / D.eps
+             - (0.5 * (D.NL - D.NH) * (b_val * b_val - a_val * a_val) + tmp) / (Lx * D.eps);
+    } else {
+      s_ce = 0.5 * Lx - acc * dx * dx / Lx;
+    }
     fld[0] = s_ce;
   }
   __syncthreads();
@@ -114,6 +123,19 @@ __global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ m
     const double xi = (q + 0.5) * dx, xl = ((q - 0.5) + 0.5) * dx, c2 = s * dx / 2., cp = dx * P;
     double *o = fld + 1 + 4 * (q - x_begin);
     o[0] = cp;
+    if (D.on) {
+      const double ND = (q <= D.a_i || q > D.b_i) ? D.NH : D.NL, a_val = (D.a_i + 1) * dx, b_val = (D.b_i + 1) * dx;
+      double r = -(P + 0.5 * m - s12[q]) * dx * dx + ND * xi * dx;
+      if (q > D.a_i) r += (D.NH - D.NL) * a_val * dx;
+      if (q > D.b_i) r += (D.NL - D.NH) * b_val * dx;
+      o[1] = r / D.eps - ce * dx;
+      o[2] = (ND - m) * dx * dx / (12. * D.eps);
+      r = (-cp + (m * xl + 0.25 * c2)) * dx / 12. + (ND - m) * dx * xi / 12. - c2 * dx / 80.;
+      if (q > D.a_i) r += (D.NH - D.NL) * a_val * dx / 12.;
+      if (q > D.b_i) r += (D.NL - D.NH) * b_val * dx / 12.;
+      o[3] = r / D.eps - ce * dx / 12.;
+      continue;
+    }
     o[1] = -ce * dx - (P + 0.5 * m - s12[q]) * dx * dx + xi * dx;
     o[2] = (1 - m) * dx * dx / 12.;
     o[3] = (-cp - ce + (m * xl + 0.25 * c2)) * dx / 12. + (1 - m) * dx * xi / 12. - c2 * dx / 80.;
@@ -122,7 +144,8 @@ __global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ m
 int lp_launch_field_scan(lpgpu_ctx *c)
 {
   const double dx = c->p.Lx / c->p.Nx;
-  k_field_scan<<<1, 256, (size_t)3 * c->p.Nx * sizeof(double), c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx);
+  DopingParams D = {c->p.doping, c->p.Nx / 3 - 1, 2 * c->p.Nx / 3 - 1, c->p.NL, c->p.NH, c->p.eps};   // a_i, b_i: LP_ompi.cpp:160-161
+  k_field_scan<<<1, 256, (size_t)3 * c->p.Nx * sizeof(double), c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx, D);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -253,9 +276,22 @@ int lp_launch_dg_stage(lpgpu_ctx *c, int stage)
   return LPGPU_OK;
 }
 
+// Doping: I3_Doping takes the upwind state beyond a domain wall from DirichletBC (advection_1.cpp:230-233, 254-257);
+// the wall planes are precomputed (tables.cpp) and copied into the halo planes that face a wall
+int lp_launch_wall_halo(lpgpu_ctx *c, double *planes)
+{
+  if (!c->p.doping || c->p.homogeneous) return LPGPU_OK;
+  const size_t plane = (size_t)6 * c->sv;
+  if (c->p.x_begin == 0)
+    LP_CUDA(cudaMemcpyAsync(planes, c->d_dirichlet, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (c->p.x_begin + c->ncell == c->p.Nx)
+    LP_CUDA(cudaMemcpyAsync(planes + plane * (c->ncell + 1), c->d_dirichlet + plane, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return LPGPU_OK;
+}
 // periodic halo when one context owns all of x (advection_1.cpp:297, :306)
 int lp_launch_local_halo(lpgpu_ctx *c, double *planes)
 {
+  if (c->p.doping) return lp_launch_wall_halo(c, planes);
   const size_t plane = (size_t)6 * c->sv;
   LP_CUDA(cudaMemcpyAsync(planes, planes + plane * c->ncell, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   LP_CUDA(cudaMemcpyAsync(planes + plane * (c->ncell + 1), planes + plane, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));

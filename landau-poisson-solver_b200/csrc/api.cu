@@ -54,6 +54,9 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
     if (p->Nx < 1 || !(p->Lx > 0)) { lp_set_error("lpgpu_init: need Nx >= 1 and Lx > 0"); return LPGPU_EINVAL; }
     if (p->x_begin < 0 || p->x_count < 1 || p->x_begin + p->x_count > p->Nx) { lp_set_error("lpgpu_init: bad shard [x_begin, x_begin + x_count)"); return LPGPU_EINVAL; }
   }
+  if (p->doping && (p->homogeneous || !(p->eps > 0) || !(p->T_L > 0) || !(p->T_R > 0))) { lp_set_error("lpgpu_init: Doping needs an inhomogeneous run, eps > 0, T_L > 0, T_R > 0"); return LPGPU_EINVAL; }
+  if (p->linear_landau && p->full_and_linear) { lp_set_error("lpgpu_init: LinearLandau and FullandLinear exclude each other (LP_ompi.cpp:681-703)"); return LPGPU_EINVAL; }
+  if (p->mass_cons_only && p->full_and_linear) { lp_set_error("lpgpu_init: MassConsOnly with FullandLinear (conserveMass_FandL) is not implemented"); return LPGPU_EINVAL; }
   const int ndev = lpgpu_device_count();
   if (ndev <= 0) { lp_set_error("lpgpu_init: no CUDA device (this library has no CPU path)"); return LPGPU_ENODEV; }
   if (p->device < 0 || p->device >= ndev) { lp_set_error("lpgpu_init: bad device ordinal"); return LPGPU_EINVAL; }
@@ -69,6 +72,11 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   c->stream = 0;
   c->launches = 0;
   lp_build_tables(c->p, c->tab);
+  if (p->linear_landau && !lp_fc3_available(c)) {
+    lp_set_error("lpgpu_init: LinearLandau runs through the FFT-convolution pipeline only (N = 8, 16, 24 or 32, computeq_variant 0 or 2)");
+    delete c;
+    return LPGPU_EINVAL;
+  }
 
   const LpTables &t = c->tab;
   int rc = LPGPU_OK;
@@ -80,6 +88,7 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
     std::vector<double> cl(t.CCt_lin, t.CCt_lin + 4);
     A_(dev_upload(&c->d_CCt_lin, cl));
   }
+  if (p->doping) A_(dev_upload(&c->d_dirichlet, t.dirichlet));
   A_(dev_upload(&c->d_C5, t.C5));
   { std::vector<double> cct(t.CCt, t.CCt + 25); A_(dev_upload(&c->d_CCt, cct)); }
   A_(dev_upload(&c->d_Wfwd, t.Wfwd));
@@ -119,6 +128,7 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   for (int s = 0; s < 4; s++) A_(dev_alloc(&c->d_q[s], 2 * n3));
   A_(dev_alloc(&c->d_lam, (size_t)5 * 8 * c->cap_cells + 8));
   A_(dev_alloc(&c->d_cpart, (size_t)5 * p->N * c->cap_cells));
+  if (p->linear_landau) A_(dev_alloc(&c->d_mhat, 2 * n3));
   if (p->full_and_linear) A_(dev_alloc(&c->d_ql, 2 * n3));   // conservation partials: 8 chunks x 5 per cell
   A_(dev_alloc(&c->d_B, (size_t)2 * c->cap_cells * p->N * 4 * p->Nv * p->Nv));
 #undef A_
@@ -134,7 +144,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   cudaDeviceSynchronize();
   double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
-                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart, c->d_Gl, c->d_ql, c->d_CCt_lin};
+                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart, c->d_Gl, c->d_ql, c->d_CCt_lin, c->d_dirichlet, c->d_mhat};
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
@@ -222,6 +232,7 @@ int lpgpu_advect_apply(lpgpu_ctx *c, int stage)
 {
   LP_ENTER(c);
   LP_TRY(check_stage(c, stage));
+  LP_TRY(lp_launch_wall_halo(c, c->d_U[stage]));       // Doping: whatever the periodic exchange delivered at a domain wall is replaced
   LP_TRY(lp_launch_field_scan(c));
   return lp_launch_dg_stage(c, stage);
 }
@@ -263,6 +274,7 @@ static int eval_async(lpgpu_ctx *c, const double *f, double *q, int B)
 static int collide_async(lpgpu_ctx *c)
 {
   const int B = c->ncell;
+  if (c->p.linear_landau && !c->have_mhat) { lp_set_error("LinearLandau: call lpgpu_set_maxwellian after uploading the initial condition"); return LPGPU_EINVAL; }
   if (c->p.full_and_linear) {
     // RK4_FandL_Inhomo / _Homo (collisionRoutines_1.cpp:800-901, 987-1085): every stage spectrum is qHat + qHat_linear
     // after conserveAllMoments_FandL; both later stage vectors carry dt (:842, :858), unlike RK4_Inhomo's third
@@ -374,6 +386,16 @@ static int step_enqueue(lpgpu_ctx *c, int nsteps)
   return LPGPU_OK;
 }
 
+int lpgpu_set_maxwellian(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  if (!c->p.linear_landau) { lp_set_error("lpgpu_set_maxwellian: the context was not created with linear_landau = 1"); return LPGPU_EINVAL; }
+  LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, c->ncell));
+  LP_TRY(lp_launch_fft3d(c, c->d_f, true, c->d_mhat, c->ncell));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_mhat = true;
+  return LPGPU_OK;
+}
 int lpgpu_sample_device(lpgpu_ctx *c)
 {
   LP_ENTER(c);
@@ -555,7 +577,14 @@ int lpgpu_eleE_from_ms(const lpgpu_params *p, const double *ms, double *EleE)
   const double Lx = p->Lx, dx = Lx / Nx;
   double P = 0., acc = 0.;
   for (int q = 0; q < Nx; q++) { acc += P + 0.5 * ms[2 * q] - ms[2 * q + 1] / 12.; P += ms[2 * q]; }
-  const double ce = 0.5 * Lx - acc * dx * dx / Lx;
+  double ce = 0.5 * Lx - acc * dx * dx / Lx;
+  if (p->doping) {
+    // computeEleE calls the dispatching computePhi_x_0 (MomentCalculations.cpp:206): the Doping constant (FieldCalculations.cpp:427-450)
+    const int a_i = Nx / 3 - 1, b_i = 2 * Nx / 3 - 1;
+    const double a_val = (a_i + 1) * dx, b_val = (b_i + 1) * dx, Phi_Lx = 1, tmp = acc * dx * dx;
+    ce = Phi_Lx / Lx + 0.5 * p->NH * Lx / p->eps + (p->NL - p->NH) * (b_val - a_val) / p->eps
+         - (0.5 * (p->NL - p->NH) * (b_val * b_val - a_val * a_val) + tmp) / (Lx * p->eps);
+  }
   double t4 = 0., t5 = 0., t6 = 0.;
   P = 0.;
   for (int i = 0; i < Nx; i++) {

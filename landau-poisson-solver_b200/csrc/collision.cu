@@ -405,10 +405,12 @@ int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B)
   // 0 = fastest validated path (FFT convolutions when N is a power of two, else the tiled direct sum),
   // 1 = simple direct kernel, 2 = FFT convolutions, 3 = tiled direct sum
   const int variant = c->p.computeq_variant;
+  if (c->p.linear_landau && !c->have_mhat) { lp_set_error("LinearLandau: call lpgpu_set_maxwellian first"); return LPGPU_EINVAL; }
   if (variant == 0 || variant == 2) {
     int rc = lp_launch_computeQ_fftconv(c, fhat, q, B, false, nullptr);
     if (rc != -1) return rc;   // -1: N is not a power of two -> direct kernels
   }
+  if (c->p.linear_landau) { lp_set_error("LinearLandau needs the FFT-convolution pipeline"); return LPGPU_EINVAL; }
   if (variant != 1) {
     int rc = lp_launch_computeQ_tiled(c, fhat, q, B);
     if (rc != -1) return rc;   // -1: size not covered by the tiled kernel -> simple kernel

@@ -279,6 +279,15 @@ struct F1 {
     }
     for (int i = tid; i < N; i += NT) sE[i] = E[i];
   }
+  // the y slab of a stored spectrum (the Maxwellian of the linear operator) into FM[x][z]
+  static LP_HD void load_slab(int tid, int cell, int y, const double2 *spec, double2 *FM)
+  {
+    const double2 *src = spec + (long long)cell * N * N * N;
+    for (int idx = tid; idx < N * N; idx += NT) {
+      const int x = idx / N, z = idx % N;
+      FM[x * P + z] = src[((long long)x * N + y) * N + z];
+    }
+  }
   // stage the seven kernel-symbol slabs of this y into shared memory: Gs[a][z][x]
   static LP_HD void issue_g(int tid, int y, const double *Gt, double *Gs)
   {
@@ -290,9 +299,12 @@ struct F1 {
   }
   // Gs + a*astride + z*N + x: the slab of array a (shared: astride = N*N; straight from Gt + y*N*N: astride = N^3)
   // rounds [round_begin, round_end) of the five (two arrays each): a launch with few cells gives every round its own CTA
+  // FU: the slab the seven u arrays are built from -- FS itself for Q(f,f); the stored transform of the Maxwellian for
+  // the linear operator Q(f,M) (ComputeQLinear, collisionRoutines_1.cpp:1185-1269: first factor M, second factor f)
   static LP_HD void lines(int tid, int cell, int y, const double *Gs, long long astride, const double2 *FS, const double *sE, double2 *Z,
-                          int round_begin = 0, int round_end = 5)
+                          int round_begin = 0, int round_end = 5, const double2 *FU = nullptr)
   {
+    if (!FU) FU = FS;
     const int x = tid % N, r = (tid / N) % 3, slot = tid / (3 * N);
     #pragma unroll 1
     for (int round = round_begin; round < round_end; round++) {
@@ -303,7 +315,7 @@ struct F1 {
         #pragma unroll
         for (int l = 0; l < L; l++) {
           const double g0 = g[l * N], g1 = g[(l + L) * N];
-          const double2 f0 = FS[x * P + l], f1 = FS[x * P + l + L];
+          const double2 f0 = FU[x * P + l], f1 = FU[x * P + l + L];
           a0[l] = make_double2(g0 * f0.x, g0 * f0.y);
           a1[l] = make_double2(g1 * f1.x, g1 * f1.y);
         }

@@ -236,17 +236,22 @@ __global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ C
 // FUSED: `in` is the output of the first fft3D pass (lp_launch_fft3d_jk); the N lines along i of this y slab are
 // transformed here (one thread per line, as k_tf_i) and post-phased straight into the shared fhat slab -- fhat
 // itself never goes to memory.  The kernel symbols of this y are staged with cp.async while that happens.
+// mhat (nullable): LinearLandau -- the seven u arrays are built from the stored transform of the Maxwellian instead of
+// fhat (its y slab sits in a second shared array behind the symbols; the launcher sizes the dynamic shared memory)
 template <int L, bool FUSED>
 __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__restrict__ in, const double *__restrict__ Gt,
-                                                           const double *__restrict__ E, double2 *__restrict__ Z, const double2 *__restrict__ post)
+                                                           const double *__restrict__ E, double2 *__restrict__ Z, const double2 *__restrict__ post,
+                                                           const double2 *__restrict__ mhat)
 {
   typedef fc3::F1<L> K;
   constexpr int N = K::N;
   extern __shared__ double2 smf[];
   double2 *FS = smf;
   double *Gs = reinterpret_cast<double *>(FS + K::SMEM_C2), *sE = Gs + 7 * N * N;
+  double2 *FM = mhat ? reinterpret_cast<double2 *>(sE + N) : nullptr;
   const int y = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
   K::issue_g(tid, y, Gt, Gs);
+  if (mhat) K::load_slab(tid, cell, y, mhat, FM);
   if (FUSED) {
     // the N lines along i of this slab, four threads per line: thread (j, k) forms the decimated sequence
     // y_j[n] = (sum_s x[n + s N/4] (-i)^(j s)) w_N^(j n) and transforms it (N/4 points): X[4q + j]
@@ -293,8 +298,8 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
   }
   fc3::cp_wait_all();
   __syncthreads();
-  if (gridDim.z == 1) K::lines(tid, cell, y, Gs, N * N, FS, sE, Z);
-  else K::lines(tid, cell, y, Gs, N * N, FS, sE, Z, blockIdx.z, blockIdx.z + 1);     // few cells: one round per CTA
+  if (gridDim.z == 1) K::lines(tid, cell, y, Gs, N * N, FS, sE, Z, 0, 5, FM);
+  else K::lines(tid, cell, y, Gs, N * N, FS, sE, Z, blockIdx.z, blockIdx.z + 1, FM);     // few cells: one round per CTA
 }
 template <int L>
 __global__ void __launch_bounds__(fc3::F2<L>::NT, 1) k_fc3_f2(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C,
@@ -484,15 +489,16 @@ __global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__rest
   }
 }
 template <int L>
-int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb, bool fused_i, double *part)
+int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb, bool fused_i, double *part, const double2 *mhat)
 {
   typedef fc3::F2<L> K2;
   constexpr int N = 2 * L, M = 3 * L;
   const size_t smem2 = (size_t)(K2::IN_C2 + K2::Y_C2) * sizeof(double2) + N * sizeof(double);
-  const size_t smem1 = (size_t)fc3::F1<L>::SMEM_C2 * sizeof(double2) + (size_t)(7 * N * N + N) * sizeof(double);
+  const size_t smem1_max = (size_t)2 * fc3::F1<L>::SMEM_C2 * sizeof(double2) + (size_t)(7 * N * N + N) * sizeof(double);
+  const size_t smem1 = smem1_max - (mhat ? 0 : (size_t)fc3::F1<L>::SMEM_C2 * sizeof(double2));
   if (!c->fc3_attr) {
-    LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1_max));
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1_max));
     LP_CUDA(cudaFuncSetAttribute(k_fc3_f2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     if (L == 16) {
       LP_CUDA(cudaFuncSetAttribute(k_fc3_f2_tmem<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -504,8 +510,8 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   const double *E = c->d_Etab + LP_ETAB_PAD;
   const double2 *post = reinterpret_cast<const double2 *>(c->d_post_fwd);
   const dim3 g1(N, nb, nb * N * 2 <= 148 ? 5 : 1);
-  if (fused_i) k_fc3_f1<L, true><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
-  else k_fc3_f1<L, false><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post);
+  if (fused_i) k_fc3_f1<L, true><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post, mhat);
+  else k_fc3_f1<L, false><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post, mhat);
   LP_LAUNCHED(c);
   static const bool no_tmem = getenv("LPGPU_FC_NO_TMEM") != nullptr;   // developer knob: accumulators in registers, 1 CTA per SM
   const bool prof2 = c->prof_on == 2 && c->prof_used + 2 <= c->prof_ev.size();
@@ -604,8 +610,10 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     static const bool generic_only = getenv("LPGPU_FFT_GENERIC") != nullptr;   // developer knob: force the shared-memory stages
     if (!generic_only && (N == 32 || N == 24 || N == 16 || N == 8)) {
       double *pp = part ? part + (size_t)b0 * N * 5 : nullptr;
-      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb, fused_i, pp) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb, fused_i, pp)
-             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb, fused_i, pp) : launch_fc3<4>(c, fh, F1, F2, qo, nb, fused_i, pp);
+      // LinearLandau: cell b of this call pairs with cell b of the context's stored Maxwellian transforms
+      const double2 *mh = (c->p.linear_landau && c->have_mhat) ? reinterpret_cast<const double2 *>(c->d_mhat) + (size_t)b0 * c->N3 : nullptr;
+      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb, fused_i, pp, mh) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb, fused_i, pp, mh)
+             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb, fused_i, pp, mh) : launch_fc3<4>(c, fh, F1, F2, qo, nb, fused_i, pp, mh);
       if (rc != LPGPU_OK) return rc;
       continue;
     }

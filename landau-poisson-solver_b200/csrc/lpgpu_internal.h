@@ -26,6 +26,7 @@ struct LpTables {
   std::vector<double> node_xi;             // N
   std::vector<double> vc;                  // Nv  cell centres Gridv(j)
   std::vector<double> Etab;                // N + 2*LP_ETAB_PAD: eta[z] - eta[N/2] for z = -PAD .. N+PAD-1
+  std::vector<double> dirichlet;           // Doping: 2 x-planes (left, right wall) of DirichletBC coefficients, plane-major [wall][c][j]
 };
 void lp_build_tables(const lpgpu_params &p, LpTables &t);
 
@@ -53,6 +54,9 @@ struct lpgpu_ctx {
   double *d_q[4];                          // complex N^3: qHat, Q1_fft..Q3_fft
   double *d_lam;                           // 5 per cell
   double *d_Gl, *d_ql, *d_CCt_lin;          // FullandLinear: linear symbols, qHat_linear work array, 2x2 inverse
+  double *d_dirichlet;                     // Doping: the two wall planes (2 * 6 * sv)
+  double *d_mhat;                          // LinearLandau: DFTMaxwell, ncell * N^3 complex
+  bool have_mhat;
   double *d_cpart;                         // [cell][N][5] partial conservation dots written by the fused ComputeQ
   double *d_B;                             // projection intermediate: ncell*N*4*Nv^2 complex
   size_t cap_cells;        // capacity (in cells) of the collision work arrays
@@ -131,6 +135,8 @@ int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes);
 int lp_launch_field_scan(lpgpu_ctx *c);
 int lp_launch_dg_stage(lpgpu_ctx *c, int stage);
 int lp_launch_local_halo(lpgpu_ctx *c, double *planes);
+// Doping: Dirichlet wall planes into the halo planes that face a domain wall (no-op otherwise)
+int lp_launch_wall_halo(lpgpu_ctx *c, double *planes);
 int lp_launch_moments(lpgpu_ctx *c, const double *planes);
 int lp_launch_marginal_sums(lpgpu_ctx *c, const double *planes, double *out_dev);
 int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev);

@@ -135,6 +135,15 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
       t.CCt[i * 5 + j] = s;
     }
   invert_in_place(t.CCt, 5);
+  if (p.mass_cons_only) {
+    // createCCtAndPivot_OnlyMass / conserveMass_Normal (conservationRoutines.cpp:290-349): M = 1, one row C1_1 = C1_5[0],
+    // lambda_0 = (sum C1_1^2)^-1 sum Re(q) C1_1.  Stored as a 5 x 5 matrix whose other entries are zero, so every
+    // conservation kernel applies exactly that correction (the other four multipliers come out as +0).
+    double a = 0.;
+    for (int q = 0; q < N3; q++) a += t.C5[q] * t.C5[q];
+    for (int i = 0; i < 25; i++) t.CCt[i] = 0.;
+    t.CCt[0] = 1. / a;
+  }
   {
     // CCt_linear (conservationRoutines.cpp:222-238): mass and energy rows only
     double a = 0., b = 0., d = 0.;
@@ -217,4 +226,36 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
     t.node_cell[l] = j;
     t.node_xi[l] = (t.v[l] - t.vc[j]) / dv;
   }
+  if (p.doping && !p.homogeneous) {
+    // DirichletBC (advection_1.cpp:24-69): DG coefficients of ND * Maxwellian(T_B) on every velocity cell, ND = NH at both
+    // walls (DopingProfile(0), DopingProfile(Nx-1), FieldCalculations.cpp:413-425), T_B = T_L / T_R; 5-point Gauss rule
+    static const double GW[5] = {0.5688888888888889, 0.4786286704993665, 0.4786286704993665, 0.2369268850561891, 0.2369268850561891};
+    static const double GT[5] = {0., -0.5384693101056831, 0.5384693101056831, -0.9061798459386640, 0.9061798459386640};
+    const size_t sv = (size_t)Nv * Nv * Nv;
+    const int a_i = p.Nx / 3 - 1, b_i = 2 * p.Nx / 3 - 1;
+    t.dirichlet.assign(2 * 6 * sv, 0.);
+    for (int wall = 0; wall < 2; wall++) {
+      const int i = wall == 0 ? 0 : p.Nx - 1;
+      const double ND = (i <= a_i || i > b_i) ? p.NH : p.NL, T = wall == 0 ? p.T_L : p.T_R;
+      double *pl = t.dirichlet.data() + (size_t)wall * 6 * sv;
+      for (int j1 = 0; j1 < Nv; j1++) for (int j2 = 0; j2 < Nv; j2++) for (int j3 = 0; j3 < Nv; j3++) {
+        double m[5] = {0., 0., 0., 0., 0.};
+        for (int a = 0; a < 5; a++) for (int b = 0; b < 5; b++) for (int c = 0; c < 5; c++) {
+          const double v1 = t.vc[j1] + 0.5 * dv * GT[a], v2 = t.vc[j2] + 0.5 * dv * GT[b], v3 = t.vc[j3] + 0.5 * dv * GT[c];
+          const double r2 = v1 * v1 + v2 * v2 + v3 * v3;
+          const double tp = GW[a] * GW[b] * GW[c] * (std::exp(-r2 / (2 * T)) / (2 * M_PI * T * std::sqrt(2 * T * M_PI)));
+          m[0] += tp; m[1] += tp * 0.5 * GT[a]; m[2] += tp * 0.5 * GT[b]; m[3] += tp * 0.5 * GT[c];
+          m[4] += tp * 0.25 * (GT[a] * GT[a] + GT[b] * GT[b] + GT[c] * GT[c]);
+        }
+        for (int l = 0; l < 5; l++) m[l] = m[l] * 0.5 * 0.5 * 0.5;
+        const size_t j = ((size_t)j1 * Nv + j2) * Nv + j3;
+        const double tp0 = ND * m[0], tp5 = ND * m[4];
+        pl[0 * sv + j] = 19 * tp0 / 4. - 15 * tp5;
+        pl[5 * sv + j] = 60 * tp5 - 15 * tp0;
+        pl[1 * sv + j] = 0;
+        pl[2 * sv + j] = ND * m[1] * 12; pl[3 * sv + j] = ND * m[2] * 12; pl[4 * sv + j] = ND * m[3] * 12;
+      }
+    }
+  }
+
 }

@@ -4,8 +4,9 @@
 // time loop with every hot-path call going to the GPU, and writes Data/Moments_*.dc (one row per step,
 // row 1 = initial state; format LP_ompi.cpp:622-630, 836-844), Data/EntropyVals_*.dc (:632, :846) and the final Data/U_*.dc checkpoint
 // (raw doubles, LP_ompi.cpp:896).  `Second = True` restarts from the last U in Data/<Second/Name>
-// (LP_ompi.cpp:529-571).  Out-of-scope options (Doping, TwoHump, FullandLinear, LinearLandau,
-// MassConsOnly, gamma != -3) stop with an error, as the reference does for bad input (exit(1)).
+// (LP_ompi.cpp:529-571).  All five decks of the reference's test suite run (Damping / TwoStream / FourHump / Doping ICs,
+// Homogeneous, FullandLinear, LinearLandau, MassConsOnly); TwoHump and gamma != -3 stop with an error, as the
+// reference does for bad input (exit(1)).
 //
 // usage: lpsolver [input-file] [--device k] [--quiet]
 #include "../../include/lpgpu.h"
@@ -85,13 +86,13 @@ double twogauss(double a, double b, double c)
          / (2 * M_PI * s * s * sqrt(2 * M_PI * s * s));
 }
 // moments of a velocity profile over DG cell (j1,j2,j3) against {1, xi1, xi2, xi3, |xi|^2}
-void cell_moments(const Grid &g, bool two, const double sh[3], int j1, int j2, int j3, double t[5])
+void cell_moments(const Grid &g, bool two, const double sh[3], int j1, int j2, int j3, double t[5], double T = 0.4)
 {
   for (int l = 0; l < 5; l++) t[l] = 0.;
   for (int a = 0; a < 5; a++) for (int b = 0; b < 5; b++) for (int c = 0; c < 5; c++) {
     const double v1 = vcentre(g, j1) + 0.5 * g.dv * GT[a] + sh[0], v2 = vcentre(g, j2) + 0.5 * g.dv * GT[b] + sh[1],
                  v3 = vcentre(g, j3) + 0.5 * g.dv * GT[c] + sh[2];
-    const double w = GW[a] * GW[b] * GW[c] * (two ? twogauss(v1, v2, v3) : maxwell3(v1, v2, v3, 0.4));
+    const double w = GW[a] * GW[b] * GW[c] * (two ? twogauss(v1, v2, v3) : maxwell3(v1, v2, v3, T));
     t[0] += w; t[1] += w * 0.5 * GT[a]; t[2] += w * 0.5 * GT[b]; t[3] += w * 0.5 * GT[c];
     t[4] += w * 0.25 * (GT[a] * GT[a] + GT[b] * GT[b] + GT[c] * GT[c]);
   }
@@ -112,6 +113,25 @@ void ic_perturbed(const Grid &g, bool two, double A, double kw, std::vector<doub
       u[5] = 60 * tp5 - 15 * tp0;
       u[1] = (0.5 * (sin(kw * xp) + sin(kw * xm)) + (cos(kw * xp) - cos(kw * xm)) / (kw * g.dx)) * (A / kw) * t[0] * 12. / g.dx;
       u[2] = xf * t[1] * 12 / g.dx; u[3] = xf * t[2] * 12 / g.dx; u[4] = xf * t[3] * 12 / g.dx;
+    }
+  }
+}
+// DopingProfile (FieldCalculations.cpp:413-425) with a_i = Nx/3 - 1, b_i = 2Nx/3 - 1 (LP_ompi.cpp:160-161)
+double doping_profile(int Nx, int i, double NL, double NH) { return (i <= Nx / 3 - 1 || i > 2 * Nx / 3 - 1) ? NH : NL; }
+// SetInit_ND (SetInit_1.cpp:125-173): ND(x_i) times a Maxwellian of temperature T_R
+void ic_doping(const Grid &g, double NL, double NH, double T0, std::vector<double> &U)
+{
+  const double zero[3] = {0, 0, 0};
+  const int sv = g.Nv * g.Nv * g.Nv;
+  for (int j1 = 0; j1 < g.Nv; j1++) for (int j2 = 0; j2 < g.Nv; j2++) for (int j3 = 0; j3 < g.Nv; j3++) {
+    double t[5]; cell_moments(g, false, zero, j1, j2, j3, t, T0);
+    for (int i = 0; i < g.Nx; i++) {
+      double *u = &U[6 * ((size_t)i * sv + (j1 * g.Nv + j2) * g.Nv + j3)];
+      const double ND = doping_profile(g.Nx, i, NL, NH), tp0 = ND * t[0], tp5 = ND * t[4];
+      u[0] = 19 * tp0 / 4. - 15 * tp5;
+      u[5] = 60 * tp5 - 15 * tp0;
+      u[1] = 0;
+      u[2] = ND * t[1] * 12; u[3] = ND * t[2] * 12; u[4] = ND * t[3] * 12;
     }
   }
 }
@@ -174,9 +194,7 @@ int main(int argc, char **argv)
   if (nic == 0) die("No initial condition has been chosen.");
   if (nic > 1) die("Please ONLY set ONE of Damping, TwoStream, FourHump or TwoHump to true.");
   if (d.flag("First") == d.flag("Second")) die("Need to choose if this is a first run or a subsequent one (First / Second).");
-  for (const char *n : {"LinearLandau", "MassConsOnly"})
-    if (d.flag(n)) die(std::string(n) + " is not part of the GPU hot path.");
-  if (ic == "Doping" || ic == "TwoHump") die(ic + " initial/boundary conditions are not part of the GPU hot path.");
+  if (ic == "TwoHump") die("TwoHump initial conditions are not part of the GPU hot path.");
   if (!d.has("flag")) die("Please set the name of 'flag' in the input file.");
   for (const char *n : {"nT", "Nx", "Nv", "N", "nu", "dt"}) if (!d.has(n)) die(std::string("Please set ") + n + " in the input file.");
 
@@ -194,6 +212,14 @@ int main(int argc, char **argv)
   if (p.homogeneous && ic != "FourHump") die("Trying to run the space homogeneous code, but current IC is not available (only FourHump).");
   p.x_begin = 0; p.x_count = p.homogeneous ? 1 : p.Nx; p.device = device; p.computeq_variant = 0;
   p.full_and_linear = d.flag("FullandLinear");
+  p.linear_landau = d.flag("LinearLandau");
+  p.mass_cons_only = d.flag("MassConsOnly");
+  if (ic == "Doping") {                                              // ReadDopingParameters, InputParsing.cpp:512-570
+    for (const char *n : {"Doping/NL", "Doping/NH", "Doping/eps"}) if (!d.has(n)) die(std::string("Please set ") + n + " in the input file.");
+    p.doping = 1;
+    p.NL = d.num("Doping/NL", 0.); p.NH = d.num("Doping/NH", 0.); p.eps = d.num("Doping/eps", 1.);
+    p.T_L = d.num("Doping/T_L", 0.4); p.T_R = d.num("Doping/T_R", 0.4);
+  }
 
   char name[512], tail[400];
   const std::string flag = d.str("flag");
@@ -225,12 +251,14 @@ int main(int argc, char **argv)
     fseek(f, bytes - need, SEEK_SET);
     if (fread(U.data(), sizeof(double), U.size(), f) != U.size()) die("Error reading file");
     fclose(f);
-  } else if (ic == "FourHump") ic_four_hump(g, p.homogeneous, U);
+  } else if (ic == "Doping") ic_doping(g, p.NL, p.NH, p.T_R, U);
+  else if (ic == "FourHump") ic_four_hump(g, p.homogeneous, U);
   else ic_perturbed(g, ic == "TwoStream", A_amp, k_wave, U);
 
   lpgpu_ctx *ctx = nullptr;
   CHECK(lpgpu_init(&p, &ctx));
   CHECK(lpgpu_upload_U(ctx, U.data()));
+  if (p.linear_landau && p.nu > 0.) CHECK(lpgpu_set_maxwellian(ctx));   // ComputeDFTofMaxwellian(U, f, DFTMaxwell), LP_ompi.cpp:516, :541
   make_parent_dir(fmom_name);
   FILE *fmom = fopen(fmom_name.c_str(), "w");
   if (!fmom) die("cannot open " + fmom_name);
@@ -310,6 +338,26 @@ int main(int argc, char **argv)
     double P = 0., acc = 0.;
     std::vector<double> Pq(p.Nx), Sq(p.Nx);                           // P_q = sum_{q' < q} m_q',  S_q = sum_{q' < q} (P_q' + m_q'/2 - s_q'/12)
     for (int q = 0; q < p.Nx; q++) { Pq[q] = P; Sq[q] = acc; acc += P + 0.5 * ms[2 * q] - ms[2 * q + 1] / 12.; P += ms[2 * q]; }
+    if (p.doping) {
+      // PrintFieldData_Doping (FieldCalculations.cpp:562-583): phi and E at 4 points per cell; computePhi_Doping (:452-522),
+      // computeE_Doping (:524-560) and computePhi_x_0_Doping (:427-450) in terms of the same per-cell sums
+      const int a_i = p.Nx / 3 - 1, b_i = 2 * p.Nx / 3 - 1;
+      const double a_val = (a_i + 1) * dx, b_val = (b_i + 1) * dx, NL = p.NL, NH = p.NH, eps = p.eps;
+      const double ce = 1. / p.Lx + 0.5 * NH * p.Lx / eps + (NL - NH) * (b_val - a_val) / eps
+                        - (0.5 * (NL - NH) * (b_val * b_val - a_val * a_val) + acc * dx * dx) / (p.Lx * eps);
+      for (int i = 0; i < p.Nx; i++) for (int nx = 0; nx < np; nx++) {
+        const double x = gridx(i - 0.5) + nx * ddx, xd = x - gridx(i - 0.5), xm = x - gridx(i), ND = doping_profile(p.Nx, i, NL, NH);
+        const double xe = xm * xm * xm / (6. * dx) - dx * xm / 8. - dx * dx / 24., xev = xm * xm / (2. * dx) - dx / 8.;
+        double phi = Sq[i] * dx * dx + Pq[i] * dx * xd + ms[2 * i] * xd * xd / 2. + ms[2 * i + 1] * xe - ND * x * x / 2.;
+        double E = ND * x - (ms[2 * i] * xd + ms[2 * i + 1] * xev + Pq[i] * dx);
+        if (i > a_i) { phi -= (NH - NL) * a_val * (x - 0.5 * a_val); E += (NH - NL) * a_val; }
+        if (i > b_i) { phi -= (NL - NH) * b_val * (x - 0.5 * b_val); E += (NL - NH) * b_val; }
+        fprintf(fphi, "%11.8g ", phi / eps + ce * x);
+        fprintf(fE, "%11.8g ", E / eps - ce);
+      }
+      fprintf(fphi, "\n"); fprintf(fE, "\n");
+      return;
+    }
     const double ce = 0.5 * p.Lx - acc * dx * dx / p.Lx;
     for (int i = 0; i < p.Nx; i++) for (int nx = 0; nx < np; nx++) {
       const double x = gridx(i - 0.5) + nx * ddx, xd = x - gridx(i - 0.5), xm = x - gridx(i);

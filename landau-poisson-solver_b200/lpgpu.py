@@ -23,7 +23,9 @@ class Params(C.Structure):
                 ("Lv", C.c_double), ("Lx", C.c_double), ("nu", C.c_double), ("dt", C.c_double),
                 ("gamma", C.c_int), ("homogeneous", C.c_int),
                 ("x_begin", C.c_int), ("x_count", C.c_int), ("device", C.c_int),
-                ("computeq_variant", C.c_int), ("full_and_linear", C.c_int)]
+                ("computeq_variant", C.c_int), ("full_and_linear", C.c_int),
+                ("doping", C.c_int), ("NL", C.c_double), ("NH", C.c_double), ("eps", C.c_double),
+                ("T_L", C.c_double), ("T_R", C.c_double), ("linear_landau", C.c_int), ("mass_cons_only", C.c_int)]
 
 
 class Exchange(C.Structure):
@@ -38,7 +40,7 @@ class Exchange(C.Structure):
 EXPORTS = [
     "lpgpu_last_error", "lpgpu_device_count", "lpgpu_init", "lpgpu_finalize", "lpgpu_set_stream",
     "lpgpu_synchronize", "lpgpu_launch_count", "lpgpu_upload_U", "lpgpu_download_U",
-    "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_step_async",
+    "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_step_async", "lpgpu_set_maxwellian",
     "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_step", "lpgpu_advect_exchange_info",
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
@@ -63,7 +65,7 @@ def load_library():
     L.lpgpu_launch_count.restype = C.c_longlong
     L.lpgpu_launch_count.argtypes = [C.c_void_p]
     L.lpgpu_init.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
-    for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_sample_device"):
+    for name in ("lpgpu_finalize", "lpgpu_synchronize", "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_sample_device", "lpgpu_set_maxwellian"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.lpgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     for name in ("lpgpu_upload_U", "lpgpu_download_U", "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_setInit_spectral", "lpgpu_field", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums"):
@@ -107,12 +109,16 @@ class LPGpu:
     function names (RK3 -> advect_rk3, ComputeQ, conserveMoments, FS, fft3D, setInit_spectral)."""
 
     def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, gamma=-3, x_begin=0, x_count=None,
-                 device=0, computeq_variant=0, full_and_linear=False):
+                 device=0, computeq_variant=0, full_and_linear=False, doping=None, linear_landau=False, mass_cons_only=False):
+        """doping: None or a dict(NL=, NH=, eps=, T_L=, T_R=) -- the [Doping] section of the input deck."""
         self.L = load_library()
         if x_count is None:
             x_count = 1 if homogeneous else Nx
+        dp = doping or {}
         self.params = Params(Nx, Nv, N, Lv, Lx, nu, dt, gamma, int(bool(homogeneous)), x_begin, x_count, device,
-                             computeq_variant, int(bool(full_and_linear)))
+                             computeq_variant, int(bool(full_and_linear)), int(doping is not None),
+                             float(dp.get("NL", 0.)), float(dp.get("NH", 0.)), float(dp.get("eps", 1.)),
+                             float(dp.get("T_L", 0.4)), float(dp.get("T_R", 0.4)), int(bool(linear_landau)), int(bool(mass_cons_only)))
         self.Nx, self.Nv, self.N = Nx, Nv, N
         self.homogeneous = bool(homogeneous)
         self.ncell = 1 if homogeneous else x_count
@@ -158,6 +164,10 @@ class LPGpu:
         assert wait or out is not None, "an enqueue-only download needs the caller's page-locked buffer"
         self._check((self.L.lpgpu_download_U if wait else self.L.lpgpu_download_U_async)(self.h, _ptr(U)))
         return U
+
+    def set_maxwellian(self):
+        """ComputeDFTofMaxwellian: the state now on the device becomes M of the linear operator Q(f, M)."""
+        self._check(self.L.lpgpu_set_maxwellian(self.h))
 
     # -- phases
     def advect_rk3(self):

@@ -72,11 +72,21 @@ class RunConfig:
         self.second_name = kv.get("Second/Name")
         self.homogeneous = _bool(kv, "Homogeneous")
         self.full_and_linear = _bool(kv, "FullandLinear")
-        for unsupported in ("LinearLandau", "MassConsOnly"):
-            if _bool(kv, unsupported):
-                raise NotImplementedError("%s is outside the GPU hot path (SURVEY.md section 8f.4)" % unsupported)
-        if self.ic in ("Doping", "TwoHump"):
-            raise NotImplementedError("%s initial/boundary conditions are outside the GPU hot path" % self.ic)
+        self.linear_landau = _bool(kv, "LinearLandau")
+        self.mass_cons_only = _bool(kv, "MassConsOnly")
+        if self.ic == "TwoHump":
+            raise NotImplementedError("TwoHump initial conditions are outside the GPU hot path")
+        if self.gamma != -3:
+            raise NotImplementedError("only the Landau kernel gamma = -3 is implemented")
+        self.doping = None
+        if self.ic == "Doping":                      # ReadDopingParameters (InputParsing.cpp:512-570)
+            if self.homogeneous:
+                raise ValueError("Doping needs an inhomogeneous run")
+            for k in ("NL", "NH", "eps"):
+                if "Doping/" + k not in kv:
+                    raise ValueError("Please set Doping/%s in the input file" % k)
+            self.doping = dict(NL=float(kv["Doping/NL"]), NH=float(kv["Doping/NH"]), eps=float(kv["Doping/eps"]),
+                               T_L=float(kv.get("Doping/T_L", 0.4)), T_R=float(kv.get("Doping/T_R", 0.4)))
         sec = self.ic
         self.A_amp = float(kv.get(sec + "/A_amp", 0.))
         self.k_wave = float(kv.get(sec + "/k_wave", 0.5))
@@ -107,6 +117,8 @@ class RunConfig:
             return set_init_4h_homo(self.Nv, self.Lv)
         if self.ic in ("Damping", "TwoStream"):
             return set_init_ld(self.Nx, self.Nv, self.Lv, self.Lx, self.A_amp, self.k_wave, self.ic == "TwoStream", x_begin, x_count)
+        if self.ic == "Doping":
+            return set_init_nd(self.Nx, self.Nv, self.Lv, self.doping["NL"], self.doping["NH"], self.doping["T_R"], x_begin, x_count)
         return set_init_4h(self.Nx, self.Nv, self.Lv, self.Lx, x_begin, x_count)
 
 
@@ -173,6 +185,29 @@ def set_init_ld(Nx, Nv, Lv, Lx, A_amp, k_wave, twostream=False, x_begin=0, x_cou
     U[..., 2] = X * t1[None] * 12 / dx
     U[..., 3] = X * t2[None] * 12 / dx
     U[..., 4] = X * t3[None] * 12 / dx
+    return U.reshape(-1)
+
+
+def doping_profile(Nx, NL, NH):
+    """DopingProfile (FieldCalculations.cpp:413-425; a_i, b_i from LP_ompi.cpp:160-161): NH in the outer thirds, NL between."""
+    i = np.arange(Nx)
+    a_i, b_i = Nx // 3 - 1, 2 * Nx // 3 - 1
+    return np.where((i <= a_i) | (i > b_i), NH, NL).astype(np.float64)
+
+
+def set_init_nd(Nx, Nv, Lv, NL, NH, T0, x_begin=0, x_count=None):
+    """SetInit_ND (SetInit_1.cpp:125-173): ND(x_i) times a Maxwellian of temperature T0 = T_R, L2-projected on the DG basis."""
+    x_count = Nx if x_count is None else x_count
+    t0, t1, t2, t3, t4 = _velocity_cell_moments(Nv, Lv, lambda a, b, c: _maxwellian(a, b, c, T0))
+    ND = doping_profile(Nx, NL, NH)[x_begin:x_begin + x_count][:, None, None, None]
+    U = np.empty((x_count, Nv, Nv, Nv, 6))
+    tp0, tp5 = ND * t0[None], ND * t4[None]
+    U[..., 0] = 19 * tp0 / 4. - 15 * tp5
+    U[..., 5] = 60 * tp5 - 15 * tp0
+    U[..., 1] = 0.
+    U[..., 2] = ND * t1[None] * 12
+    U[..., 3] = ND * t2[None] * 12
+    U[..., 4] = ND * t3[None] * 12
     return U.reshape(-1)
 
 
@@ -256,7 +291,7 @@ class ShardedSolver:
     """One rank of the x-sharded solver.  world == 1 needs no process group."""
 
     def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None, full_and_linear=False,
-                 stream=None):
+                 stream=None, doping=None, linear_landau=False, mass_cons_only=False):
         """stream: a torch.cuda.Stream all work of this solver (kernels, copies, the NCCL exchange) is ordered on;
         None = torch's current stream for sharded runs, the library's default otherwise.  Two solvers on two streams
         pipeline: the host<->device copies of one overlap the kernels of the other."""
@@ -268,7 +303,9 @@ class ShardedSolver:
         else:
             self.x_begin, self.x_count = shard_range(Nx, world, rank)
         self.g = lpgpu.LPGpu(Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=homogeneous, x_begin=self.x_begin,
-                             x_count=self.x_count, device=device, full_and_linear=full_and_linear)
+                             x_count=self.x_count, device=device, full_and_linear=full_and_linear, doping=doping,
+                             linear_landau=linear_landau, mass_cons_only=mass_cons_only)
+        self.linear_landau = bool(linear_landau)
         self.nu = nu
         self._ex = None
         if stream is not None:
@@ -289,6 +326,10 @@ class ShardedSolver:
 
     def upload(self, U_shard, wait=True):
         self.g.upload_U(U_shard, wait=wait)
+
+    def set_maxwellian(self):
+        """LinearLandau: the state now on the device becomes M of Q(f, M) (ComputeDFTofMaxwellian, LP_ompi.cpp:516)."""
+        self.g.set_maxwellian()
 
     def download(self, out=None, wait=True):
         return self.g.download_U(out, wait=wait)
@@ -348,8 +389,11 @@ def run_from_input_file(path="LPsolver-input.txt", outdir=".", device=0, quiet=F
     LPsolver-input.txt: writes Data/Moments_*.dc with one row per step (row 1 = initial state)."""
     cfg = RunConfig.from_file(path)
     s = ShardedSolver(cfg.Nx, cfg.Nv, cfg.N, cfg.Lv, cfg.Lx, cfg.nu, cfg.dt, homogeneous=cfg.homogeneous, device=device,
-                      full_and_linear=cfg.full_and_linear)
+                      full_and_linear=cfg.full_and_linear, doping=cfg.doping, linear_landau=cfg.linear_landau,
+                      mass_cons_only=cfg.mass_cons_only)
     s.upload(cfg.initial_condition())
+    if cfg.linear_landau and cfg.nu > 0:
+        s.set_maxwellian()
     out = os.path.join(outdir, cfg.moments_filename())
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as fh:

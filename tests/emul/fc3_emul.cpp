@@ -7,8 +7,9 @@
 #include <vector>
 #include "../../landau-poisson-solver_b200/csrc/fc3.cuh"
 
+// mhat (nullable): the linear operator Q(f, M) -- the u arrays come from the stored Maxwellian transform
 template <int L>
-static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit)
+static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr)
 {
   using namespace fc3;
   constexpr int N = 2 * L, M = 3 * L;
@@ -21,13 +22,14 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
   std::vector<double2> Z((size_t)B * 10 * M * N * N), C((size_t)nsplit * split_stride);
   {
     typedef F1<L> K;
-    std::vector<double2> FS(K::SMEM_C2);
+    std::vector<double2> FS(K::SMEM_C2), FM(K::SMEM_C2);
     std::vector<double> sE(N), Gs((size_t)7 * N * N);
     for (int cell = 0; cell < B; cell++)
       for (int y = 0; y < N; y++) {
         for (int t = 0; t < K::NT; t++) K::issue_g(t, y, Gt.data(), Gs.data());
         for (int t = 0; t < K::NT; t++) K::load(t, cell, y, fhat, E, FS.data(), sE.data());
-        for (int t = 0; t < K::NT; t++) K::lines(t, cell, y, Gs.data(), N * N, FS.data(), sE.data(), Z.data());
+        if (mhat) for (int t = 0; t < K::NT; t++) K::load_slab(t, cell, y, mhat, FM.data());
+        for (int t = 0; t < K::NT; t++) K::lines(t, cell, y, Gs.data(), N * N, FS.data(), sE.data(), Z.data(), 0, 5, mhat ? FM.data() : nullptr);
       }
   }
   {
@@ -81,16 +83,33 @@ extern "C" int fc3_emulate_split(int N, int B, const double *fhat, const double 
   return 1;
 }
 
+extern "C" int fc3_emulate_linear(int N, int B, const double *fhat, const double *mhat, const double *G7, const double *E, double *q)
+{
+  const double2 *f = reinterpret_cast<const double2 *>(fhat), *m = reinterpret_cast<const double2 *>(mhat);
+  double2 *o = reinterpret_cast<double2 *>(q);
+  switch (N) {
+    case 8: emulate<4>(B, f, G7, E, o, 1, m); return 0;
+    case 16: emulate<8>(B, f, G7, E, o, 1, m); return 0;
+    case 24: emulate<12>(B, f, G7, E, o, 1, m); return 0;
+    case 32: emulate<16>(B, f, G7, E, o, 1, m); return 0;
+  }
+  return 1;
+}
+
 extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
 {
   return fc3_emulate_split(N, B, fhat, G7, E, q, 1);
 }
 
-extern "C" int fc3_direct(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+static int direct_sum(int N, int B, const double *fhat, const double *mhat, const double *G7, const double *E, double *q);
+extern "C" int fc3_direct(int N, int B, const double *fhat, const double *G7, const double *E, double *q) { return direct_sum(N, B, fhat, fhat, G7, E, q); }
+// ComputeQLinear's pair sum (collisionRoutines_1.cpp:1259-1260): first factor from the Maxwellian, second from f
+extern "C" int fc3_direct_linear(int N, int B, const double *fhat, const double *mhat, const double *G7, const double *E, double *q) { return direct_sum(N, B, fhat, mhat, G7, E, q); }
+static int direct_sum(int N, int B, const double *fhat, const double *mhat, const double *G7, const double *E, double *q)
 {
   const int H = N / 2, N3 = N * N * N;
   for (int cell = 0; cell < B; cell++) {
-    const double *fh = fhat + (size_t)2 * N3 * cell;
+    const double *fh = fhat + (size_t)2 * N3 * cell, *mh = mhat + (size_t)2 * N3 * cell;
     #pragma omp parallel for collapse(2)
     for (int i = 0; i < N; i++)
       for (int j = 0; j < N; j++)
@@ -106,7 +125,7 @@ extern "C" int fc3_direct(int N, int B, const double *fhat, const double *G7, co
                 const double *g = G7 + 7 * w;
                 const double e1 = E[x], e2 = E[y], e3 = E[z];
                 const double W = g[0] - (g[1] * e1 * e1 + g[2] * e2 * e2 + g[3] * e3 * e3 + g[4] * e1 * e2 + g[5] * e1 * e3 + g[6] * e2 * e3);
-                const double ar = fh[2 * w], ai = fh[2 * w + 1], br = fh[2 * b], bi = fh[2 * b + 1];
+                const double ar = mh[2 * w], ai = mh[2 * w + 1], br = fh[2 * b], bi = fh[2 * b + 1];
                 t0 += W * (ar * br - ai * bi);
                 t1 += W * (ar * bi + ai * br);
               }

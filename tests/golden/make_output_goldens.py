@@ -1,5 +1,5 @@
 """Generate tests/golden/ref_outputs.npz: the Marginals / PhiVals / FieldVals / EntropyVals files the UNMODIFIED
-reference writes for its own test0 and test4 decks (oracle/_ref/solver, built from /root/reference by
+reference writes for its own test0, test4 and test1 decks (oracle/_ref/solver, built from /root/reference by
 oracle/Makefile).  Run in the build container; the GPU box only reads the committed .npz.
 
     python tests/golden/make_output_goldens.py
@@ -22,7 +22,7 @@ def rows(path):
 
 
 out = {}
-for case in ("test0", "test4"):
+for case in ("test0", "test4", "test1"):
     with tempfile.TemporaryDirectory() as tmp:
         shutil.copy(os.path.join(HERE, "LPsolver-input-%s.txt" % case), os.path.join(tmp, "LPsolver-input.txt"))
         subprocess.run([SOLVER], cwd=tmp, check=True, capture_output=True)

@@ -50,6 +50,23 @@ def test_product_split_over_three_ctas(emul):
     assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("N,B", [(8, 2), (16, 1)])
+def test_linear_operator_pipeline_matches_direct_sum(emul, N, B):
+    """LinearLandau: Q(f, M) -- F1 builds the seven u arrays from the stored Maxwellian transform, the v arrays from
+    fhat (ComputeQLinear, collisionRoutines_1.cpp:1185-1269)."""
+    rng = np.random.default_rng(100 + N)
+    fh = rng.standard_normal((B, N ** 3, 2))
+    mh = rng.standard_normal((B, N ** 3, 2))
+    G = rng.standard_normal((N ** 3, 7))
+    E = (np.arange(N) - N / 2) * 0.37
+    got, want = np.zeros_like(fh), np.zeros_like(fh)
+    assert emul.fc3_emulate_linear(N, B, fh.ctypes.data_as(P), mh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), got.ctypes.data_as(P)) == 0
+    assert emul.fc3_direct_linear(N, B, fh.ctypes.data_as(P), mh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), want.ctypes.data_as(P)) == 0
+    assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
+    assert emul.fc3_direct(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), got.ctypes.data_as(P)) == 0
+    assert np.abs(got - want).max() > 1e-3 * np.abs(want).max()        # and it is a different operator
+
+
 def test_unsupported_size_is_refused(emul):
     z = np.zeros(8)
     assert emul.fc3_emulate(10, 1, z.ctypes.data_as(P), z.ctypes.data_as(P), z.ctypes.data_as(P), z.ctypes.data_as(P)) == 1

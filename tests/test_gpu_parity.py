@@ -380,12 +380,15 @@ def test_ComputeQ_checksums_full_size(pkg, N):
     assert float(np.sum(q[:, 1] ** 2)) < 1e-20               # symmetric IC -> real spectrum
 
 
-def test_sharded_advection_matches_single(pkg):
+@pytest.mark.parametrize("doping", [None, dict(NL=0.001, NH=1., eps=0.1, T_L=0.4, T_R=0.5)])
+def test_sharded_advection_matches_single(pkg, doping):
     """Two contexts on one GPU, each owning half of x, exchanging halos and (m_i,s_i) by hand:
-    the sharded stage API must reproduce the single-context RK3 exactly."""
+    the sharded stage API must reproduce the single-context RK3 exactly.  With Doping the planes the periodic
+    exchange delivers at the two domain walls are replaced by the Dirichlet planes inside lpgpu_advect_apply."""
     import ctypes as C
     cfg = dict(SMALL)
     ora = PortOracle(**cfg)
+    cfg["doping"] = doping
     U = _perturbed(ora, 5)
     sv6 = 6 * cfg["Nv"] ** 3
     half = cfg["Nx"] // 2
@@ -422,6 +425,116 @@ def test_sharded_advection_matches_single(pkg):
     for s in shards:
         s.close()
     assert np.array_equal(got, want)
+
+
+TEST1_DOPING = dict(NL=0.001, NH=1., eps=0.1, T_L=0.4, T_R=0.4)      # [Doping] section of LPsolver-input-test1.txt
+
+
+def test_doping_field_RK3_and_moments(pkg):
+    """Doping = True: *_Doping field integrals, Dirichlet walls in I3, EleE with the Doping constant -- against the
+    oracle (pinned to the unmodified reference by Moments_Test1.dc and ref_test1.npz)."""
+    dp = dict(NL=0.01, NH=1., eps=0.2, T_L=0.35, T_R=0.5)       # distinct wall temperatures: both Dirichlet planes matter
+    ora = PortOracle(**SMALL)
+    ora.set_doping(**dp)
+    g = pkg.LPGpu(doping=dp, **SMALL)
+    U = ora.SetInit_ND()
+    rng = np.random.default_rng(11)
+    U = U * (1 + 0.05 * rng.standard_normal(U.shape)) + 1e-4 * rng.standard_normal(U.shape)
+    g.upload_U(U)
+    want_f, got_f = ora.field(U), g.field()
+    assert np.max(np.abs(got_f - want_f)) < 1e-12 * np.max(np.abs(want_f))
+    assert relerr(g.moments(), ora.moments(U)) < 1e-12
+    g.advect_rk3()
+    got, want = g.download_U(), ora.RK3(U)
+    assert relerr(got, want) < TOL_U
+    assert relerr(got - U, want - U) < TOL_DU
+    plain = PortOracle(**SMALL).RK3(U)
+    assert relerr(plain - U, want - U) > 1e-3                     # and the walls / doping terms are visible
+    g.close()
+
+
+@pytest.mark.parametrize("N", [8, 16])
+def test_linear_landau_and_mass_only_operators(pkg, N):
+    """LinearLandau: ComputeQ evaluates Q(f, M) (ComputeQLinear) with M captured by lpgpu_set_maxwellian;
+    MassConsOnly: conserveMoments is conserveMass_Normal.  Then a whole collision step (RK4Linear)."""
+    cfg = dict(SMALL, N=N)
+    ora = PortOracle(**cfg)
+    U0 = _perturbed(ora, 3)
+    ora.set_linear_landau(U0)
+    ora.set_mass_cons_only(True)
+    g = pkg.LPGpu(linear_landau=True, mass_cons_only=True, **cfg)
+    g.upload_U(U0)
+    with pytest.raises(pkg.lpgpu.LPGpuError):
+        g.collide_step()                                           # no Maxwellian captured yet
+    g.set_maxwellian()
+    U = _perturbed(ora, 4)                                         # the state has moved on from the Maxwellian
+    f = ora.setInit_spectral(U)
+    mh = np.stack([ora.fft3D(np.stack([x, 0 * x], 1)) for x in ora.setInit_spectral(U0)])
+    B = 2
+    got = g.ComputeQ(f[:B])
+    for b in range(B):
+        assert relerr(got[b], ora.ComputeQLinear(f[b], mh[b])) < TOL_SPEC
+    qc = g.conserveMoments(got[0])[0]
+    want_c = ora.conserveMoments(got[0])
+    assert relerr(qc, want_c) < TOL_SPEC
+    C5, _ = ora.conservation()
+    assert abs(np.dot(qc[:, 0], C5[0])) < 1e-12 * np.abs(got[0]).max() * np.abs(C5[0]).sum()     # mass row annihilated
+    assert relerr(qc[:, 1], got[0][:, 1]) == 0.                                                    # nothing else touched
+    g.upload_U(U)
+    g.collide_step()
+    gu, wu = g.download_U(), ora.collide_step(U)
+    assert relerr(gu, wu) < TOL_U
+    assert relerr(gu - U, wu - U) < TOL_DU
+    g.close()
+
+
+def test_linear_operator_reduces_to_quadratic_at_full_size(pkg):
+    """N = 32 (no oracle at this size in seconds): Q(f, M) with M = f must equal Q(f, f) from the same pipeline, and the
+    operator is linear in f for fixed M."""
+    cfg = dict(Nx=2, Nv=32, N=32, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
+    from lpsolver_b200 import solver
+    U = solver.set_init_ld(2, 32, 5.25, 4.0, 0.5, np.pi / 2, True)
+    gq = pkg.LPGpu(**cfg)
+    gq.upload_U(U)
+    f = gq.setInit_spectral()
+    qq = gq.ComputeQ(f)
+    gq.close()
+    gl = pkg.LPGpu(linear_landau=True, **cfg)
+    gl.upload_U(U)
+    gl.set_maxwellian()
+    ql = gl.ComputeQ(f)
+    assert relerr(ql, qq) < 1e-13
+    f2 = f * (1 + 0.1 * np.sin(np.arange(f.shape[1]))[None, :])
+    a, b = gl.ComputeQ(f2), gl.ComputeQ(3. * f2 - 2. * f)
+    assert relerr(b, 3. * a - 2. * ql) < 1e-12
+    gl.close()
+
+
+def test_reference_test1_five_steps_against_the_unmodified_reference(pkg):
+    """tests/LPsolver-input-test1.txt (Doping, LinearLandau, MassConsOnly) through the Python mirror: the final state
+    against the U the unmodified reference dumps (tests/golden/ref_test1.npz) and its Moments rows."""
+    import os
+    from lpsolver_b200 import solver
+    here = os.path.dirname(__file__)
+    z = np.load(os.path.join(here, "golden", "ref_test1.npz"))
+    c1 = solver.RunConfig.from_file(os.path.join(here, "golden", "LPsolver-input-test1.txt"))
+    s = solver.ShardedSolver(c1.Nx, c1.Nv, c1.N, c1.Lv, c1.Lx, c1.nu, c1.dt, doping=c1.doping, linear_landau=True, mass_cons_only=True)
+    U0 = c1.initial_condition()
+    s.upload(U0)
+    s.set_maxwellian()
+    for step in range(6):
+        m = s.moments()
+        row = [m[0], m[1], m[2], m[3], m[4], m[5], np.sqrt(m[5]), np.log(np.sqrt(m[5])), m[4] + m[5]]
+        for col in (0, 1, 4, 5, 6, 7, 8):
+            assert abs(row[col] - z["moments"][step][col]) <= 6e-8 * max(1.0, abs(z["moments"][step][col])), (step, col)
+        if step < 5:
+            s.step(1)
+    U = s.download()
+    s.close()
+    st = int(z["stride"])
+    assert relerr(U[::st], z["U_sample"]) < 1e-11
+    assert relerr((U - U0)[::st], z["U_sample"] - U0[::st]) < 1e-9
+    assert abs(U.sum() - float(z["U_sum"])) < 1e-10 * float(z["U_abs_sum"])
 
 
 def test_against_committed_reference_vectors(pkg):
@@ -466,7 +579,7 @@ def test_against_committed_reference_vectors(pkg):
     gh.close()
 
 
-@pytest.mark.parametrize("case,homog", [("test0", False), ("test4", True), ("test3", False)])
+@pytest.mark.parametrize("case,homog", [("test0", False), ("test4", True), ("test3", False), ("test1", False)])
 def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
     """The reference's own end-to-end test (tests/LPsolver_tests + moment_differ.sh): run the driver in a
     directory holding LPsolver-input.txt and compare row 6 of the Moments file it writes with the golden."""
@@ -480,6 +593,7 @@ def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     name = {"test0": "Data/Moments_nu0.05A0.2k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test0.dc",
             "test3": "Data/Moments_nu0.05A0.2k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test3.dc",
+            "test1": "Data/Moments_nu0.05A0k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test1.dc",
             "test4": "Data/Moments_nu0.05A0k0.5Nv16Lv5.25SpectralN8dt0.01nT5_Test4.dc"}[case]
     rows = [[float(x) for x in line.split()] for line in open(tmp_path / name) if line.strip()]
     gold = json.load(open(os.path.join(here, "golden", "reference_moments.json")))["Moments_T%s.dc" % case[1:]]
@@ -488,9 +602,9 @@ def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
     assert abs(r[0] - g[0]) <= 2e-6                                      # moment_differ.sh:9,30
     assert all(abs(r[d] - g[d]) <= 1e-10 for d in (1, 2, 3))              # :10-12
     last = len(g) - 1
-    assert r[last] - g[last] <= 3e-5 and g[last] - r[last] <= 1e-7        # :13,83 (golden holds 8 digits)
+    assert r[last] - g[last] <= 3e-5 and g[last] - r[last] <= (1e-7 if g[last] < 10 else 1e-6)   # :13,83 (golden holds 8 digits)
     for row, grow in zip(rows, gold):                                     # every printed digit of the non-noise columns
-        for col in ([0, 4, 5, 6, 7, 8] if not homog else [0, 7]):
+        for col in ([0, 7] if homog else [0, 1, 4, 5, 6, 7, 8] if case == "test1" else [0, 4, 5, 6, 7, 8]):   # test 1: the walls make P1 a signal
             assert abs(row[col] - grow[col]) <= 1.5e-7 * max(1.0, abs(grow[col])), (row, grow, col)
     assert os.path.exists(tmp_path / name.replace("Moments_", "U_"))
     # the other per-run files (LP_ompi.cpp:448-470, :632, :648-655, :846, :868-875) against what the unmodified reference

@@ -58,11 +58,30 @@ def test_input_file_and_output_names(pkg):
 
 def test_unsupported_options_fail_loudly(pkg, tmp_path):
     from lpsolver_b200 import solver
-    txt = open(os.path.join(GOLD, "LPsolver-input-test0.txt")).read().replace("LinearLandau     = False", "LinearLandau     = True")
+    txt = open(os.path.join(GOLD, "LPsolver-input-test0.txt")).read().replace("Damping          = True", "Damping          = False").replace(
+        "TwoHump          = False", "TwoHump          = True")
     p = tmp_path / "in.txt"
     p.write_text(txt)
     with pytest.raises(NotImplementedError):
         solver.RunConfig.from_file(str(p))
+    p.write_text("gamma = 0\n" + open(os.path.join(GOLD, "LPsolver-input-test0.txt")).read())
+    with pytest.raises(NotImplementedError):
+        solver.RunConfig.from_file(str(p))
+
+
+def test_reference_test1_deck_is_parsed(pkg):
+    """Doping + LinearLandau + MassConsOnly (tests/LPsolver-input-test1.txt): flags, [Doping] section, file name,
+    and SetInit_ND against the oracle."""
+    from lpsolver_b200 import solver
+    c1 = solver.RunConfig.from_file(os.path.join(GOLD, "LPsolver-input-test1.txt"))
+    assert c1.ic == "Doping" and c1.linear_landau and c1.mass_cons_only and not c1.full_and_linear
+    assert c1.doping == dict(NL=0.001, NH=1.0, eps=0.1, T_L=0.4, T_R=0.4)
+    assert c1.moments_filename() == "Data/Moments_nu0.05A0k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test1.dc"
+    P = PortOracle(Nx=c1.Nx, Nv=c1.Nv, N=c1.N, Lv=c1.Lv, Lx=c1.Lx, nu=c1.nu, dt=c1.dt)
+    P.set_doping(**c1.doping)
+    assert relerr(c1.initial_condition(), P.SetInit_ND()) < 1e-13
+    assert relerr(c1.initial_condition(4, 8), P.SetInit_ND().reshape(c1.Nx, -1)[4:12].reshape(-1)) < 1e-13
+    assert list(solver.doping_profile(16, 0.001, 1.)) == [1.] * 5 + [0.001] * 5 + [1.] * 6
 
 
 def test_initial_conditions_match_oracle(pkg):
