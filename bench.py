@@ -201,7 +201,6 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    g.profile_computeQ(2)
     l0 = g.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -211,10 +210,22 @@ def main():
     barrier()
     t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = sum_over_ranks(g.launch_count - l0)
+    value = 4. * Nx * args.steps / t_dev
+    # instrumented pass for the roofline: the same K steps again with a CUDA-event pair around every launch of the
+    # dominant kernel.  It cannot share the timed pass: there a step is a CUDA-graph replay in which the cells run as
+    # concurrent chains (api.cu, collide_async), so one kernel's launch has no duration of its own; with the events on,
+    # the library launches eagerly, one chain over all cells, and each F2 launch runs alone on the GPU.
+    g.profile_computeQ(2)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    s.step(args.steps)
+    e3.record()
+    barrier()
+    t_instr = max_over_ranks(e2.elapsed_time(e3) * 1e-3)
     cq_ms, cq_n = g.profile_read()
     g.profile_computeQ(False)
     clocks = sampler.finish()
-    value = 4. * Nx * args.steps / t_dev
 
     # ---- end to end: host buffers in, host buffers out, every step --------------------------------
     # (a) serial: one context, upload -> timestep -> download, each call synchronous (what LP_ompi.cpp's loop does
@@ -313,7 +324,8 @@ def main():
         roof = {"bound": "fp64", "kernel": "k_fc3_f2_tmem (ComputeQ as FFT convolutions: y/x line transforms + products + inverse x/y of one kz plane per CTA, accumulators in TMEM)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "traffic": traffic.get("fc3_f2_dram_bytes_per_launch"),
-                "avg_launch_ms": avg_s * 1e3, "launches": cq_n, "share_of_step": cq_ms * 1e-3 / t_dev, "peak_source": fp64_src,
+                "avg_launch_ms": avg_s * 1e3, "launches": cq_n, "share_of_step": cq_ms * 1e-3 / t_instr, "measured_in": "instrumented pass: the same %d steps, eager launches, one chain over all cells, CUDA events around every F2 launch (%.3f ms/step); the timed pass replays a CUDA graph with the cells in concurrent chains" % (args.steps, t_instr / args.steps * 1e3),
+                "peak_source": fp64_src,
                 "algorithmic_flop_per_launch": f2_flop_per_cell * s.x_count,
                 "hbm_view": {"algorithmic_bytes_per_launch_whole_chain": chain_bytes_per_cell * s.x_count, "hbm_peak_gbs": peaks.get("hbm_gbs"),
                              "note": "F1+F2+F3 move 10+1 arrays of N^2 M complex once each way; at the measured HBM peak that is ~0.08 ms per launch chain, well under the FP64 time"},

@@ -150,6 +150,10 @@ int lpgpu_finalize(lpgpu_ctx *c)
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
   if (c->gexec) cudaGraphExecDestroy(c->gexec);
   if (c->gstream) cudaStreamDestroy(c->gstream);
+  for (lpgpu_ctx *v : c->groups) delete v;             // views own nothing on the device
+  for (cudaStream_t st : c->group_streams) if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : c->group_done) if (ev) cudaEventDestroy(ev);
+  if (c->group_fork) cudaEventDestroy(c->group_fork);
   delete c;
   return LPGPU_OK;
 }
@@ -271,7 +275,7 @@ static int eval_async(lpgpu_ctx *c, const double *f, double *q, int B)
   }
   return lp_launch_conserve(c, q, B);
 }
-static int collide_async(lpgpu_ctx *c)
+static int collide_cells(lpgpu_ctx *c)
 {
   const int B = c->ncell;
   if (c->p.linear_landau && !c->have_mhat) { lp_set_error("LinearLandau: call lpgpu_set_maxwellian after uploading the initial condition"); return LPGPU_EINVAL; }
@@ -306,6 +310,70 @@ static int collide_async(lpgpu_ctx *c)
     LP_TRY(eval_async(c, c->d_f1, c->d_q[s], B));
   }
   return lp_launch_project(c, c->d_U[0], B);
+}
+// Concurrent collision chains.  The collision step of a cell depends on no other cell, but it is a chain of ~33
+// dependent kernels: run over all local cells at once, every kernel ends in a partly filled last wave (ComputeQ's
+// dominant kernel: 1536 CTAs on 296 slots = 5.2 waves) and the short bandwidth-bound kernels leave the FP64 pipes
+// idle while the long FP64-bound one leaves HBM idle.  The cells are therefore cut into a few contiguous groups, each
+// a view of the context on its own stream: the block scheduler fills one group's tails with another group's kernels.
+// Results are bit-identical (no kernel combines values of different cells).
+static int group_count(lpgpu_ctx *c)
+{
+  static const int knob = getenv("LPGPU_GROUPS") ? atoi(getenv("LPGPU_GROUPS")) : 0;   // developer knob; 1 = one chain
+  if (c->is_view || c->prof_on || c->p.full_and_linear || !lp_fc3_available(c) || c->ncell < 16) return 1;
+  if (lp_fc_prepare(c) != LPGPU_OK || c->fc_chunk < c->ncell) return 1;    // chunked ComputeQ reuses one set of work arrays
+  int g = knob > 0 ? knob : 4;             // measured, 32 cells at N = Nv = 32: 1.646 / 1.649 / 1.599 / 1.586 ms per step for 1 / 2 / 3 / 4 groups
+  while (g > 1 && c->ncell < 8 * g) g--;   // a group should still fill the GPU on its own
+  return g;
+}
+static int make_groups(lpgpu_ctx *c, int G)
+{
+  const int B = c->ncell, N = c->p.N, M = 3 * N / 2, Nv = c->p.Nv;
+  LP_CUDA(cudaEventCreateWithFlags(&c->group_fork, cudaEventDisableTiming));
+  for (int g = 0; g < G; g++) {
+    const size_t b0 = (size_t)((long long)B * g / G), b1 = (size_t)((long long)B * (g + 1) / G);
+    lpgpu_ctx *v = new (std::nothrow) lpgpu_ctx(*c);
+    if (!v) return LPGPU_ENOMEM;
+    c->groups.push_back(v);
+    v->is_view = true; v->ncell = (int)(b1 - b0); v->cap_cells = b1 - b0; v->launches = 0;
+    v->gexec = nullptr; v->gstream = nullptr; v->graph_failed = true; v->prof_on = 0; v->prof_ev.clear();
+    v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
+    const size_t n3 = (size_t)c->N3 * b0;
+    v->d_U[0] += (size_t)6 * c->sv * b0;
+    v->d_f += n3; v->d_f1 += n3; v->d_Qv += n3; v->d_fhat += 2 * n3; v->d_tmp += 2 * n3;
+    for (int s = 0; s < 4; s++) v->d_q[s] += 2 * n3;
+    if (v->d_mhat) v->d_mhat += 2 * n3;
+    v->d_lam += (size_t)5 * 8 * b0; v->d_cpart += (size_t)5 * N * b0; v->d_B += (size_t)2 * b0 * N * 4 * Nv * Nv;
+    v->d_fc1 += (size_t)20 * N * N * M * b0; v->d_fc2 += (size_t)4 * N * M * M * b0;
+    cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+    if (g > 0) {
+      LP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      LP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    c->group_streams.push_back(st); c->group_done.push_back(ev);
+  }
+  return LPGPU_OK;
+}
+static int collide_async(lpgpu_ctx *c)
+{
+  const int G = group_count(c);
+  if (G <= 1) return collide_cells(c);
+  if (c->groups.empty()) LP_TRY(make_groups(c, G));
+  LP_CUDA(cudaEventRecord(c->group_fork, c->stream));
+  int rc = LPGPU_OK;
+  for (size_t g = 0; g < c->groups.size() && rc == LPGPU_OK; g++) {
+    lpgpu_ctx *v = c->groups[g];
+    v->stream = g == 0 ? c->stream : c->group_streams[g];
+    v->have_mhat = c->have_mhat;
+    if (g > 0) LP_CUDA(cudaStreamWaitEvent(v->stream, c->group_fork, 0));
+    rc = collide_cells(v);
+    c->launches += v->launches; v->launches = 0;
+    if (g > 0) {
+      LP_CUDA(cudaEventRecord(c->group_done[g], v->stream));
+      LP_CUDA(cudaStreamWaitEvent(c->stream, c->group_done[g], 0));
+    }
+  }
+  return rc;
 }
 int lpgpu_collide_step(lpgpu_ctx *c)
 {

@@ -348,11 +348,14 @@ struct F2 {
   static constexpr int IN_C2 = 2 * N * N, Y_C2 = 2 * N * PY;
   static_assert(3 * L * PN <= IN_C2, "T2 must fit the input-plane buffer");
   static_assert(3 * L * PY <= Y_C2, "T must fit the Y buffer");
-  // x-stage task of a thread; L = 16: 24 lanes of each of the 6 warps, one r per warp pair (no divergence)
+  // x-stage task of a thread: the 3M tasks (r, ky) on consecutive threads.  L = 16: 144 tasks fill four and a half of
+  // the six warps (the sixth issues nothing: an idle warp costs no FP64 slot, an idle lane does); the one warp that
+  // holds r = 0 and r = 1 runs both pre-stages, the cheap r = 0 one (additions only) at half mask
   static LP_HD bool xtask(int tid, int &r, int &ky)
   {
-    if (L == 16) { const int w = tid >> 5, lane = tid & 31; r = w >> 1; ky = (w & 1) * 24 + lane; return lane < 24; }
-    r = tid / M; ky = tid % M; return tid < 3 * M;
+    r = tid / M; ky = tid % M;
+    if (r > 2) { r = 2; return false; }
+    return true;
   }
   // product range [p_begin, p_end) of split sp of nsplit (p = 0 and 1 stay together: p = 1 reuses p = 0's y transform)
   static LP_HD void psplit(int sp, int nsplit, int &p_begin, int &p_end)

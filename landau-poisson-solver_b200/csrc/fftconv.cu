@@ -396,10 +396,11 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const unsigned tbase = s_tmem;
   const unsigned tacc = tbase + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * LP_F2TM_PER);
-  // x-stage task; every lane of a warp runs it (the tcgen05 instructions are warp-wide), idle lanes on a clamped line
+  // x-stage task: 3M = 144 of them on the first XW = 5 warps; every lane of those warps runs (the tcgen05 instructions
+  // are warp-wide), the idle half of the fifth on a duplicate line; the sixth warp skips the stage
+  constexpr int XW = (3 * K::M + 31) / 32;
   int r, ky;
   const bool xok = K::xtask(tid, r, ky);
-  if (ky > K::M - 1) ky = K::M - 1;
   #pragma unroll 1
   for (int p = p_begin; p < p_end; p++) {
     fc3::cp_wait_all();
@@ -407,11 +408,12 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
     K::ystage(tid, p, IN, sE, Y);
     __syncthreads();                       // Y complete; IN consumed
     if (p + 1 < p_end) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
-    {
+    if (warp < XW) {
       double2 a0[L], a1[L], uh[L], vh[L];
       #pragma unroll
       for (int l = 0; l < L; l++) { a0[l] = Y[l * K::PY + ky]; a1[l] = Y[(l + L) * K::PY + ky]; }
       fc3::fwd_third<L>(a0, a1, r, uh);
+      __syncwarp();                         // the warp holding two r values diverged in the pre-stage; tcgen05.* is warp-wide
       if constexpr (PARK) {
         #pragma unroll
         for (int c4 = 0; c4 < L / 4; c4++) { double2 t4[4] = {uh[4 * c4], uh[4 * c4 + 1], uh[4 * c4 + 2], uh[4 * c4 + 3]}; tmem_st4c(tacc + 64 + 16 * c4, t4); }
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
       #pragma unroll
       for (int l = 0; l < L; l++) { a0[l] = Y[K::N * K::PY + l * K::PY + ky]; a1[l] = Y[K::N * K::PY + (l + L) * K::PY + ky]; }
       fc3::fwd_third<L>(a0, a1, r, vh);
+      __syncwarp();
       #pragma unroll
       for (int c4 = 0; c4 < L / 4; c4++) {
         double2 a[4];
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
     }
   }
   __syncthreads();
-  {
+  if (warp < XW) {
     double2 acc[L];
     #pragma unroll
     for (int c4 = 0; c4 < L / 4; c4++) {
@@ -558,14 +561,13 @@ bool lp_fc3_available(const lpgpu_ctx *c)
   return (v == 0 || v == 2) && !fc3_knobs_off() && (N == 32 || N == 24 || N == 16 || N == 8);
 }
 // fused_i: `fhat` is the output of lp_launch_fft3d_jk (only valid when lp_fc3_available)
-int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part)
+// work arrays, twiddles and re-laid symbols of the FFT-convolution pipeline (idempotent; first use allocates)
+int lp_fc_prepare(lpgpu_ctx *c)
 {
-  if ((fused_i || part) && !lp_fc3_available(c)) { lp_set_error("fused ComputeQ needs the fc3 pipeline"); return LPGPU_EINVAL; }
   const int N = c->p.N, M = 3 * N / 2;
   FcPlan pl;
   if ((N & 1) || !make_plan(M, pl)) return -1;
   const size_t plane_bytes = ((size_t)M * (M + 1) + M) * sizeof(double2);
-  const size_t line_bytes = ((size_t)16 * (M + 1) + M) * sizeof(double2);
   if (!c->d_fc1) {
     // chunk of cells whose transformed arrays fit a fixed budget: 10 arrays of N^2 M for the register-resident pipeline
     // (7.9 MB per cell at N = 32), 14 of N M^2 for the shared-memory fallback
@@ -599,6 +601,17 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
     LP_CUDA(cudaFuncSetAttribute(k_fc_fwd_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     LP_CUDA(cudaFuncSetAttribute(k_fc_inv_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
+  return LPGPU_OK;
+}
+int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part)
+{
+  if ((fused_i || part) && !lp_fc3_available(c)) { lp_set_error("fused ComputeQ needs the fc3 pipeline"); return LPGPU_EINVAL; }
+  const int N = c->p.N, M = 3 * N / 2;
+  FcPlan pl;
+  if ((N & 1) || !make_plan(M, pl)) return -1;
+  const size_t plane_bytes = ((size_t)M * (M + 1) + M) * sizeof(double2);
+  const size_t line_bytes = ((size_t)16 * (M + 1) + M) * sizeof(double2);
+  { const int rc = lp_fc_prepare(c); if (rc != LPGPU_OK) return rc; }
   const double2 *tw = reinterpret_cast<const double2 *>(c->d_fctw);
   const bool prof = c->prof_on == 1 && c->prof_used + 2 <= c->prof_ev.size();
   if (prof) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));

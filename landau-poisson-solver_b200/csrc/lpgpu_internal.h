@@ -70,6 +70,13 @@ struct lpgpu_ctx {
   cudaGraphExec_t gexec;
   bool graph_failed;
   long long graph_launches;   // kernels per replay
+  // ---- concurrent collision chains: the local cells in contiguous groups, each group a view of this context (same
+  //      tables, per-cell arrays offset to its first cell) with its own stream; group 0 runs on `stream` itself
+  std::vector<lpgpu_ctx *> groups;
+  std::vector<cudaStream_t> group_streams;
+  std::vector<cudaEvent_t> group_done;
+  cudaEvent_t group_fork;
+  bool is_view;
   int prof_on;            // 0 off, 1 events around the whole ComputeQ chain, 2 around its dominant kernel (F2) only
   std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
   size_t prof_used;        // events used so far
@@ -118,6 +125,8 @@ int lp_launch_fft3d_jk(lpgpu_ctx *c, const double *in, bool in_real, int B);
 bool lp_fc3_available(const lpgpu_ctx *c);
 // part (nullable, fc3 only): receives the [cell][N][5] partial conservation dot products of the unconserved spectrum
 int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part);
+// allocates the pipeline's work arrays on first use (idempotent); -1 when the size has no FFT-convolution form
+int lp_fc_prepare(lpgpu_ctx *c);
 // conservation correction from those partials (in place)
 int lp_launch_conserve_from_parts(lpgpu_ctx *c, double *q, const double *part, int B);
 // FS whose first pass also applies the conservation correction from `part` to q (in place) before transforming
