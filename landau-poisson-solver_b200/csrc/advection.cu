@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(256) k_moments_cell(const double *__restrict__
   const long long cell = blockIdx.x;
   const double *u = planes + ((cell + 1) * 6) * (long long)sv;
   double v[5] = {0., 0., 0., 0., 0.};
-  for (int j = threadIdx.x; j < sv; j += blockDim.x) {
+  const int per = (sv + gridDim.y - 1) / gridDim.y, jlo = blockIdx.y * per, jhi = min(sv, jlo + per);
+  for (int j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
     const int j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
     const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv, c3 = -Lv + (j3 + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
     const double U0 = u[j], U2 = u[2LL * sv + j], U3 = u[3LL * sv + j], U4 = u[4LL * sv + j], U5 = u[5LL * sv + j];
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(256) k_moments_cell(const double *__restrict__
   }
   block_sum<5>(v, red);
   if (threadIdx.x == 0)
-    for (int m = 0; m < 5; m++) part[5 * cell + m] = v[m];
+    for (int m = 0; m < 5; m++) part[5 * (cell * gridDim.y + blockIdx.y) + m] = v[m];
 }
 __global__ void k_moments_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double xs, double dv, double scalev)
 {
@@ -355,15 +356,20 @@ __global__ void __launch_bounds__(256) k_diag_cell(const double *__restrict__ pl
     double e = 0., avg = 0.;
     for (int a = 0; a < nxq; a++)
       for (int b = 0; b < 5; b++)
-        for (int cc = 0; cc < 5; cc++)
+        for (int cc = 0; cc < 5; cc++) {
+          // same expressions, same association as the one-line form: only what does not depend on d is computed once
+          const double xs = homogeneous ? 0. : 0.5 * c_gt[a], x1 = 0.5 * c_gt[b], x2 = 0.5 * c_gt[cc];
+          const double head = U0 + (homogeneous ? 0. : U1 * xs) + U2 * x1 + U3 * x2;
+          const double wabc = (homogeneous ? 1. : c_gw[a]) * c_gw[b] * c_gw[cc], q12 = x1 * x1 + x2 * x2;
           #pragma unroll
           for (int d = 0; d < 5; d++) {
-            const double xs = homogeneous ? 0. : 0.5 * c_gt[a], x1 = 0.5 * c_gt[b], x2 = 0.5 * c_gt[cc], x3 = 0.5 * c_gt[d];
-            const double f = U0 + (homogeneous ? 0. : U1 * xs) + U2 * x1 + U3 * x2 + U4 * x3 + U5 * (x1 * x1 + x2 * x2 + x3 * x3);
-            const double w = (homogeneous ? 1. : c_gw[a]) * c_gw[b] * c_gw[cc] * c_gw[d];
+            const double x3 = 0.5 * c_gt[d];
+            const double f = head + U4 * x3 + U5 * (q12 + x3 * x3);
+            const double w = wabc * c_gw[d];
             if (f > 0) e += w * f * log(f);
             avg += w * f;
           }
+        }
     const int j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
     const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv, c3 = -Lv + (j3 + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
     const double ke = U0 * (r2 + dv * dv / 4.) * dv + (c1 * U2 + c2 * U3 + c3 * U4) * dv * dv / 6. + U5 * (dv * dv * dv * 19. / 240. + r2 * dv / 4.);
@@ -432,10 +438,11 @@ int lp_launch_moments(lpgpu_ctx *c, const double *planes)
 {
   // d_B is free outside the projection: use its head for the per-cell partials
   double *part = c->d_B;
-  k_moments_cell<<<c->ncell, 256, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv);
+  const int chunks = c->sv >= 4096 ? 16 : 1;   // blocks per x cell (one block per cell left most of the GPU idle)
+  k_moments_cell<<<dim3(c->ncell, chunks), 256, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv);
   LP_LAUNCHED(c);
   const double xs = c->p.homogeneous ? 1. : c->p.Lx / c->p.Nx;
-  k_moments_fold<<<1, 32, 0, c->stream>>>(part, c->d_mom, c->ncell, xs, c->tab.dv, c->tab.scalev);
+  k_moments_fold<<<1, 32, 0, c->stream>>>(part, c->d_mom, c->ncell * chunks, xs, c->tab.dv, c->tab.scalev);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }

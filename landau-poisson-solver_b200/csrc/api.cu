@@ -46,7 +46,8 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
 {
   if (!p || !out) { lp_set_error("lpgpu_init: null argument"); return LPGPU_EINVAL; }
   *out = nullptr;
-  if (p->gamma != -3) { lp_set_error("lpgpu_init: only gamma = -3 (Landau) is implemented"); return LPGPU_EINVAL; }
+  if (p->gamma != -3 && p->gamma != 0 && p->gamma != 1) { lp_set_error("lpgpu_init: gamma must be -3 (Landau), 0 (Maxwell molecules) or 1 (hard spheres), as InputParsing.cpp:202-238"); return LPGPU_EINVAL; }
+  if (p->gamma != -3 && p->full_and_linear) { lp_set_error("lpgpu_init: FullandLinear is implemented for gamma = -3 only (gHat3_linear has no other branch, collisionRoutines_1.cpp:193-218)"); return LPGPU_EINVAL; }
   if (p->N < 2 || p->N > 32 || (p->N & 1)) { lp_set_error("lpgpu_init: N must be even and in [2, 32]"); return LPGPU_EINVAL; }
   if (p->Nv < 2 || p->Nv > 64 || (p->Nv & 1)) { lp_set_error("lpgpu_init: Nv must be even and in [2, 64]"); return LPGPU_EINVAL; }
   if (!(p->Lv > 0) || !(p->dt > 0) || p->nu < 0) { lp_set_error("lpgpu_init: need Lv > 0, dt > 0, nu >= 0"); return LPGPU_EINVAL; }

@@ -18,7 +18,7 @@ namespace {
 
 struct Cx { double re, im; };
 
-// symbols of the Landau collision kernel (Coulomb, gamma = -3) on the ball of radius R
+// symbols of the Landau collision kernel (Coulomb, gamma = -3) on the ball of radius R: collisionRoutines_1.cpp:18-36
 double sym_s1(double R, double k1, double k2, double k3)
 {
   if (k1 == 0. && k2 == 0. && k3 == 0.) return std::sqrt(1. / (2 * M_PI)) * R * R;
@@ -38,6 +38,47 @@ double sym_s213(double R, double k1, double k2, double k3)
   const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r;
   return -std::sqrt(2 / M_PI) * k1 * k3 * (2. * Rr + Rr * std::cos(Rr) - 3. * std::sin(Rr)) / (R * std::pow(r, 5.));
 }
+// gamma = 0 (Maxwell molecules): collisionRoutines_1.cpp:38-66
+double sym_s1_mm(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, c = std::cos(Rr), s = std::sin(Rr);
+  if (r == 0.) return 2 * std::sqrt(1. / (2. * M_PI)) * std::pow(R, 5.) / 5.;
+  return std::sqrt(2. / M_PI) * (-Rr * Rr * Rr * c + 3 * Rr * Rr * s + 6 * Rr * c - 6 * s) / std::pow(r, 5.);
+}
+double sym_s233_mm(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, c = std::cos(Rr), s = std::sin(Rr);
+  if (r == 0.) return 2 * std::sqrt(1. / (2. * M_PI)) * std::pow(R, 5.) / 15.;
+  return std::sqrt(2. / M_PI) * ((k1 * k1 + k2 * k2) * (-Rr * Rr * s - 3 * Rr * c + 3 * s)
+                                 + k3 * k3 * (-Rr * Rr * Rr * c + 5 * Rr * Rr * s + 12 * Rr * c - 12 * s)) / std::pow(r, 7.);
+}
+double sym_s213_mm(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, c = std::cos(Rr), s = std::sin(Rr);
+  if (k1 == 0. || k3 == 0.) return 0.;
+  return std::sqrt(2. / M_PI) * k1 * k3 * (-Rr * Rr * Rr * c + 6 * Rr * Rr * s + 15 * Rr * c - 15 * s) / (std::pow(r, 7.));
+}
+// gamma = 1 (hard spheres): collisionRoutines_1.cpp:68-96
+double sym_s1_hs(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, c = std::cos(Rr), s = std::sin(Rr);
+  if (r == 0.) return std::sqrt(1. / (2. * M_PI)) * std::pow(R, 6.) / 3.;
+  return std::sqrt(2. / M_PI) * (4. * (Rr * Rr - 6.) * Rr * s - (Rr * Rr * (Rr * Rr - 12.) + 24.) * c + 24.) / std::pow(r, 6.);
+}
+double sym_s233_hs(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, c = std::cos(Rr), s = std::sin(Rr);
+  if (r == 0.) return std::sqrt(1. / (2. * M_PI)) * std::pow(R, 6.) / 9.;
+  return std::sqrt(2. / M_PI) * ((k1 * k1 + k2 * k2) * ((8. - Rr * Rr) * Rr * s + 4. * (2. - Rr * Rr) * c - 8.)
+                                 + k3 * k3 * ((Rr * Rr * (20. - Rr * Rr) - 40.) * c + (6. * Rr * Rr - 40.) * Rr * s + 40.)) / std::pow(r, 8.);
+}
+double sym_s213_hs(double R, double k1, double k2, double k3)
+{
+  const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, c = std::cos(Rr), s = std::sin(Rr);
+  if (k1 == 0. || k3 == 0.) return 0.;
+  return std::sqrt(2. / M_PI) * k1 * k3 * ((Rr * Rr * (24. - Rr * Rr) - 48.) * c + (7. * Rr * Rr - 48.) * Rr * s + 48.) / (std::pow(r, 8.));
+}
+typedef double (*sym_fn)(double, double, double, double);
 double sinc1(double x) { return x == 0.0 ? 1.0 : std::sin(x) / x; }
 
 // in-place inverse of a small dense matrix (partial pivoting); replaces dgetrf_/dgetri_
@@ -86,15 +127,22 @@ void lp_build_tables(const lpgpu_params &p, LpTables &t)
   t.G.assign((size_t)7 * N3, 0.);
   t.Gl.assign((size_t)3 * N3, 0.);
   const double R = p.Lv, pref = t.h_eta * t.h_eta * t.h_eta;
+  const sym_fn f_s1 = p.gamma == 0 ? sym_s1_mm : p.gamma == 1 ? sym_s1_hs : sym_s1;
+  const sym_fn f_s233 = p.gamma == 0 ? sym_s233_mm : p.gamma == 1 ? sym_s233_hs : sym_s233;
+  const sym_fn f_s213 = p.gamma == 0 ? sym_s213_mm : p.gamma == 1 ? sym_s213_hs : sym_s213;
   for (int l = 0; l < N; l++)
     for (int m = 0; m < N; m++)
       for (int n = 0; n < N; n++) {
         const double k1 = t.eta[l], k2 = t.eta[m], k3 = t.eta[n];
         const double r = std::sqrt(k1 * k1 + k2 * k2 + k3 * k3);
-        const double s1 = sym_s1(R, k1, k2, k3);
-        const double S11 = s1 - sym_s233(R, k2, k3, k1), S22 = s1 - sym_s233(R, k1, k3, k2), S33 = s1 - sym_s233(R, k1, k2, k3);
-        const double S12 = -sym_s213(R, k1, k3, k2), S13 = -sym_s213(R, k1, k2, k3), S23 = -sym_s213(R, k2, k1, k3);
-        const double A = (r == 0.) ? 0. : std::sqrt(8. / M_PI) * (R * r - std::sin(R * r)) / (R * r);
+        const double s1 = f_s1(R, k1, k2, k3);
+        const double S11 = s1 - f_s233(R, k2, k3, k1), S22 = s1 - f_s233(R, k1, k3, k2), S33 = s1 - f_s233(R, k1, k2, k3);
+        const double S12 = -f_s213(R, k1, k3, k2), S13 = -f_s213(R, k1, k2, k3), S23 = -f_s213(R, k2, k1, k3);
+        // the part of gHat3 that depends on omega alone.  gamma = -3 (:137-146): the Coulomb term, 0 at omega = 0.
+        // gamma = 0, 1 (:149-157): sum_ij S_ij (2 w_j - xi_j) xi_i with xi = w + e is sum_ij S_ij w_i w_j - sum_ij S_ij e_i e_j
+        // (the cross terms cancel, S being symmetric) -- the same seven-symbol form with another first symbol
+        const double A = p.gamma == -3 ? ((r == 0.) ? 0. : std::sqrt(8. / M_PI) * (R * r - std::sin(R * r)) / (R * r))
+                                       : S11 * k1 * k1 + S22 * k2 * k2 + S33 * k3 * k3 + 2. * (S12 * k1 * k2 + S13 * k1 * k3 + S23 * k2 * k3);
         const double w = pref * t.wt[l] * t.wt[m] * t.wt[n];
         double *g = &t.G[(size_t)7 * (n + N * (m + N * l))];
         g[0] = w * A; g[1] = w * S11; g[2] = w * S22; g[3] = w * S33;

@@ -5,7 +5,7 @@
 // row 1 = initial state; format LP_ompi.cpp:622-630, 836-844), Data/EntropyVals_*.dc (:632, :846) and the final Data/U_*.dc checkpoint
 // (raw doubles, LP_ompi.cpp:896).  `Second = True` restarts from the last U in Data/<Second/Name>
 // (LP_ompi.cpp:529-571).  All five decks of the reference's test suite run (Damping / TwoStream / FourHump / Doping ICs,
-// Homogeneous, FullandLinear, LinearLandau, MassConsOnly); TwoHump and gamma != -3 stop with an error, as the
+// Homogeneous, FullandLinear, LinearLandau, MassConsOnly; gamma = -3, 0, 1); TwoHump stops with an error, as the
 // reference does for bad input (exit(1)).
 //
 // usage: lpsolver [input-file] [--device k] [--quiet]

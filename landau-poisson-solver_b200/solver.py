@@ -76,8 +76,10 @@ class RunConfig:
         self.mass_cons_only = _bool(kv, "MassConsOnly")
         if self.ic == "TwoHump":
             raise NotImplementedError("TwoHump initial conditions are outside the GPU hot path")
-        if self.gamma != -3:
-            raise NotImplementedError("only the Landau kernel gamma = -3 is implemented")
+        if self.gamma not in (-3, 0, 1):              # ReadGamma (InputParsing.cpp:202-238)
+            raise ValueError("Currently the code can only use gamma = -3 (True Landau), 0 (Maxwell Molecules) or 1 (Hard Spheres)")
+        if self.gamma != -3 and self.full_and_linear:
+            raise NotImplementedError("FullandLinear is implemented for gamma = -3 only")
         self.doping = None
         if self.ic == "Doping":                      # ReadDopingParameters (InputParsing.cpp:512-570)
             if self.homogeneous:
@@ -291,7 +293,7 @@ class ShardedSolver:
     """One rank of the x-sharded solver.  world == 1 needs no process group."""
 
     def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None, full_and_linear=False,
-                 stream=None, doping=None, linear_landau=False, mass_cons_only=False):
+                 stream=None, doping=None, linear_landau=False, mass_cons_only=False, gamma=-3):
         """stream: a torch.cuda.Stream all work of this solver (kernels, copies, the NCCL exchange) is ordered on;
         None = torch's current stream for sharded runs, the library's default otherwise.  Two solvers on two streams
         pipeline: the host<->device copies of one overlap the kernels of the other."""
@@ -304,7 +306,7 @@ class ShardedSolver:
             self.x_begin, self.x_count = shard_range(Nx, world, rank)
         self.g = lpgpu.LPGpu(Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=homogeneous, x_begin=self.x_begin,
                              x_count=self.x_count, device=device, full_and_linear=full_and_linear, doping=doping,
-                             linear_landau=linear_landau, mass_cons_only=mass_cons_only)
+                             linear_landau=linear_landau, mass_cons_only=mass_cons_only, gamma=gamma)
         self.linear_landau = bool(linear_landau)
         self.nu = nu
         self._ex = None
@@ -390,7 +392,7 @@ def run_from_input_file(path="LPsolver-input.txt", outdir=".", device=0, quiet=F
     cfg = RunConfig.from_file(path)
     s = ShardedSolver(cfg.Nx, cfg.Nv, cfg.N, cfg.Lv, cfg.Lx, cfg.nu, cfg.dt, homogeneous=cfg.homogeneous, device=device,
                       full_and_linear=cfg.full_and_linear, doping=cfg.doping, linear_landau=cfg.linear_landau,
-                      mass_cons_only=cfg.mass_cons_only)
+                      mass_cons_only=cfg.mass_cons_only, gamma=cfg.gamma)
     s.upload(cfg.initial_condition())
     if cfg.linear_landau and cfg.nu > 0:
         s.set_maxwellian()

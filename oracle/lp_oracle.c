@@ -67,22 +67,71 @@ static double s213hat(double R, double k1, double k2, double k3)
   double Rr = R * r;
   return -sqrt(2 / M_PI) * k1 * k3 * (2. * Rr + Rr * cos(Rr) - 3. * sin(Rr)) / (R * pow(r, 5.));
 }
-/* the symmetric 3x3 symbol matrix at omega: collisionRoutines_1.cpp:113-125 */
-static void shat_matrix(double R, double k1, double k2, double k3, double S[3][3])
+/* Maxwell molecules (gamma = 0): collisionRoutines_1.cpp:38-66 */
+static double s1hat_mm(double R, double k1, double k2, double k3)
 {
-  double s1 = s1hat(R, k1, k2, k3);
-  S[0][0] = s1 - s233hat(R, k2, k3, k1);
-  S[1][1] = s1 - s233hat(R, k1, k3, k2);
-  S[2][2] = s1 - s233hat(R, k1, k2, k3);
-  S[0][1] = -s213hat(R, k1, k3, k2);
-  S[0][2] = -s213hat(R, k1, k2, k3);
-  S[1][2] = -s213hat(R, k2, k1, k3);
+  double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, cR = cos(Rr), sR = sin(Rr);
+  if (r == 0.) return 2 * sqrt(1. / (2. * M_PI)) * pow(R, 5.) / 5.;
+  return sqrt(2. / M_PI) * (-Rr * Rr * Rr * cR + 3 * Rr * Rr * sR + 6 * Rr * cR - 6 * sR) / pow(r, 5.);
+}
+static double s233hat_mm(double R, double k1, double k2, double k3)
+{
+  double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, cR = cos(Rr), sR = sin(Rr);
+  if (r == 0.) return 2 * sqrt(1. / (2. * M_PI)) * pow(R, 5.) / 15.;
+  return sqrt(2. / M_PI) * ((k1 * k1 + k2 * k2) * (-Rr * Rr * sR - 3 * Rr * cR + 3 * sR)
+                            + k3 * k3 * (-Rr * Rr * Rr * cR + 5 * Rr * Rr * sR + 12 * Rr * cR - 12 * sR)) / pow(r, 7.);
+}
+static double s213hat_mm(double R, double k1, double k2, double k3)
+{
+  double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, cR = cos(Rr), sR = sin(Rr);
+  if (k1 == 0. || k3 == 0.) return 0.;
+  return sqrt(2. / M_PI) * k1 * k3 * (-Rr * Rr * Rr * cR + 6 * Rr * Rr * sR + 15 * Rr * cR - 15 * sR) / (pow(r, 7.));
+}
+/* hard spheres (gamma = 1): collisionRoutines_1.cpp:68-96 */
+static double s1hat_hs(double R, double k1, double k2, double k3)
+{
+  double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, cR = cos(Rr), sR = sin(Rr);
+  if (r == 0.) return sqrt(1. / (2. * M_PI)) * pow(R, 6.) / 3.;
+  return sqrt(2. / M_PI) * (4. * (Rr * Rr - 6.) * Rr * sR - (Rr * Rr * (Rr * Rr - 12.) + 24.) * cR + 24.) / pow(r, 6.);
+}
+static double s233hat_hs(double R, double k1, double k2, double k3)
+{
+  double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, cR = cos(Rr), sR = sin(Rr);
+  if (r == 0.) return sqrt(1. / (2. * M_PI)) * pow(R, 6.) / 9.;
+  return sqrt(2. / M_PI) * ((k1 * k1 + k2 * k2) * ((8. - Rr * Rr) * Rr * sR + 4. * (2. - Rr * Rr) * cR - 8.)
+                            + k3 * k3 * ((Rr * Rr * (20. - Rr * Rr) - 40.) * cR + (6. * Rr * Rr - 40.) * Rr * sR + 40.)) / pow(r, 8.);
+}
+static double s213hat_hs(double R, double k1, double k2, double k3)
+{
+  double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3), Rr = R * r, cR = cos(Rr), sR = sin(Rr);
+  if (k1 == 0. || k3 == 0.) return 0.;
+  return sqrt(2. / M_PI) * k1 * k3 * ((Rr * Rr * (24. - Rr * Rr) - 48.) * cR + (7. * Rr * Rr - 48.) * Rr * sR + 48.) / (pow(r, 8.));
+}
+/* the symmetric 3x3 symbol matrix at omega: collisionRoutines_1.cpp:106-136 */
+typedef double (*sym_fn)(double, double, double, double);
+static void shat_matrix_g(int gamma, double R, double k1, double k2, double k3, double S[3][3])
+{
+  sym_fn f1 = gamma == 0 ? s1hat_mm : gamma == 1 ? s1hat_hs : s1hat;
+  sym_fn f233 = gamma == 0 ? s233hat_mm : gamma == 1 ? s233hat_hs : s233hat;
+  sym_fn f213 = gamma == 0 ? s213hat_mm : gamma == 1 ? s213hat_hs : s213hat;
+  double s1 = f1(R, k1, k2, k3);
+  S[0][0] = s1 - f233(R, k2, k3, k1);
+  S[1][1] = s1 - f233(R, k1, k3, k2);
+  S[2][2] = s1 - f233(R, k1, k2, k3);
+  S[0][1] = -f213(R, k1, k3, k2);
+  S[0][2] = -f213(R, k1, k2, k3);
+  S[1][2] = -f213(R, k2, k1, k3);
   S[1][0] = S[0][1]; S[2][0] = S[0][2]; S[2][1] = S[1][2];
 }
-/* gHat3, gamma = -3 branch: collisionRoutines_1.cpp:98-161 */
-static double ghat3_from(const double S[3][3], double A, int r_is_zero, const double z[3], const double k[3])
+/* gHat3: collisionRoutines_1.cpp:98-161; gamma = -3 (:137-146), gamma = 0, 1 (:148-157) */
+static double ghat3_from(int gamma, const double S[3][3], double A, int r_is_zero, const double z[3], const double k[3])
 {
   double res = 0.;
+  if (gamma != -3) {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) res += S[i][j] * (2. * k[j] - z[j]) * z[i];
+    return res;
+  }
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) res += S[i][j] * (z[i] - k[i]) * (z[j] - k[j]);
   return r_is_zero ? -res : A - res;
@@ -91,9 +140,9 @@ double lpo_gHat3(const lpo_ctx *c, double z1, double z2, double z3, double k1, d
 {
   double S[3][3], z[3] = {z1, z2, z3}, k[3] = {k1, k2, k3};
   double R = c->Lv, r = sqrt(k1 * k1 + k2 * k2 + k3 * k3);
-  shat_matrix(R, k1, k2, k3, S);
+  shat_matrix_g(c->gamma, R, k1, k2, k3, S);
   double A = (r == 0.) ? 0. : sqrt(8. / M_PI) * (R * r - sin(R * r)) / (R * r);
-  return ghat3_from(S, A, r == 0., z, k);
+  return ghat3_from(c->gamma, S, A, r == 0., z, k);
 }
 static double weight_at(const lpo_ctx *c, int i, int j, int k, int l, int m, int n)
 {
@@ -105,7 +154,7 @@ static double weight_at(const lpo_ctx *c, int i, int j, int k, int l, int m, int
   S[1][2] = S[2][1] = c->Sh[6 * N3 + w];
   double z[3] = {c->eta[i], c->eta[j], c->eta[k]}, kk[3] = {c->eta[l], c->eta[m], c->eta[n]};
   int rz = (kk[0] == 0. && kk[1] == 0. && kk[2] == 0.);
-  return ghat3_from(S, c->Sh[w], rz, z, kk);
+  return ghat3_from(c->gamma, S, c->Sh[w], rz, z, kk);
 }
 /* row xi of generate_conv_weights' table: collisionRoutines_1.cpp:220-237 */
 void lpo_weight_row(const lpo_ctx *c, int xi, double *row)
@@ -229,7 +278,7 @@ void lpo_IntModes(const lpo_ctx *c, int k1, int k2, int k3, int j1, int j2, int 
 lpo_ctx *lpo_create(int Nx, int Nv, int N, double Lv, double Lx, double nu, double dt,
                     int homogeneous, int gamma)
 {
-  if (gamma != -3) return NULL; /* only the Landau kernel is in scope */
+  if (gamma != -3 && gamma != 0 && gamma != 1) return NULL; /* InputParsing.cpp:202-238 */
   lpo_ctx *c = (lpo_ctx *)calloc(1, sizeof(lpo_ctx));
   c->Nx = Nx; c->Nv = Nv; c->N = N; c->homogeneous = homogeneous; c->gamma = gamma;
   c->Lv = Lv; c->Lx = Lx; c->nu = nu; c->dt = dt;
@@ -261,7 +310,7 @@ lpo_ctx *lpo_create(int Nx, int Nv, int N, double Lv, double Lx, double nu, doub
     int n = w % N, m = (w / N) % N, l = w / (N * N);
     double k1 = c->eta[l], k2 = c->eta[m], k3 = c->eta[n], S[3][3];
     double r = sqrt(k1 * k1 + k2 * k2 + k3 * k3);
-    shat_matrix(Lv, k1, k2, k3, S);
+    shat_matrix_g(gamma, Lv, k1, k2, k3, S);
     c->Sh[w] = (r == 0.) ? 0. : sqrt(8. / M_PI) * (Lv * r - sin(Lv * r)) / (Lv * r);
     c->Sh[1 * N3 + w] = S[0][0]; c->Sh[2 * N3 + w] = S[1][1]; c->Sh[3 * N3 + w] = S[2][2];
     c->Sh[4 * N3 + w] = S[0][1]; c->Sh[5 * N3 + w] = S[0][2]; c->Sh[6 * N3 + w] = S[1][2];

@@ -619,3 +619,37 @@ def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
         if want.size:
             assert got.shape == want.shape, (kind, got.shape, want.shape)
             assert np.max(np.abs(got - want)) <= 2e-7 * np.max(np.abs(want)), kind
+
+
+@pytest.mark.parametrize("gamma", [0, 1])
+@pytest.mark.parametrize("variant", [0, 3])
+def test_other_collision_kernels(pkg, gamma, variant):
+    """gamma = 0 / 1 (generate_conv_weights(conv_weights, gamma), LP_ompi.cpp:424): the same seven-symbol convolution with
+    the Maxwell-molecule / hard-sphere symbols; checked against the unmodified reference's outputs and the oracle."""
+    import json, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_gamma.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    t = "g%d_" % gamma
+    g = pkg.LPGpu(gamma=gamma, computeq_variant=variant, **cfg)
+    assert relerr(g.ComputeQ(z[t + "f"])[0], z[t + "qHat"]) < TOL_SPEC
+    U0 = z[t + "U0"]
+    g.upload_U(U0)
+    g.collide_step()
+    U = g.download_U()
+    assert relerr(U, z[t + "U_collide"]) < TOL_U
+    assert relerr(U - U0, z[t + "U_collide"] - U0) < TOL_DU
+    g.close()
+    gh = pkg.LPGpu(homogeneous=True, gamma=gamma, computeq_variant=variant, **cfg)
+    Uh = z[t + "Uh0"]
+    gh.upload_U(Uh)
+    gh.collide_step()
+    assert relerr(gh.download_U() - Uh, z[t + "Uh_collide"] - Uh) < TOL_DU
+    gh.close()
+    # a larger spectral grid against the oracle (N = 16 through the FFT-convolution pipeline / the tiled direct sum)
+    cfg16 = dict(TEST0, N=16, Nv=16)
+    ora = PortOracle(homogeneous=True, gamma=gamma, **cfg16)
+    g16 = pkg.LPGpu(homogeneous=True, gamma=gamma, computeq_variant=variant, **cfg16)
+    f = ora.setInit_spectral(ora.SetInit_4H_Homo())[0]
+    f = f * (1 + 0.1 * np.sin(np.arange(f.size)))
+    assert relerr(g16.ComputeQ(f)[0], ora.ComputeQ(f)) < TOL_SPEC
+    g16.close()

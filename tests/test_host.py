@@ -64,9 +64,11 @@ def test_unsupported_options_fail_loudly(pkg, tmp_path):
     p.write_text(txt)
     with pytest.raises(NotImplementedError):
         solver.RunConfig.from_file(str(p))
-    p.write_text("gamma = 0\n" + open(os.path.join(GOLD, "LPsolver-input-test0.txt")).read())
-    with pytest.raises(NotImplementedError):
+    p.write_text("gamma = 2\n" + open(os.path.join(GOLD, "LPsolver-input-test0.txt")).read())
+    with pytest.raises(ValueError):             # ReadGamma accepts -3, 0 and 1 only (InputParsing.cpp:202-238)
         solver.RunConfig.from_file(str(p))
+    p.write_text("gamma = 1\n" + open(os.path.join(GOLD, "LPsolver-input-test0.txt")).read())
+    assert solver.RunConfig.from_file(str(p)).gamma == 1
 
 
 def test_reference_test1_deck_is_parsed(pkg):

@@ -162,3 +162,26 @@ def test_port_matches_live_reference():
     assert relerr(P.moments(U), R.moments(U)) < 1e-13
     a, b = P.step(U), R.step(U)
     assert relerr(a, b) < 1e-13 and relerr(a - U, b - U) < 1e-10
+
+
+@pytest.mark.parametrize("gamma", [0, 1])
+def test_port_matches_reference_for_other_kernels(gamma):
+    """gamma = 0 (Maxwell molecules) and 1 (hard spheres), collisionRoutines_1.cpp:38-96, 116-157: no reference deck uses
+    them, so the port is pinned by outputs of the unmodified reference (tests/golden/make_gamma_golden.py)."""
+    z = np.load(os.path.join(GOLD, "ref_gamma.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    t = "g%d_" % gamma
+    P = PortOracle(gamma=gamma, **cfg)
+    got = np.array([P.gHat3(p[:3], p[3:]) for p in z["pairs"]])
+    assert relerr(got, z[t + "gHat3"]) < 1e-15
+    assert relerr(P.ComputeQ(z[t + "f"]), z[t + "qHat"]) < 1e-14
+    assert relerr(P.conserveMoments(z[t + "qHat"]), z[t + "qHat_conserved"]) < 1e-13
+    U0 = z[t + "U0"]
+    assert relerr(P.collide_step(U0) - U0, z[t + "U_collide"] - U0) < 1e-10
+    Ph = PortOracle(homogeneous=True, gamma=gamma, **cfg)
+    Uh = z[t + "Uh0"]
+    assert relerr(Ph.collide_step(Uh) - Uh, z[t + "Uh_collide"] - Uh) < 1e-10
+    if have_ref():
+        R = RefOracle(gamma=gamma, **cfg)
+        f = z[t + "f"] * (1 + 0.05 * np.cos(0.3 * np.arange(z[t + "f"].size)))
+        assert relerr(P.ComputeQ(f), R.ComputeQ(f)) < 1e-14
