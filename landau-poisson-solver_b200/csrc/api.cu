@@ -149,7 +149,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
-  if (c->gexec) cudaGraphExecDestroy(c->gexec);
+  for (int k = 0; k < 2; k++) if (c->gexec[k]) cudaGraphExecDestroy(c->gexec[k]);
   if (c->gstream) cudaStreamDestroy(c->gstream);
   for (lpgpu_ctx *v : c->groups) delete v;             // views own nothing on the device
   for (cudaStream_t st : c->group_streams) if (st) cudaStreamDestroy(st);
@@ -337,7 +337,7 @@ static int make_groups(lpgpu_ctx *c, int G)
     if (!v) return LPGPU_ENOMEM;
     c->groups.push_back(v);
     v->is_view = true; v->ncell = (int)(b1 - b0); v->cap_cells = b1 - b0; v->launches = 0;
-    v->gexec = nullptr; v->gstream = nullptr; v->graph_failed = true; v->prof_on = 0; v->prof_ev.clear();
+    v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->graph_failed[0] = v->graph_failed[1] = true; v->prof_on = 0; v->prof_ev.clear();
     v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
     const size_t n3 = (size_t)c->N3 * b0;
     v->d_U[0] += (size_t)6 * c->sv * b0;
@@ -376,53 +376,73 @@ static int collide_async(lpgpu_ctx *c)
   }
   return rc;
 }
-int lpgpu_collide_step(lpgpu_ctx *c)
-{
-  LP_ENTER(c);
-  if (!(c->p.nu > 0.)) return LPGPU_OK;    // nu = 0: collisionless (LP_ompi.cpp:669)
-  LP_TRY(collide_async(c));
-  LP_CUDA(cudaStreamSynchronize(c->stream));
-  return LPGPU_OK;
-}
 static int one_step_async(lpgpu_ctx *c)
 {
   if (!c->p.homogeneous) LP_TRY(advect_rk3_async(c));
   if (c->p.nu > 0.) LP_TRY(collide_async(c));
   return LPGPU_OK;
 }
-// Capture one timestep (about 40 dependent launches) into a CUDA graph.  A single homogeneous cell is launch-latency
-// bound (each kernel runs a few microseconds); replaying the graph removes the per-launch gaps.
-static void capture_step_graph(lpgpu_ctx *c)
+// Capture one timestep (kind 0) or one collision step (kind 1) into a CUDA graph: 40 dependent launches, about 150 on
+// five streams with the cells in concurrent chains.  A single homogeneous cell is launch-latency bound (each kernel
+// runs a few microseconds) and the many-stream form is bound by the host's launch calls; replaying the graph removes both.
+static void capture_graph(lpgpu_ctx *c, int kind)
 {
-  if (!c->gstream && cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->graph_failed = true; return; }
+  if (!c->gstream && cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->graph_failed[kind] = true; return; }
   cudaStream_t user = c->stream;
   const long long before = c->launches;
   c->stream = c->gstream;
   cudaGraph_t graph = nullptr;
   int rc = LPGPU_ECUDA;
   if (cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-    rc = one_step_async(c);
+    rc = kind == 0 ? one_step_async(c) : collide_async(c);
     if (cudaStreamEndCapture(c->gstream, &graph) != cudaSuccess) rc = LPGPU_ECUDA;
   }
   c->stream = user;
-  c->graph_launches = c->launches - before;
+  c->graph_launches[kind] = c->launches - before;
   c->launches = before;                      // captured, not executed
-  if (rc == LPGPU_OK && graph && cudaGraphInstantiate(&c->gexec, graph, 0) == cudaSuccess) {
+  if (rc == LPGPU_OK && graph && cudaGraphInstantiate(&c->gexec[kind], graph, 0) == cudaSuccess) {
     cudaGraphDestroy(graph);
     return;
   }
   if (graph) cudaGraphDestroy(graph);
   cudaGetLastError();
-  c->gexec = nullptr;
-  c->graph_failed = true;
+  c->gexec[kind] = nullptr;
+  c->graph_failed[kind] = true;
+}
+// one execution of kind 0 / 1: eager the first time, captured the second, replayed from then on
+static int run_kind(lpgpu_ctx *c, int kind)
+{
+  static const bool no_graph = getenv("LPGPU_NO_GRAPH") != nullptr;   // developer knob
+  if (!no_graph && c->prof_on == 0 && !c->graph_failed[kind]) {
+    if (!c->gexec[kind] && c->eager_runs[kind] >= 1) capture_graph(c, kind);
+    if (c->gexec[kind]) {
+      LP_CUDA(cudaGraphLaunch(c->gexec[kind], c->stream));
+      c->launches += c->graph_launches[kind];
+      return LPGPU_OK;
+    }
+  }
+  c->eager_runs[kind]++;
+  return kind == 0 ? one_step_async(c) : collide_async(c);
+}
+int lpgpu_collide_step(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  if (!(c->p.nu > 0.)) return LPGPU_OK;    // nu = 0: collisionless (LP_ompi.cpp:669)
+  LP_TRY(run_kind(c, 1));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
 }
 int lpgpu_collide_step_async(lpgpu_ctx *c)
 {
   LP_ENTER(c);
   if (!(c->p.nu > 0.)) return LPGPU_OK;
-  return collide_async(c);
+  return run_kind(c, 1);
 }
-static int step_enqueue(lpgpu_ctx *c, int nsteps);
+static int step_enqueue(lpgpu_ctx *c, int nsteps)
+{
+  for (int done = 0; done < nsteps; done++) LP_TRY(run_kind(c, 0));
+  return LPGPU_OK;
+}
 int lpgpu_step(lpgpu_ctx *c, int nsteps)
 {
   LP_ENTER(c);
@@ -434,25 +454,6 @@ int lpgpu_step_async(lpgpu_ctx *c, int nsteps)
 {
   LP_ENTER(c);
   return step_enqueue(c, nsteps);
-}
-static int step_enqueue(lpgpu_ctx *c, int nsteps)
-{
-  static const bool no_graph = getenv("LPGPU_NO_GRAPH") != nullptr;   // developer knob
-  int done = 0;
-  if (!no_graph && c->prof_on == 0 && !c->graph_failed && nsteps >= 2) {
-    if (!c->gexec) {
-      LP_TRY(one_step_async(c));             // eager first step: lazy allocations and function attributes happen here
-      done = 1;
-      capture_step_graph(c);
-    }
-    if (c->gexec)
-      for (; done < nsteps; done++) {
-        LP_CUDA(cudaGraphLaunch(c->gexec, c->stream));
-        c->launches += c->graph_launches;
-      }
-  }
-  for (; done < nsteps; done++) LP_TRY(one_step_async(c));
-  return LPGPU_OK;
 }
 
 int lpgpu_set_maxwellian(lpgpu_ctx *c)

@@ -65,11 +65,14 @@ struct lpgpu_ctx {
   bool fc3_attr;
   int fc_chunk;
   // ---- optional CUDA-event timing of the ComputeQ launches (bench.py roofline)
-  // ---- CUDA graph of one timestep (lpgpu_step with nsteps >= 2): captured once on gstream, replayed on `stream`
+  // ---- CUDA graphs, captured once on gstream and replayed on `stream`: [0] one whole timestep (lpgpu_step*),
+  //      [1] the collision step alone (lpgpu_collide_step*, what the sharded driver calls between its exchanges).
+  //      The first execution of either runs eagerly (lazy allocations, function attributes), the second is captured.
   cudaStream_t gstream;
-  cudaGraphExec_t gexec;
-  bool graph_failed;
-  long long graph_launches;   // kernels per replay
+  cudaGraphExec_t gexec[2];
+  bool graph_failed[2];
+  int eager_runs[2];
+  long long graph_launches[2];   // kernels per replay
   // ---- concurrent collision chains: the local cells in contiguous groups, each group a view of this context (same
   //      tables, per-cell arrays offset to its first cell) with its own stream; group 0 runs on `stream` itself
   std::vector<lpgpu_ctx *> groups;

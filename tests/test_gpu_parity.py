@@ -157,12 +157,15 @@ def test_full_step_small(small):
 
 
 def test_graph_replay_matches_eager_steps(small, pkg):
-    """lpgpu_step(n >= 2) replays a CUDA graph of the timestep after one eager step: same bits as n single steps."""
+    """The second lpgpu_step is captured into a CUDA graph and replayed from then on: same bits as eager launches
+    (with the launch profiler on, the library launches eagerly)."""
     ora, g = small
     U = _perturbed(ora, 5)
     g.upload_U(U)
+    g.profile_computeQ(1)
     for _ in range(4):
         g.step(1)                                         # eager
+    g.profile_computeQ(False)
     want = g.download_U()
     g2 = pkg.LPGpu(**SMALL)
     g2.upload_U(U)
@@ -172,6 +175,37 @@ def test_graph_replay_matches_eager_steps(small, pkg):
     g2.close()
     assert np.array_equal(got, want)
     assert relerr(got, ora.step(ora.step(ora.step(ora.step(U))))) < TOL_U
+
+
+def test_concurrent_cell_groups_match_one_chain(pkg):
+    """From 16 local cells on, the collision step runs as concurrent chains over contiguous groups of cells (views of
+    the context on their own streams, api.cu); eagerly, inside the timestep graph and inside the collide-only graph the
+    sharded driver uses, the result must equal the single chain bit for bit."""
+    cfg = dict(SMALL, Nx=16)
+    ora = PortOracle(**cfg)
+    U = _perturbed(ora, 9)
+    g = pkg.LPGpu(**cfg)
+    g.upload_U(U)
+    g.profile_computeQ(1)                                 # profiler on: eager launches, one chain over all cells
+    l0 = g.launch_count
+    for _ in range(3):
+        g.step(1)
+    one_chain_launches = (g.launch_count - l0) // 3
+    g.profile_computeQ(False)
+    want = g.download_U()
+    g.upload_U(U)
+    l0 = g.launch_count
+    g.step(1)                                             # eager, two groups
+    assert g.launch_count - l0 > one_chain_launches       # every group launches its own chain
+    g.step(2)                                             # captured + replayed
+    assert np.array_equal(g.download_U(), want)
+    g.upload_U(U)
+    for _ in range(3):                                    # phase calls: collide-only graph from the second call on
+        g.advect_rk3()
+        g.collide_step()
+    assert np.array_equal(g.download_U(), want)
+    g.close()
+    assert relerr(want, ora.step(ora.step(ora.step(U)))) < TOL_U
 
 
 def test_pipelined_contexts_match_synchronous_calls(pkg):
