@@ -162,6 +162,14 @@ int lpgpu_moments_partial(lpgpu_ctx *c, double *out5, double *ms_local_host);
  * out4[2]/out4[1] after summing over shards, MomentCalculations.cpp:133-199), number of cells FindNegVals
  * flags (NegativityChecks.cpp:24-160). */
 int lpgpu_diagnostics_partial(lpgpu_ctx *c, double *out4);
+/* The same numbers without stalling the time loop (the reference computes them on rank 0 between two timesteps,
+ * LP_ompi.cpp:817-849; its 5^4-point entropy rule costs about as much FP64 work as a timestep).  _begin snapshots the
+ * state on the context's stream and enqueues the moment, density and entropy/negativity reductions of the snapshot on a
+ * side stream; the caller goes on to enqueue the next timestep; _end waits for the reductions and returns what
+ * lpgpu_moments_partial (out5, ms_local_host: 2*x_count doubles, may be NULL) and lpgpu_diagnostics_partial (out4)
+ * return for the snapshotted state.  One snapshot in flight per context: _end before the next _begin. */
+int lpgpu_diagnostics_begin(lpgpu_ctx *c);
+int lpgpu_diagnostics_end(lpgpu_ctx *c, double *out5, double *ms_local_host, double *out4);
 /* PrintMarginal (LP_ompi.cpp:649, :870; MarginalCreation.cpp:16-67): the sums over the velocity directions that are
  * integrated out, per output cell: x_count*Nv rows of (sum U0, U1, U2, U5 over j2, j3) or, homogeneous, Nv*Nv rows of
  * (sum U0, U2, U3, U5 over j3).  The host evaluates the marginal at its 4 x 4 sub-grid points from them. */

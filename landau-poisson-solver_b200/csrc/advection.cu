@@ -7,6 +7,7 @@
 // the x halos), c = DG coefficient 0..5, j = j1*Nv^2 + j2*Nv + j3.  Every access below is
 // unit-stride in j across a warp; an x-plane is one contiguous 6*sv block, so a halo is one copy.
 #include "lpgpu_internal.h"
+#include <numeric>
 
 #define LP_LAUNCHED(c)                                  \
   do {                                                  \
@@ -342,10 +343,33 @@ __global__ void k_moments_fold(const double *__restrict__ part, double *__restri
 // number of negative cells.
 __constant__ double c_gw[5] = {0.5688888888888889, 0.4786286704993665, 0.4786286704993665, 0.2369268850561891, 0.2369268850561891};
 __constant__ double c_gt[5] = {0., -0.5384693101056831, 0.5384693101056831, -0.9061798459386640, 0.9061798459386640};
-__global__ void __launch_bounds__(256) k_diag_cell(const double *__restrict__ planes, double *__restrict__ part, int Nv, int sv,
+// log of a positive double for the entropy integrand: 64-interval table on the mantissa (c_i = 1 + (i + 1/2)/64, the
+// table holds rc_i = fl(1/c_i) and -log(rc_i)), d = m rc_i - 1 by one FMA (|d| <= 1/128), log1p(d) to degree 7
+// (truncation 2e-18).  |error| <= 2e-16 (1 + |log x|): the same bound as libm's to within a factor of two, at a fifth of
+// its FP64 instructions -- the entropy (5^4 logarithms per DG cell per step) is bound by exactly those.
+// x is a normal number here (the caller clamps at 1e-300): no special cases, no branches.
+__device__ __forceinline__ double log_pos(double x, const double2 *__restrict__ tab)
+{
+  const long long bits = __double_as_longlong(x);
+  const int hi = (int)(bits >> 32), ex = (hi >> 20) & 0x7ff;
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);   // [1, 2)
+  const double2 t = tab[(hi >> 14) & 63];
+  const double d = fma(m, t.x, -1.0);
+  double q = fma(d, 1. / 7., -1. / 6.);
+  q = fma(d, q, 0.2); q = fma(d, q, -0.25); q = fma(d, q, 1. / 3.); q = fma(d, q, -0.5);
+  const double p = fma(d * d, q, d);
+  return fma((double)(ex - 1023), 0.693147180559945309417, t.y + p);
+}
+__global__ void __launch_bounds__(128, 4) k_diag_cell(const double *__restrict__ planes, double *__restrict__ part, int Nv, int sv,
                                                    double dv, double Lv, int homogeneous)
 {
   __shared__ double red[4 * 32];
+  __shared__ double2 ltab[64];
+  if (threadIdx.x < 64) {
+    const double rc = 1.0 / (1.0 + (threadIdx.x + 0.5) / 64.);
+    ltab[threadIdx.x] = make_double2(rc, -log(rc));
+  }
+  __syncthreads();
   const long long cell = blockIdx.x;
   const double *u = planes + ((cell + 1) * 6) * (long long)sv;
   double v[4] = {0., 0., 0., 0.};
@@ -356,6 +380,7 @@ __global__ void __launch_bounds__(256) k_diag_cell(const double *__restrict__ pl
     double e = 0., avg = 0.;
     for (int a = 0; a < nxq; a++)
       for (int b = 0; b < 5; b++)
+        #pragma unroll
         for (int cc = 0; cc < 5; cc++) {
           // same expressions, same association as the one-line form: only what does not depend on d is computed once
           const double xs = homogeneous ? 0. : 0.5 * c_gt[a], x1 = 0.5 * c_gt[b], x2 = 0.5 * c_gt[cc];
@@ -366,7 +391,9 @@ __global__ void __launch_bounds__(256) k_diag_cell(const double *__restrict__ pl
             const double x3 = 0.5 * c_gt[d];
             const double f = head + U4 * x3 + U5 * (q12 + x3 * x3);
             const double w = wabc * c_gw[d];
-            if (f > 0) e += w * f * log(f);
+            // below 1e-300 the integrand is below 1e-297: the clamp keeps log_pos on normal numbers and changes nothing
+            const double lf = log_pos(fmax(f, 1e-300), ltab);
+            e = f > 0 ? fma(w * f, lf, e) : e;
             avg += w * f;
           }
         }
@@ -391,8 +418,11 @@ __global__ void k_diag_fold(const double *__restrict__ part, double *__restrict_
 int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev)
 {
   double *part = c->d_B;   // free outside the projection
-  const int chunks = 16;   // blocks per x cell
-  k_diag_cell<<<dim3(c->ncell, chunks), 256, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv, c->p.homogeneous);
+  // blocks per x cell: four 128-thread blocks fit an SM, so a grid that is a multiple of 4 x 148 runs in full waves
+  // (32 cells x 37 chunks = 2 waves); the 5^4-point rule makes this kernel FP64-bound, a ragged last wave costs real time
+  int chunks = 148 / std::gcd(c->ncell, 148);
+  while (chunks > 1 && c->sv / chunks < 128) chunks = (chunks + 1) / 2;
+  k_diag_cell<<<dim3(c->ncell, chunks), 128, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv, c->p.homogeneous);
   LP_LAUNCHED(c);
   const double dv = c->tab.dv, dx = c->p.Lx / c->p.Nx;
   const double scale = 0.5 * dv * 0.5 * dv * 0.5 * dv * (c->p.homogeneous ? 1. : 0.5 * dx);

@@ -151,6 +151,13 @@ int lpgpu_finalize(lpgpu_ctx *c)
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
   for (int k = 0; k < 2; k++) if (c->gexec[k]) cudaGraphExecDestroy(c->gexec[k]);
   if (c->gstream) cudaStreamDestroy(c->gstream);
+  if (c->diag_view) delete c->diag_view;
+  if (c->d_snap) cudaFree(c->d_snap);
+  if (c->d_diag_scratch) cudaFree(c->d_diag_scratch);
+  if (c->h_diag) cudaFreeHost(c->h_diag);
+  if (c->diag_stream) cudaStreamDestroy(c->diag_stream);
+  if (c->diag_snap) cudaEventDestroy(c->diag_snap);
+  if (c->diag_done) cudaEventDestroy(c->diag_done);
   for (lpgpu_ctx *v : c->groups) delete v;             // views own nothing on the device
   for (cudaStream_t st : c->group_streams) if (st) cudaStreamDestroy(st);
   for (cudaEvent_t ev : c->group_done) if (ev) cudaEventDestroy(ev);
@@ -621,6 +628,60 @@ int lpgpu_diagnostics_partial(lpgpu_ctx *c, double *out4)
   LP_TRY(lp_launch_diagnostics(c, c->d_U[0], c->d_lam));
   LP_CUDA(cudaMemcpyAsync(out4, c->d_lam, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+int lpgpu_diagnostics_begin(lpgpu_ctx *c)
+{
+  LP_ENTER(c);
+  if (c->diag_pending) { lp_set_error("lpgpu_diagnostics_begin: a snapshot is already in flight (call lpgpu_diagnostics_end first)"); return LPGPU_EINVAL; }
+  const size_t nst = (size_t)6 * c->sv * (c->ncell + 2);
+  if (!c->diag_view) {
+    // partial-sum scratch: moments 5 x 16 per cell, entropy/negativity 4 x <=148 per cell, density 2 x 32 per cell
+    const size_t nscr = (size_t)c->ncell * (4 * 148 + 64 + 2) + 64;
+    LP_TRY(dev_alloc(&c->d_snap, nst));
+    LP_TRY(dev_alloc(&c->d_diag_scratch, nscr));
+    LP_CUDA(cudaMallocHost((void **)&c->h_diag, (size_t)(9 + 2 * c->ncell) * sizeof(double)));
+    LP_CUDA(cudaStreamCreateWithFlags(&c->diag_stream, cudaStreamNonBlocking));
+    LP_CUDA(cudaEventCreateWithFlags(&c->diag_snap, cudaEventDisableTiming));
+    LP_CUDA(cudaEventCreateWithFlags(&c->diag_done, cudaEventDisableTiming));
+    lpgpu_ctx *v = new (std::nothrow) lpgpu_ctx(*c);
+    if (!v) return LPGPU_ENOMEM;
+    v->is_view = true; v->stream = c->diag_stream; v->launches = 0; v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
+    v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->prof_on = 0; v->prof_ev.clear(); v->diag_view = nullptr;
+    double *q = c->d_diag_scratch;
+    v->d_mom = q; q += 8; v->d_lam = q; q += 8;
+    v->d_ms_local = q; q += 2 * c->ncell; v->d_ms_part = q; q += (size_t)64 * c->ncell;
+    v->d_B = q;                                  // 4 x 148 per cell
+    c->diag_view = v;
+  }
+  lpgpu_ctx *v = c->diag_view;
+  LP_CUDA(cudaStreamWaitEvent(c->stream, c->diag_done, 0));      // the previous snapshot has been consumed
+  LP_CUDA(cudaMemcpyAsync(c->d_snap, c->d_U[0], nst * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  LP_CUDA(cudaEventRecord(c->diag_snap, c->stream));
+  LP_CUDA(cudaStreamWaitEvent(v->stream, c->diag_snap, 0));
+  LP_TRY(lp_launch_moments(v, c->d_snap));
+  LP_CUDA(cudaMemcpyAsync(c->h_diag, v->d_mom, 5 * sizeof(double), cudaMemcpyDeviceToHost, v->stream));
+  if (!c->p.homogeneous) {
+    LP_TRY(lp_launch_field_reduce(v, c->d_snap));
+    LP_CUDA(cudaMemcpyAsync(c->h_diag + 9, v->d_ms_local, (size_t)2 * c->ncell * sizeof(double), cudaMemcpyDeviceToHost, v->stream));
+  }
+  LP_TRY(lp_launch_diagnostics(v, c->d_snap, v->d_lam));
+  LP_CUDA(cudaMemcpyAsync(c->h_diag + 5, v->d_lam, 4 * sizeof(double), cudaMemcpyDeviceToHost, v->stream));
+  LP_CUDA(cudaEventRecord(c->diag_done, v->stream));
+  c->launches += v->launches; v->launches = 0;
+  c->diag_pending = true;
+  return LPGPU_OK;
+}
+int lpgpu_diagnostics_end(lpgpu_ctx *c, double *out5, double *ms_local_host, double *out4)
+{
+  LP_ENTER(c);
+  if (!c->diag_pending) { lp_set_error("lpgpu_diagnostics_end: no snapshot in flight"); return LPGPU_EINVAL; }
+  LP_CUDA(cudaEventSynchronize(c->diag_done));
+  c->diag_pending = false;
+  if (out5) memcpy(out5, c->h_diag, 5 * sizeof(double));
+  if (out4) memcpy(out4, c->h_diag + 5, 4 * sizeof(double));
+  if (ms_local_host && !c->p.homogeneous) memcpy(ms_local_host, c->h_diag + 9, (size_t)2 * c->ncell * sizeof(double));
   return LPGPU_OK;
 }
 

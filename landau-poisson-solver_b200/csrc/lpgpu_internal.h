@@ -80,6 +80,12 @@ struct lpgpu_ctx {
   std::vector<cudaEvent_t> group_done;
   cudaEvent_t group_fork;
   bool is_view;
+  // ---- diagnostics of a snapshot on a side stream (lpgpu_diagnostics_begin/_end)
+  lpgpu_ctx *diag_view;            // stream = diag_stream, scratch and result arrays of its own
+  cudaStream_t diag_stream;
+  cudaEvent_t diag_snap, diag_done;
+  double *d_snap, *d_diag_scratch, *h_diag;   // state copy (with halo planes); partials; pinned results (5 + 4 + 2*ncell)
+  bool diag_pending;
   int prof_on;            // 0 off, 1 events around the whole ComputeQ chain, 2 around its dominant kernel (F2) only
   std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
   size_t prof_used;        // events used so far

@@ -46,6 +46,7 @@ EXPORTS = [
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
     "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums",
+    "lpgpu_diagnostics_begin", "lpgpu_diagnostics_end",
 ]
 
 _lib = None
@@ -78,6 +79,8 @@ def load_library():
     L.lpgpu_conserveMoments.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.lpgpu_get_stage_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.lpgpu_moments_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lpgpu_diagnostics_begin.argtypes = [C.c_void_p]
+    L.lpgpu_diagnostics_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpgpu_profile_computeQ.argtypes = [C.c_void_p, C.c_int]
     L.lpgpu_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.lpgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -270,6 +273,17 @@ class LPGpu:
         out = np.empty(4)
         self._check(self.L.lpgpu_diagnostics_partial(self.h, _ptr(out)))
         return out
+
+    def diagnostics_begin(self):
+        """Snapshot the state and enqueue its moment / density / entropy / negativity reductions on a side stream; the
+        caller enqueues the next timestep, then collects with diagnostics_end()."""
+        self._check(self.L.lpgpu_diagnostics_begin(self.h))
+
+    def diagnostics_end(self):
+        """(m5, ms_local, d4) of the snapshot: what moments_partial() and diagnostics_partial() return for that state."""
+        m5, ms, d4 = np.empty(5), np.zeros(2 * self.ncell), np.empty(4)
+        self._check(self.L.lpgpu_diagnostics_end(self.h, _ptr(m5), _ptr(ms), _ptr(d4)))
+        return m5, ms, d4
 
     def moments(self):
         """mass, P1, P2, P3, KiE, EleE for a single-shard context."""

@@ -263,23 +263,32 @@ def shard_range(Nx, world, rank):
     return rank * n, n
 
 
-def exchange_stage(dist, rank, world, ms_local, ms_all, send_left, send_right, recv_left, recv_right):
-    """The one exchange step of an SSP-RK3 stage: all-gather of (m_i, s_i) and the periodic halo
-    planes.  Arguments are torch tensors (CUDA for NCCL, CPU for gloo) aliasing the buffers of
-    lpgpu_exchange.  recv_left <- left neighbour's send_right, recv_right <- right neighbour's
-    send_left."""
+def exchange_density(dist, world, ms_local, ms_all, group=None):
+    """All-gather of the local (m_i, s_i) block: every rank then evaluates the same Nx-long field scan."""
     if ms_all.is_cuda:
-        dist.all_gather_into_tensor(ms_all, ms_local)
+        dist.all_gather_into_tensor(ms_all, ms_local, group=group)
     else:
-        dist.all_gather(list(ms_all.chunk(world)), ms_local)
+        dist.all_gather(list(ms_all.chunk(world)), ms_local, group=group)
+
+
+def exchange_halo(dist, rank, world, send_left, send_right, recv_left, recv_right, group=None):
+    """The periodic halo planes: recv_left <- left neighbour's send_right, recv_right <- right neighbour's send_left."""
     left, right = (rank - 1) % world, (rank + 1) % world
     # One grouped launch (ncclGroupStart/End): separately issued NCCL sends would deadlock, each rank's
     # send waiting for a receive queued behind the peer's own send.  Order matters when left == right
     # (world == 2): the first send to a peer pairs with the first receive from it on the other side.
-    ops = [dist.P2POp(dist.isend, send_right, right), dist.P2POp(dist.isend, send_left, left),
-           dist.P2POp(dist.irecv, recv_left, left), dist.P2POp(dist.irecv, recv_right, right)]
+    ops = [dist.P2POp(dist.isend, send_right, right, group), dist.P2POp(dist.isend, send_left, left, group),
+           dist.P2POp(dist.irecv, recv_left, left, group), dist.P2POp(dist.irecv, recv_right, right, group)]
     for r in dist.batch_isend_irecv(ops):
         r.wait()
+
+
+def exchange_stage(dist, rank, world, ms_local, ms_all, send_left, send_right, recv_left, recv_right):
+    """The one exchange step of an SSP-RK3 stage: all-gather of (m_i, s_i) and the periodic halo
+    planes.  Arguments are torch tensors (CUDA for NCCL, CPU for gloo) aliasing the buffers of
+    lpgpu_exchange."""
+    exchange_density(dist, world, ms_local, ms_all)
+    exchange_halo(dist, rank, world, send_left, send_right, recv_left, recv_right)
 
 
 class _DeviceBuffer:
@@ -317,6 +326,8 @@ class ShardedSolver:
             self.torch = torch
             if stream is None:
                 self.g.set_stream(torch.cuda.current_stream().cuda_stream)
+            self.halo_group = dist.new_group(backend="nccl")   # collective: every rank constructs its solver
+            self.halo_stream = torch.cuda.Stream(device=device)
             self._ex = []
             for stage in range(3):
                 e = self.g.exchange_info(stage)
@@ -345,13 +356,20 @@ class ShardedSolver:
         if self.world == 1:
             self.g.advect_rk3()
             return
+        torch = self.torch
+        main = self.stream if self.stream is not None else torch.cuda.current_stream()
         for stage in range(3):
+            ex = self._ex[stage]
+            # the halo planes travel on their own stream and communicator while the density reduction, its all-gather
+            # and the field scan run: one NCCL latency per stage on the critical path instead of two
+            self.halo_stream.wait_stream(main)                 # this stage's input planes are final
+            with torch.cuda.stream(self.halo_stream):
+                exchange_halo(self.dist, self.rank, self.world, ex["send_left"], ex["send_right"], ex["recv_left"], ex["recv_right"],
+                              group=self.halo_group)
             self.g.advect_reduce(stage)
-            if self.stream is not None:
-                with self.torch.cuda.stream(self.stream):
-                    exchange_stage(self.dist, self.rank, self.world, **self._ex[stage])
-            else:
-                exchange_stage(self.dist, self.rank, self.world, **self._ex[stage])
+            with torch.cuda.stream(main):
+                exchange_density(self.dist, self.world, ex["ms_local"], ex["ms_all"])
+            main.wait_stream(self.halo_stream)
             self.g.advect_apply(stage)
 
     def step(self, nsteps=1, wait=True):
@@ -366,6 +384,27 @@ class ShardedSolver:
                 self.g.collide_step(wait=False)      # enqueue only: the host runs ahead into the next exchange
         if wait:
             self.g.synchronize()
+
+    def diagnostics_begin(self):
+        """Snapshot the state now on the device and start its per-step diagnostics (LP_ompi.cpp:817-849) on a side
+        stream; enqueue the next timestep, then call diagnostics_end()."""
+        self.g.diagnostics_begin()
+
+    def diagnostics_end(self):
+        """(moments[6], entropy, KiE ratio, number of negative cells) of the snapshot, global over the ranks."""
+        m5, ms, d4 = self.g.diagnostics_end()
+        if self.world > 1 and not self.homogeneous:
+            torch = self.torch
+            t = torch.from_numpy(np.concatenate([m5, d4])).cuda()
+            self.dist.all_reduce(t)
+            red = t.cpu().numpy()
+            m5, d4 = red[:5], red[5:]
+            loc = torch.from_numpy(ms).cuda()
+            allms = torch.empty(2 * self.g.Nx, dtype=torch.float64, device=loc.device)
+            self.dist.all_gather_into_tensor(allms, loc)
+            ms = allms.cpu().numpy()
+        ele = 0. if self.homogeneous else self.g.eleE_from_ms(ms)
+        return np.concatenate([m5, [ele]]), d4[0], (d4[2] / d4[1] if d4[1] != 0 else 0.), d4[3]
 
     def moments(self):
         """Global mass, P1..3, KiE, EleE (LP_ompi.cpp:820-827) on every rank."""

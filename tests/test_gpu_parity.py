@@ -262,6 +262,32 @@ def test_entropy_and_negativity_diagnostics(small, pkg):
     gh.close()
 
 
+def test_overlapped_diagnostics_equal_synchronous_ones(small, pkg):
+    """lpgpu_diagnostics_begin/_end: the diagnostics of step k over a snapshot, on a side stream, while step k+1 runs --
+    the same numbers, bit for bit, as the synchronous calls made between the two steps."""
+    ora, g = small
+    U = _perturbed(ora, 11)
+    g.upload_U(U)
+    want = []
+    for _ in range(3):
+        g.step(1)
+        want.append((g.moments_partial(), g.diagnostics_partial()))
+    final = g.download_U()
+    g.upload_U(U)
+    got = []
+    for k in range(3):
+        g.step(1, wait=False)
+        if k:
+            got.append(g.diagnostics_end())
+        g.diagnostics_begin()
+    got.append(g.diagnostics_end())
+    assert np.array_equal(g.download_U(), final)
+    for ((m5, ms), d4), (m5b, msb, d4b) in zip(want, got):
+        assert np.array_equal(m5, m5b) and np.array_equal(ms, msb) and np.array_equal(d4, d4b)
+    with pytest.raises(Exception):
+        g.diagnostics_end()                                # nothing in flight
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_full_step_each_ComputeQ_variant(pkg, variant):
     """Every ComputeQ kernel (simple direct, FFT convolutions, tiled direct) through a whole timestep."""

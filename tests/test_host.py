@@ -128,6 +128,13 @@ def _gloo_worker(rank, world, port, q):
     solver.exchange_stage(dist, rank, world, ms_local, ms_all, send_left, send_right, recv_left, recv_right)
     ok = (recv_left == float((x0 - 1) % Nx)).all() and (recv_right == float((x0 + n) % Nx)).all()
     ok = ok and ms_all.tolist() == [v for i in range(Nx) for v in (float(i), -float(i))]
+    # the order the sharded driver uses: halo planes on their own communicator first, then the density all-gather
+    grp = dist.new_group(backend="gloo")
+    recv_left.zero_(); recv_right.zero_(); ms_all.zero_()
+    solver.exchange_halo(dist, rank, world, send_left, send_right, recv_left, recv_right, group=grp)
+    solver.exchange_density(dist, world, ms_local, ms_all)
+    ok = ok and (recv_left == float((x0 - 1) % Nx)).all() and (recv_right == float((x0 + n) % Nx)).all()
+    ok = ok and ms_all.tolist() == [v for i in range(Nx) for v in (float(i), -float(i))]
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
