@@ -275,8 +275,10 @@ def main():
 
     NFLIGHT = 3                                           # copy-in, kernels and copy-out of three batches overlap
     streams = [torch.cuda.Stream() for _ in range(NFLIGHT)]
-    pair = [solver.ShardedSolver(Nx, NV, NSPEC, homogeneous=False, rank=rank, world=world, device=local, dist=dist, stream=st, **PHYS)
-            for st in streams]
+    # several contexts in flight per rank: their exchanges go through NCCL (one communicator orders them the same way on
+    # every rank); flag-synchronised peer writes of independent contexts could wait on each other across hardware queues
+    pair = [solver.ShardedSolver(Nx, NV, NSPEC, homogeneous=False, rank=rank, world=world, device=local, dist=dist, stream=st,
+                                 exchange="nccl", **PHYS) for st in streams]
     hosts_t = [host] + [host.clone().pin_memory() for _ in range(NFLIGHT - 1)]
     hosts = [h.numpy() for h in hosts_t]
     backs_t = [torch.empty_like(host).pin_memory() for _ in range(NFLIGHT)]
@@ -377,7 +379,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(world), l2="per-GPU working set %.0f MB > 126 MB L2; no flush between steps" % ws_mb),
+                "config": dict(workload_config(world), l2="per-GPU working set %.0f MB > 126 MB L2; no flush between steps" % ws_mb,
+                               exchange=("none (one GPU)" if world == 1 else
+                                         "peer memory: kernels write halo planes and densities into the neighbours' buffers (CUDA IPC), flag-synchronised; no NCCL call in the timestep" if s.exchange == "peer" else
+                                         "NCCL all-gather + send/recv per SSP-RK3 stage")),
                 "timesteps_per_s": args.steps / t_dev, "roofline": roof, "roofline_direct": roof_direct, "e2e": e2e, "as_reference_loop": as_reference,
                 "gpu_launches": int(launches), "clocks": clocks}
 

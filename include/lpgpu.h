@@ -120,6 +120,22 @@ int lpgpu_advect_reduce(lpgpu_ctx *c, int stage);
  * SSP combination of this stage (asynchronous on the context's stream) */
 int lpgpu_advect_apply(lpgpu_ctx *c, int stage);
 
+/* Peer-memory exchange: with one process per GPU on one node, the ranks map each other's stage buffers and a small
+ * mailbox (CUDA IPC); from then on every rank writes its boundary planes straight into its neighbours' halo planes and its
+ * densities into every rank's mailbox, followed by a flag, from kernels on the context's stream.  This replaces the
+ * reference's MPI_Bcast(U) / the all-gather + send/recv above: lpgpu_advect_rk3 and lpgpu_step* then work on a shard,
+ * the host makes no call per stage, and the whole timestep replays as one CUDA graph.
+ *   every rank:  lpgpu_peer_export(ctx, blob)  ->  all-gather the blobs (MPI_Allgather / torch.distributed)  ->
+ *                lpgpu_peer_import(ctx, rank, world, blobs)     (rank r owns cells [r Nx/world, (r+1) Nx/world), world <= 8)
+ * All ranks must then execute the same sequence of steps, with one peer-mapped context in flight per process (the
+ * waits of two independent contexts could block each other across hardware queues); synchronise the ranks before
+ * lpgpu_finalize.
+ * lpgpu_peer_status returns an error if a bounded wait (10 s) for a peer ever timed out. */
+#define LPGPU_PEER_HANDLE_BYTES 256
+int lpgpu_peer_export(lpgpu_ctx *c, void *blob);
+int lpgpu_peer_import(lpgpu_ctx *c, int rank, int world, const void *blobs);
+int lpgpu_peer_status(lpgpu_ctx *c, long long *timeouts);
+
 /* ---- fine-grained entry points (host buffers, B cells per call) -------------------------- */
 /* void setInit_spectral(double *U, double **f)            SetInit_1.h:48 ; f: x_count*N^3 */
 int lpgpu_setInit_spectral(lpgpu_ctx *c, double *f_host);

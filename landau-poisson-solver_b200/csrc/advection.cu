@@ -300,6 +300,101 @@ int lp_launch_local_halo(lpgpu_ctx *c, double *planes)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-memory exchange (replaces the MPI_Bcast / the NCCL all-gather + halo send/recv of the sharded run).
+// Flags carry epochs that only grow, so nothing is ever reset: the publisher bumps its own epoch and stores it into the
+// peers' flag words after its data (release at system scope); a consumer waits until every flag has reached its own
+// epoch -- all ranks execute the same sequence of stages.  A rank can be at most one stage ahead of a peer (its next
+// stage needs that peer's next densities), hence two density buffers selected by the epoch's parity; the halo planes
+// belong to three different stage buffers.  Waits are bounded (10 s): on a timeout the kernel counts it in the mailbox
+// and goes on, so that a dead peer gives wrong numbers and an error from lpgpu_peer_status, not a hung GPU.
+typedef unsigned long long ull;
+__device__ __forceinline__ void st_release_sys(ull *p, ull v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ ull ld_acquire_sys(const ull *p) { ull v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ ull global_ns() { ull t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+struct PeerBoxes { ull *box[LP_MAX_PEERS]; };
+
+// first owned plane -> left neighbour's right halo, last owned plane -> right neighbour's left halo; the last block to
+// finish raises the two flags
+__global__ void __launch_bounds__(256) k_peer_put_halo(const double2 *__restrict__ first, const double2 *__restrict__ last, double2 *__restrict__ left_dst,
+                                                       double2 *__restrict__ right_dst, long long n2, ull *mbox, ull *left_flag, ull *right_flag)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n2; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n2) left_dst[i] = first[i];
+    else right_dst[i - n2] = last[i - n2];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const ull done = atomicAdd(mbox + LP_MB_PUTCNT, 1ULL);
+    if (done == gridDim.x - 1) {
+      mbox[LP_MB_PUTCNT] = 0;
+      const ull e = mbox[LP_MB_EPOCH_H] + 1;
+      mbox[LP_MB_EPOCH_H] = e;
+      __threadfence_system();
+      st_release_sys(left_flag, e);       // the left neighbour's "from the right" flag
+      st_release_sys(right_flag, e);      // the right neighbour's "from the left" flag
+    }
+  }
+}
+// this rank's (m_i, s_i) into the parity buffer of every mailbox, then the flags
+__global__ void __launch_bounds__(256) k_peer_publish_density(const double *__restrict__ ms_local, int n2, int off2, int Nx2, PeerBoxes pb, int world, int rank)
+{
+  ull *mine = pb.box[rank];
+  const ull e = mine[LP_MB_EPOCH_D] + 1;
+  for (int t = threadIdx.x; t < n2 * world; t += blockDim.x) {
+    const int r = t / n2, i = t % n2;
+    reinterpret_cast<double *>(pb.box[r] + LP_MB_MS)[(e & 1) * Nx2 + off2 + i] = ms_local[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) st_release_sys(pb.box[threadIdx.x] + LP_MB_DFLAG + rank, e);
+  if (threadIdx.x == 0) mine[LP_MB_EPOCH_D] = e;
+}
+// wait for every rank's densities and both halo planes of this stage; gather the densities into ms_all
+__global__ void __launch_bounds__(256) k_peer_wait(ull *mbox, int world, double *__restrict__ ms_all, int Nx2)
+{
+  const ull ed = mbox[LP_MB_EPOCH_D], eh = mbox[LP_MB_EPOCH_H];
+  if (threadIdx.x < world + 2) {
+    const ull *flag = threadIdx.x < world ? mbox + LP_MB_DFLAG + threadIdx.x : mbox + LP_MB_HFLAG + (threadIdx.x - world);
+    const ull want = threadIdx.x < world ? ed : eh;
+    const ull t0 = global_ns();
+    while (ld_acquire_sys(flag) < want) {
+      __nanosleep(200);
+      if (global_ns() - t0 > 10000000000ULL) { atomicAdd(mbox + LP_MB_ERR, 1ULL); break; }
+    }
+  }
+  __syncthreads();
+  const double *src = reinterpret_cast<const double *>(mbox + LP_MB_MS) + (ed & 1) * Nx2;
+  for (int i = threadIdx.x; i < Nx2; i += blockDim.x) ms_all[i] = __ldcg(src + i);
+}
+int lp_launch_peer_put_halo(lpgpu_ctx *c, int stage)
+{
+  const long long plane = (long long)6 * c->sv;
+  const double *in = c->d_U[stage];
+  double *left_dst = c->peer_U[0][stage] + plane * (c->ncell + 1), *right_dst = c->peer_U[1][stage];
+  const int left = (c->peer_rank + c->peer_world - 1) % c->peer_world, right = (c->peer_rank + 1) % c->peer_world;
+  k_peer_put_halo<<<148, 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(in + plane), reinterpret_cast<const double2 *>(in + plane * c->ncell),
+                                              reinterpret_cast<double2 *>(left_dst), reinterpret_cast<double2 *>(right_dst), plane / 2, c->d_mbox,
+                                              c->peer_mbox[left] + LP_MB_HFLAG + 1, c->peer_mbox[right] + LP_MB_HFLAG + 0);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+int lp_launch_peer_publish_density(lpgpu_ctx *c)
+{
+  PeerBoxes pb;
+  for (int r = 0; r < LP_MAX_PEERS; r++) pb.box[r] = r < c->peer_world ? c->peer_mbox[r] : nullptr;
+  k_peer_publish_density<<<1, 256, 0, c->stream>>>(c->d_ms_local, 2 * c->ncell, 2 * c->p.x_begin, 2 * c->p.Nx, pb, c->peer_world, c->peer_rank);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+int lp_launch_peer_wait(lpgpu_ctx *c)
+{
+  k_peer_wait<<<1, 256, 0, c->stream>>>(c->d_mbox, c->peer_world, c->d_ms_all, 2 * c->p.Nx);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // computeMass / computeMomentum / computeKiE (MomentCalculations.cpp:23-131) partial sums over the
 // local cells: one block per cell, then one block folds the per-cell partials in cell order.
 __global__ void __launch_bounds__(256) k_moments_cell(const double *__restrict__ planes, double *__restrict__ part, int Nv, int sv,

@@ -151,6 +151,8 @@ int lpgpu_finalize(lpgpu_ctx *c)
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
   for (int k = 0; k < 2; k++) if (c->gexec[k]) cudaGraphExecDestroy(c->gexec[k]);
   if (c->gstream) cudaStreamDestroy(c->gstream);
+  for (void *p : c->peer_opened) cudaIpcCloseMemHandle(p);
+  if (c->d_mbox) cudaFree(c->d_mbox);
   if (c->diag_view) delete c->diag_view;
   if (c->d_snap) cudaFree(c->d_snap);
   if (c->d_diag_scratch) cudaFree(c->d_diag_scratch);
@@ -250,7 +252,20 @@ int lpgpu_advect_apply(lpgpu_ctx *c, int stage)
 }
 static int advect_rk3_async(lpgpu_ctx *c)
 {
-  if (c->ncell != c->p.Nx) { lp_set_error("lpgpu_advect_rk3: context is a shard; drive the per-stage calls instead"); return LPGPU_EINVAL; }
+  if (c->ncell != c->p.Nx && c->peer_ready) {
+    // sharded, peers mapped: the exchange is kernels on this stream (advection.cu), no host or NCCL call per stage
+    for (int s = 0; s < 3; s++) {
+      LP_TRY(lp_launch_peer_put_halo(c, s));
+      LP_TRY(lp_launch_field_reduce(c, c->d_U[s]));
+      LP_TRY(lp_launch_peer_publish_density(c));
+      LP_TRY(lp_launch_peer_wait(c));
+      LP_TRY(lp_launch_wall_halo(c, c->d_U[s]));
+      LP_TRY(lp_launch_field_scan(c));
+      LP_TRY(lp_launch_dg_stage(c, s));
+    }
+    return LPGPU_OK;
+  }
+  if (c->ncell != c->p.Nx) { lp_set_error("lpgpu_advect_rk3: context is a shard; map the peers (lpgpu_peer_import) or drive the per-stage calls"); return LPGPU_EINVAL; }
   for (int s = 0; s < 3; s++) {
     LP_TRY(lp_launch_local_halo(c, c->d_U[s]));
     LP_TRY(lp_launch_field_reduce(c, c->d_U[s]));
@@ -266,6 +281,69 @@ int lpgpu_advect_rk3(lpgpu_ctx *c)
   LP_TRY(check_stage(c, 0));
   LP_TRY(advect_rk3_async(c));
   LP_CUDA(cudaStreamSynchronize(c->stream));
+  return LPGPU_OK;
+}
+
+// ---- peer-memory exchange (CUDA IPC, one process per GPU on one node) ---------------------------
+static int peer_alloc(lpgpu_ctx *c)
+{
+  if (c->d_mbox) return LPGPU_OK;
+  const size_t words = LP_MB_MS + (size_t)4 * c->p.Nx;
+  LP_CUDA(cudaMalloc((void **)&c->d_mbox, words * sizeof(unsigned long long)));
+  LP_CUDA(cudaMemset(c->d_mbox, 0, words * sizeof(unsigned long long)));
+  LP_CUDA(cudaDeviceSynchronize());
+  return LPGPU_OK;
+}
+int lpgpu_peer_export(lpgpu_ctx *c, void *blob)
+{
+  LP_ENTER(c);
+  if (!blob || c->p.homogeneous) { lp_set_error("lpgpu_peer_export: needs an inhomogeneous shard and a buffer of LPGPU_PEER_HANDLE_BYTES"); return LPGPU_EINVAL; }
+  static_assert(4 * sizeof(cudaIpcMemHandle_t) <= LPGPU_PEER_HANDLE_BYTES, "handle blob too small");
+  LP_TRY(peer_alloc(c));
+  cudaIpcMemHandle_t h[4];
+  LP_CUDA(cudaIpcGetMemHandle(&h[0], c->d_mbox));
+  for (int s = 0; s < 3; s++) LP_CUDA(cudaIpcGetMemHandle(&h[1 + s], c->d_U[s]));
+  memset(blob, 0, LPGPU_PEER_HANDLE_BYTES);
+  memcpy(blob, h, sizeof(h));
+  return LPGPU_OK;
+}
+int lpgpu_peer_import(lpgpu_ctx *c, int rank, int world, const void *blobs)
+{
+  LP_ENTER(c);
+  if (!blobs || world < 2 || world > LP_MAX_PEERS || rank < 0 || rank >= world || c->p.homogeneous) { lp_set_error("lpgpu_peer_import: bad arguments (2 <= world <= 8, inhomogeneous shard)"); return LPGPU_EINVAL; }
+  if (c->p.Nx % world || c->ncell != c->p.Nx / world || c->p.x_begin != rank * c->ncell) { lp_set_error("lpgpu_peer_import: rank r must own the r-th block of Nx/world cells"); return LPGPU_EINVAL; }
+  if (c->peer_ready) { lp_set_error("lpgpu_peer_import: peers already mapped"); return LPGPU_EINVAL; }
+  LP_TRY(peer_alloc(c));
+  const int left = (rank + world - 1) % world, right = (rank + 1) % world;
+  for (int r = 0; r < world; r++) {
+    cudaIpcMemHandle_t h[4];
+    memcpy(h, (const char *)blobs + (size_t)r * LPGPU_PEER_HANDLE_BYTES, sizeof(h));
+    if (r == rank) { c->peer_mbox[r] = c->d_mbox; continue; }
+    void *p = nullptr;
+    LP_CUDA(cudaIpcOpenMemHandle(&p, h[0], cudaIpcMemLazyEnablePeerAccess));
+    c->peer_opened.push_back(p);
+    c->peer_mbox[r] = (unsigned long long *)p;
+    if (r == left || r == right)
+      for (int s = 0; s < 3; s++) {
+        LP_CUDA(cudaIpcOpenMemHandle(&p, h[1 + s], cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened.push_back(p);
+        if (r == left) c->peer_U[0][s] = (double *)p;
+        if (r == right) c->peer_U[1][s] = (double *)p;
+      }
+  }
+  c->peer_rank = rank; c->peer_world = world; c->peer_ready = true;
+  return LPGPU_OK;
+}
+int lpgpu_peer_status(lpgpu_ctx *c, long long *timeouts)
+{
+  LP_ENTER(c);
+  if (!timeouts) return LPGPU_EINVAL;
+  *timeouts = 0;
+  if (!c->d_mbox) return LPGPU_OK;
+  unsigned long long v = 0;
+  LP_CUDA(cudaMemcpy(&v, c->d_mbox + LP_MB_ERR, sizeof(v), cudaMemcpyDeviceToHost));
+  *timeouts = (long long)v;
+  if (v) { lp_set_error("peer exchange: a wait for a peer's flag timed out (a rank died or fell out of step)"); return LPGPU_ECUDA; }
   return LPGPU_OK;
 }
 

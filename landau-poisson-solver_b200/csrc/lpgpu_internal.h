@@ -6,6 +6,16 @@
 #include <vector>
 
 #define LP_ETAB_PAD 8
+#define LP_MAX_PEERS 8
+// mailbox, in 8-byte words: density flags (epoch published by rank r), halo flags (from the left, from the right
+// neighbour), timeout counter, own density epoch, own halo epoch, block counter of the halo put; then ms[2][2*Nx] doubles
+#define LP_MB_DFLAG 0
+#define LP_MB_HFLAG 8
+#define LP_MB_ERR 10
+#define LP_MB_EPOCH_D 11
+#define LP_MB_EPOCH_H 12
+#define LP_MB_PUTCNT 13
+#define LP_MB_MS 16
 
 // Host-side tables that depend only on (N, Nv, Lv): built once in lpgpu_init.
 struct LpTables {
@@ -80,6 +90,15 @@ struct lpgpu_ctx {
   std::vector<cudaEvent_t> group_done;
   cudaEvent_t group_fork;
   bool is_view;
+  // ---- peer-memory exchange of the sharded advection (one process per GPU on one node, CUDA IPC): every rank writes
+  //      its densities into all ranks' mailboxes and its boundary planes into its neighbours' halo planes, then raises a
+  //      flag; replaces the NCCL all-gather + send/recv, so the whole sharded timestep is one stream of kernels (one graph)
+  bool peer_ready;
+  int peer_rank, peer_world;
+  unsigned long long *d_mbox;            // own mailbox (layout: LP_MB_* below)
+  unsigned long long *peer_mbox[LP_MAX_PEERS];   // every rank's mailbox as mapped here ([peer_rank] = d_mbox)
+  double *peer_U[2][3];                  // left / right neighbour's three stage buffers as mapped here
+  std::vector<void *> peer_opened;       // cudaIpcOpenMemHandle results to close
   // ---- diagnostics of a snapshot on a side stream (lpgpu_diagnostics_begin/_end)
   lpgpu_ctx *diag_view;            // stream = diag_stream, scratch and result arrays of its own
   cudaStream_t diag_stream;
@@ -153,6 +172,11 @@ int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes);
 int lp_launch_field_scan(lpgpu_ctx *c);
 int lp_launch_dg_stage(lpgpu_ctx *c, int stage);
 int lp_launch_local_halo(lpgpu_ctx *c, double *planes);
+// peer-memory exchange of one stage: boundary planes into the neighbours' halos; densities into every mailbox;
+// wait for all of them (and copy the gathered densities to d_ms_all)
+int lp_launch_peer_put_halo(lpgpu_ctx *c, int stage);
+int lp_launch_peer_publish_density(lpgpu_ctx *c);
+int lp_launch_peer_wait(lpgpu_ctx *c);
 // Doping: Dirichlet wall planes into the halo planes that face a domain wall (no-op otherwise)
 int lp_launch_wall_halo(lpgpu_ctx *c, double *planes);
 int lp_launch_moments(lpgpu_ctx *c, const double *planes);

@@ -47,7 +47,9 @@ EXPORTS = [
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
     "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums",
     "lpgpu_diagnostics_begin", "lpgpu_diagnostics_end",
+    "lpgpu_peer_export", "lpgpu_peer_import", "lpgpu_peer_status",
 ]
+PEER_HANDLE_BYTES = 256
 
 _lib = None
 
@@ -80,6 +82,9 @@ def load_library():
     L.lpgpu_get_stage_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.lpgpu_moments_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpgpu_diagnostics_begin.argtypes = [C.c_void_p]
+    L.lpgpu_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.lpgpu_peer_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.lpgpu_peer_status.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     L.lpgpu_diagnostics_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpgpu_profile_computeQ.argtypes = [C.c_void_p, C.c_int]
     L.lpgpu_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
@@ -273,6 +278,23 @@ class LPGpu:
         out = np.empty(4)
         self._check(self.L.lpgpu_diagnostics_partial(self.h, _ptr(out)))
         return out
+
+    # -- peer-memory exchange of a sharded run (CUDA IPC)
+    def peer_export(self):
+        blob = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)
+        self._check(self.L.lpgpu_peer_export(self.h, _ptr(blob)))
+        return blob
+
+    def peer_import(self, rank, world, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        assert blobs.size == world * PEER_HANDLE_BYTES
+        self._check(self.L.lpgpu_peer_import(self.h, int(rank), int(world), _ptr(blobs)))
+
+    def peer_status(self):
+        """Raises if a bounded wait for a peer's flag ever timed out."""
+        n = C.c_longlong()
+        self._check(self.L.lpgpu_peer_status(self.h, C.byref(n)))
+        return n.value
 
     def diagnostics_begin(self):
         """Snapshot the state and enqueue its moment / density / entropy / negativity reductions on a side stream; the

@@ -302,10 +302,13 @@ class ShardedSolver:
     """One rank of the x-sharded solver.  world == 1 needs no process group."""
 
     def __init__(self, Nx, Nv, N, Lv, Lx, nu, dt, homogeneous=False, rank=0, world=1, device=0, dist=None, full_and_linear=False,
-                 stream=None, doping=None, linear_landau=False, mass_cons_only=False, gamma=-3):
+                 stream=None, doping=None, linear_landau=False, mass_cons_only=False, gamma=-3, exchange=None):
         """stream: a torch.cuda.Stream all work of this solver (kernels, copies, the NCCL exchange) is ordered on;
         None = torch's current stream for sharded runs, the library's default otherwise.  Two solvers on two streams
-        pipeline: the host<->device copies of one overlap the kernels of the other."""
+        pipeline: the host<->device copies of one overlap the kernels of the other.
+        exchange: "peer" (default on NCCL process groups) maps the ranks' buffers into each other (CUDA IPC): the halo
+        planes and densities of every SSP-RK3 stage are written straight into the peers' memory by kernels and the whole
+        timestep replays as one CUDA graph; "nccl" keeps the all-gather + send/recv per stage through torch.distributed."""
         self.rank, self.world, self.dist = rank, world, dist
         self.stream = stream
         self.homogeneous = bool(homogeneous)
@@ -319,6 +322,7 @@ class ShardedSolver:
         self.linear_landau = bool(linear_landau)
         self.nu = nu
         self._ex = None
+        self.exchange = None
         if stream is not None:
             self.g.set_stream(stream.cuda_stream)
         if world > 1 and not homogeneous:
@@ -326,6 +330,15 @@ class ShardedSolver:
             self.torch = torch
             if stream is None:
                 self.g.set_stream(torch.cuda.current_stream().cuda_stream)
+            if exchange is None:
+                exchange = os.environ.get("LPGPU_EXCHANGE", "peer")
+            self.exchange = exchange
+            if exchange == "peer":
+                mine = torch.from_numpy(self.g.peer_export()).cuda(device)
+                allb = torch.empty(world * mine.numel(), dtype=torch.uint8, device=mine.device)
+                dist.all_gather_into_tensor(allb, mine)       # also orders every rank's mailbox initialisation before any put
+                self.g.peer_import(rank, world, allb.cpu().numpy())
+                dist.barrier()
             self.halo_group = dist.new_group(backend="nccl")   # collective: every rank constructs its solver
             self.halo_stream = torch.cuda.Stream(device=device)
             self._ex = []
@@ -353,7 +366,7 @@ class ShardedSolver:
     def advect(self):
         if self.homogeneous:
             return
-        if self.world == 1:
+        if self.world == 1 or self.exchange == "peer":
             self.g.advect_rk3()
             return
         torch = self.torch
@@ -375,7 +388,7 @@ class ShardedSolver:
     def step(self, nsteps=1, wait=True):
         """nsteps passes of the while(t<nT) body (LP_ompi.cpp:662-813) without diagnostics.  wait=False only
         enqueues (pipelined callers: synchronize() before touching host buffers)."""
-        if self.world == 1 or self.homogeneous:
+        if self.world == 1 or self.homogeneous or self.exchange == "peer":
             self.g.step(nsteps, wait=wait)
             return
         for _ in range(nsteps):
@@ -422,6 +435,10 @@ class ShardedSolver:
         return np.concatenate([m5, [ele]])
 
     def close(self):
+        if self.world > 1 and not self.homogeneous and self.exchange == "peer":
+            self.g.synchronize()
+            self.g.peer_status()                 # raises if a wait for a peer ever timed out
+            self.dist.barrier()                  # nobody unmaps or frees while a peer may still write
         self.g.close()
 
 
