@@ -334,13 +334,13 @@ class ShardedSolver:
                 exchange = os.environ.get("LPGPU_EXCHANGE", "peer")
             self.exchange = exchange
             if exchange == "peer":
-                mine = torch.from_numpy(self.g.peer_export()).cuda(device)
-                allb = torch.empty(world * mine.numel(), dtype=torch.uint8, device=mine.device)
-                dist.all_gather_into_tensor(allb, mine)       # also orders every rank's mailbox initialisation before any put
-                self.g.peer_import(rank, world, allb.cpu().numpy())
+                blobs = [None] * world
+                dist.all_gather_object(blobs, self.g.peer_export().tobytes())   # also orders every rank's mailbox initialisation before any put
+                self.g.peer_import(rank, world, np.frombuffer(b"".join(blobs), dtype=np.uint8))
                 dist.barrier()
-            self.halo_group = dist.new_group(backend="nccl")   # collective: every rank constructs its solver
-            self.halo_stream = torch.cuda.Stream(device=device)
+            else:
+                self.halo_group = dist.new_group(backend="nccl")   # collective: every rank constructs its solver
+                self.halo_stream = torch.cuda.Stream(device=device)
             self._ex = []
             for stage in range(3):
                 e = self.g.exchange_info(stage)
