@@ -12,6 +12,7 @@ all-gather of the per-cell sums (m_i, s_i) and one periodic halo plane from each
 """
 import math
 import os
+import sys
 
 import numpy as np
 
@@ -334,11 +335,26 @@ class ShardedSolver:
                 exchange = os.environ.get("LPGPU_EXCHANGE", "peer")
             self.exchange = exchange
             if exchange == "peer":
+                # every rank must end up on the same exchange: a rank that cannot map its peers (no CUDA IPC between the
+                # processes, GPUs without peer access) sends everybody to the NCCL path
+                try:
+                    blob, err = self.g.peer_export().tobytes(), None
+                except lpgpu.LPGpuError as e:
+                    blob, err = b"", str(e)
                 blobs = [None] * world
-                dist.all_gather_object(blobs, self.g.peer_export().tobytes())   # also orders every rank's mailbox initialisation before any put
-                self.g.peer_import(rank, world, np.frombuffer(b"".join(blobs), dtype=np.uint8))
-                dist.barrier()
-            else:
+                dist.all_gather_object(blobs, blob)     # also orders every rank's mailbox initialisation before any put
+                if all(len(b) == lpgpu.PEER_HANDLE_BYTES for b in blobs):
+                    try:
+                        self.g.peer_import(rank, world, np.frombuffer(b"".join(blobs), dtype=np.uint8))
+                    except lpgpu.LPGpuError as e:
+                        err = str(e)
+                oks = [None] * world
+                dist.all_gather_object(oks, err is None)
+                if not all(oks):
+                    if rank == 0:
+                        print("lpsolver_b200: peer-memory exchange unavailable (%s); using NCCL" % (err or "on another rank"), file=sys.stderr)
+                    exchange = self.exchange = "nccl"
+            if exchange != "peer":
                 self.halo_group = dist.new_group(backend="nccl")   # collective: every rank constructs its solver
                 self.halo_stream = torch.cuda.Stream(device=device)
             self._ex = []
