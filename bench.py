@@ -224,6 +224,12 @@ def main():
     barrier()
     t_instr = max_over_ranks(e2.elapsed_time(e3) * 1e-3)
     cq_ms, cq_n = g.profile_read()
+    #     ... and once more with the events around the DG stage kernels of the advection (HBM-bound)
+    g.profile_computeQ(3)
+    barrier()
+    s.step(args.steps)
+    barrier()
+    dg_ms, dg_n = g.profile_read()
     g.profile_computeQ(False)
     clocks = sampler.finish()
 
@@ -350,6 +356,19 @@ def main():
                              "note": "F1+F2+F3 move 10+1 arrays of N^2 M complex once each way; at the measured HBM peak that is ~0.08 ms per launch chain, well under the FP64 time"},
                 "direct_form_equivalent_tflops": flop_per_eval(NSPEC) * s.x_count / avg_s / 1e12,
                 "note": "bound is the FP64 vector pipe (not hbm/tensor): the contraction is not dense, see DESIGN.md 4.1; direct_form_equivalent_tflops counts the 10 flop/pair of the O(N^6) sum this kernel replaces and exceeds the FP64 peak because the FFT form executes ~50x fewer flops for the same result (parity-tested)"}
+    roof_adv = None
+    if dg_n > 0:
+        # 384 B per DG cell per timestep = 96 (stage 1: 6 read + 6 written doubles) + 144 + 144 (12 read + 6
+        # written); the x- and v1-upwind neighbours a DG cell also reads are other cells' own coefficients, served by L1/L2
+        adv_bytes_per_launch = 128. * s.x_count * NV ** 3
+        avg_dg = dg_ms * 1e-3 / dg_n
+        hbm_peak = peaks.get("hbm_gbs") or 6500.
+        roof_adv = {"bound": "hbm", "kernel": "k_dg_stage<0..2> (SSP-RK3 stages of the DG upwind advection: I1, I2, I3, I5, H and the stage combination per DG cell)",
+                    "achieved": adv_bytes_per_launch / avg_dg / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": adv_bytes_per_launch / avg_dg / 1e9 / hbm_peak, "traffic": None,
+                    "avg_launch_ms": avg_dg * 1e3, "launches": dg_n, "share_of_step": dg_ms * 1e-3 / t_instr,
+                    "algorithmic_bytes_per_launch": adv_bytes_per_launch,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6500 GB/s (B200_PROFILING.md)"}
     try:
         d = pkg.LPGpu(Nx, NV, NSPEC, homogeneous=False, x_begin=s.x_begin, x_count=s.x_count, device=local, computeq_variant=3, **PHYS)
         d.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -383,7 +402,7 @@ def main():
                                exchange=("none (one GPU)" if world == 1 else
                                          "peer memory: kernels write halo planes and densities into the neighbours' buffers (CUDA IPC), flag-synchronised; no NCCL call in the timestep" if s.exchange == "peer" else
                                          "NCCL all-gather + send/recv per SSP-RK3 stage")),
-                "timesteps_per_s": args.steps / t_dev, "roofline": roof, "roofline_direct": roof_direct, "e2e": e2e, "as_reference_loop": as_reference,
+                "timesteps_per_s": args.steps / t_dev, "roofline": roof, "roofline_direct": roof_direct, "roofline_advection": roof_adv, "e2e": e2e, "as_reference_loop": as_reference,
                 "gpu_launches": int(launches), "clocks": clocks}
 
     # ---- BASELINE's single-cell homogeneous config, and the CPU baseline (N=1 only) --------------

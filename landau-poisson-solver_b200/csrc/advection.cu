@@ -268,12 +268,15 @@ int lp_launch_dg_stage(lpgpu_ctx *c, int stage)
   P.scalev = c->tab.scalev; P.Lv = c->p.Lv; P.inv_dxs = 1. / (P.dx * P.scalev);
   const long long n = (long long)c->ncell * c->sv;
   const unsigned grid = (unsigned)((n + 255) / 256);
+  const bool prof3 = c->prof_on == 3 && c->prof_used + 2 <= c->prof_ev.size();   // bench.py: HBM roofline of the DG stage kernels
+  if (prof3) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   // buffers: stage 0 reads U -> writes U1; stage 1 reads U1 (+U) -> U2; stage 2 reads U2 (+U) -> U
   if (stage == 0) k_dg_stage<0><<<grid, 256, 0, c->stream>>>(c->d_U[0], c->d_U[0], c->d_U[1], c->d_fld, P);
   else if (stage == 1) k_dg_stage<1><<<grid, 256, 0, c->stream>>>(c->d_U[1], c->d_U[0], c->d_U[2], c->d_fld, P);
   else if (stage == 2) k_dg_stage<2><<<grid, 256, 0, c->stream>>>(c->d_U[2], c->d_U[0], c->d_U[0], c->d_fld, P);
   else { lp_set_error("lp_launch_dg_stage: stage must be 0, 1 or 2"); return LPGPU_EINVAL; }
   LP_LAUNCHED(c);
+  if (prof3) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
   return LPGPU_OK;
 }
 
