@@ -198,11 +198,13 @@ __device__ __forceinline__ void tf_epilogue(double2 acc, long long g, double *ou
   if (EPI == 0) {
     reinterpret_cast<double2 *>(out)[g] = acc;
   } else {
+    // f and (in stages 2, 3) Qv are only read here: non-coherent loads, so that the loads of later lines are not held
+    // behind the stores of earlier ones (one warp per slab: the memory latency is hidden by loads in flight, not by warps)
     const double Q = acc.x * ep.inv;
     if (EPI == 4) reinterpret_cast<double2 *>(out)[g] = make_double2(Q, 0.);
-    if (EPI == 1) { ep.Qv[g] = Q; ep.f1[g] = ep.f[g] + ep.dt * Q * ep.nu; }
-    if (EPI == 2) ep.f1[g] = ep.f[g] + 0.5 * ep.dt * ep.Qv[g] * ep.nu + 0.5 * ep.dt * Q * ep.nu;
-    if (EPI == 3) ep.f1[g] = ep.f[g] + 0.5 * ep.Qv[g] * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
+    if (EPI == 1) { ep.Qv[g] = Q; ep.f1[g] = __ldg(ep.f + g) + ep.dt * Q * ep.nu; }
+    if (EPI == 2) ep.f1[g] = __ldg(ep.f + g) + 0.5 * ep.dt * __ldg(ep.Qv + g) * ep.nu + 0.5 * ep.dt * Q * ep.nu;
+    if (EPI == 3) ep.f1[g] = __ldg(ep.f + g) + 0.5 * __ldg(ep.Qv + g) * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
   }
 }
 template <int N, int SIGN, bool IN_REAL, int EPI, bool PRE, bool POST>
@@ -212,12 +214,12 @@ __global__ void __launch_bounds__(N) k_tf_jk(const double *__restrict__ in, doub
   __shared__ double2 X[N * P];
   const long long slab = blockIdx.x;                 // cell*N + i
   const int i = (int)(slab % N), t = threadIdx.x;
-  #pragma unroll 4
+  #pragma unroll 16
   for (int j = 0; j < N; j++) {
     const long long g = slab * N * N + j * N + t;
-    double2 x = IN_REAL ? make_double2(in[g], 0.) : reinterpret_cast<const double2 *>(in)[g];
+    double2 x = IN_REAL ? make_double2(__ldg(in + g), 0.) : __ldg(reinterpret_cast<const double2 *>(in) + g);
     if (PRE) {
-      x = phase_mul(ph.pre[i + j + t], x);
+      x = phase_mul(__ldg(ph.pre + i + j + t), x);
       if (ph.wt) { const double fac = ph.c3 * ph.wt[i] * ph.wt[j] * ph.wt[t]; x.x = __dmul_rn(fac, x.x); x.y = __dmul_rn(fac, x.y); }
     }
     X[j * P + t] = x;
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(N) k_tf_jk(const double *__restrict__ in, doub
   #pragma unroll
   for (int j = 0; j < N; j++) {
     double2 acc = v[j];
-    if (POST) acc = phase_mul(ph.post[(i * N + j) * N + t], acc);
+    if (POST) acc = phase_mul(__ldg(ph.post + (i * N + j) * N + t), acc);
     tf_epilogue<EPI>(acc, slab * N * N + j * N + t, out, ep);
   }
 }
