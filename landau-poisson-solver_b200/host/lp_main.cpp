@@ -265,13 +265,10 @@ int main(int argc, char **argv)
   FILE *fent = fopen(fent_name.c_str(), "w");
   if (!fent) die("cannot open " + fent_name);
 
-  auto diagnostics = [&](int step) {
-    double m5[5], ele = 0.;
-    std::vector<double> ms((size_t)2 * ncell);
-    CHECK(lpgpu_moments_partial(ctx, m5, ms.data()));
+  // the rows of one step from the numbers lpgpu_diagnostics_end (or the synchronous pair) returns
+  auto report = [&](int step, const double *m5, const std::vector<double> &ms, const double *d4) {
+    double ele = 0.;                                // d4: entropy, KiE over positive / negative cells, #negative cells
     if (!p.homogeneous) CHECK(lpgpu_eleE_from_ms(&p, ms.data(), &ele));
-    double d4[4];                                   // entropy, KiE over positive / negative cells, #negative cells
-    CHECK(lpgpu_diagnostics_partial(ctx, d4));
     const double ent = d4[0], lent = log(fabs(ent));
     fprintf(fent, "%11.8g %11.8g %11.8g \n", ent, lent, log(fabs(lent)));   // LP_ompi.cpp:632, 846
     if (!quiet) printf("entropy = %11.8g, Kinetic Energy Ratio = %g\n", ent, d4[2] / d4[1]);
@@ -283,6 +280,19 @@ int main(int argc, char **argv)
       if (!quiet) printf("step %d: %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g %11.8g \n", step, m5[0], m5[1], m5[2], m5[3], m5[4], ele, t, log(t), m5[4] + ele);
       fprintf(fmom, "%11.8g %11.8g %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g  %11.8g \n", m5[0], m5[1], m5[2], m5[3], m5[4], ele, t, log(t), m5[4] + ele);
     }
+  };
+  auto diagnostics = [&](int step) {                // synchronous: the state now on the device
+    double m5[5], d4[4];
+    std::vector<double> ms((size_t)2 * ncell);
+    CHECK(lpgpu_moments_partial(ctx, m5, ms.data()));
+    CHECK(lpgpu_diagnostics_partial(ctx, d4));
+    report(step, m5, ms, d4);
+  };
+  auto collect = [&](int step) {                    // the snapshot lpgpu_diagnostics_begin took after `step`
+    double m5[5], d4[4];
+    std::vector<double> ms((size_t)2 * ncell);
+    CHECK(lpgpu_diagnostics_end(ctx, m5, ms.data(), d4));
+    report(step, m5, ms, d4);
   };
   // ---- Marginals_*.dc / PhiVals_*.dc / FieldVals_*.dc: first the evaluation points, then one row for the initial state
   // and one every 20 steps (LP_ompi.cpp:648-655, :868-875).  The GPU reduces over the integrated-out velocity
@@ -370,11 +380,15 @@ int main(int argc, char **argv)
   diagnostics(0);
   print_marginal_and_field();
   const auto t0 = std::chrono::steady_clock::now();
+  // The reference computes the diagnostics of step t between steps t and t+1 (LP_ompi.cpp:817-849); here they run on a side
+  // stream over a snapshot while step t+1 runs, and their rows are written one step later, in the same order.
   for (int t = 0; t < nT; t++) {
-    CHECK(lpgpu_step(ctx, 1));
-    diagnostics(t + 1);
+    CHECK(lpgpu_step_async(ctx, 1));
+    if (t > 0) collect(t);                                           // rows of step t while step t+1 runs
+    CHECK(lpgpu_diagnostics_begin(ctx));                             // snapshot of the state after step t+1
     if (t % 20 == 0) print_marginal_and_field();                     // after steps 1, 21, 41, ...: the reference tests its 0-based counter (LP_ompi.cpp:79, :868)
   }
+  if (nT > 0) collect(nT);
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("\nTime duration for %d time steps is %gs\n\n", nT, secs);
   fclose(fmom);
