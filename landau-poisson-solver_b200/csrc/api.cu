@@ -412,6 +412,14 @@ static int group_count(lpgpu_ctx *c)
   while (g > 1 && c->ncell < 8 * g) g--;   // a group should still fill the GPU on its own
   return g;
 }
+// a view shares the parent's device arrays and keeps the scalars of the host tables; the table vectors themselves (MBs,
+// only read while the device copies are built) are dropped from the copy
+static void drop_host_tables(lpgpu_ctx *v)
+{
+  LpTables &t = v->tab;
+  for (std::vector<double> *x : {&t.G, &t.Gl, &t.C5, &t.Wfwd, &t.Winv, &t.pre_fwd, &t.pre_inv, &t.post_fwd, &t.post_inv, &t.T, &t.M, &t.S, &t.dirichlet, &t.Etab})
+    std::vector<double>().swap(*x);
+}
 static int make_groups(lpgpu_ctx *c, int G)
 {
   const int B = c->ncell, N = c->p.N, M = 3 * N / 2, Nv = c->p.Nv;
@@ -421,6 +429,7 @@ static int make_groups(lpgpu_ctx *c, int G)
     lpgpu_ctx *v = new (std::nothrow) lpgpu_ctx(*c);
     if (!v) return LPGPU_ENOMEM;
     c->groups.push_back(v);
+    drop_host_tables(v);
     v->is_view = true; v->ncell = (int)(b1 - b0); v->cap_cells = b1 - b0; v->launches = 0;
     v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->graph_failed[0] = v->graph_failed[1] = true; v->prof_on = 0; v->prof_ev.clear();
     v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
@@ -725,6 +734,7 @@ int lpgpu_diagnostics_begin(lpgpu_ctx *c)
     LP_CUDA(cudaEventCreateWithFlags(&c->diag_done, cudaEventDisableTiming));
     lpgpu_ctx *v = new (std::nothrow) lpgpu_ctx(*c);
     if (!v) return LPGPU_ENOMEM;
+    drop_host_tables(v);
     v->is_view = true; v->stream = c->diag_stream; v->launches = 0; v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
     v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->prof_on = 0; v->prof_ev.clear(); v->diag_view = nullptr;
     double *q = c->d_diag_scratch;
