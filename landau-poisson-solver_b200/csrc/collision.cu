@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(512) k_conserve(double2 *__restrict__ q, const
 // cell fold them (fixed order), apply CCt and correct their slice.  One block per cell leaves 116 of 148
 // SMs idle when a GPU holds 32 cells.
 #define LP_CONS_CH 8
+#define LP_APPLY_CH 32   // blocks per cell of the correction pass (independent of the number of partial sums folded)
 __global__ void __launch_bounds__(256) k_conserve_dots(const double2 *__restrict__ q, const double *__restrict__ C5,
                                                        double *__restrict__ part, int N3)
 {
@@ -505,7 +506,8 @@ __global__ void __launch_bounds__(256) k_conserve_apply(double2 *__restrict__ q,
   __syncthreads();
   const double b0 = lam[0], b1 = lam[1], b2 = lam[2], b3 = lam[3], b4 = lam[4];
   double2 *qc = q + cell * N3;
-  const int per = (N3 + LP_CONS_CH - 1) / LP_CONS_CH, lo = ch * per, hi = min(N3, lo + per);
+  const int per = (N3 + gridDim.y - 1) / gridDim.y, lo = ch * per, hi = min(N3, lo + per);
+  #pragma unroll 4
   for (int idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
     double2 v = qc[idx];
     v.x -= (C5[idx] * b0 + C5[4 * N3 + idx] * b4);
@@ -522,7 +524,7 @@ int lp_launch_conserve(lpgpu_ctx *c, double *q, int B)
   }
   k_conserve_dots<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(q), c->d_C5, c->d_lam, c->N3);
   LP_LAUNCHED(c);
-  k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->d_lam, c->N3, LP_CONS_CH);
+  k_conserve_apply<<<dim3(B, LP_APPLY_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, c->d_lam, c->N3, LP_CONS_CH);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -622,7 +624,7 @@ int lp_launch_conserve_fandl(lpgpu_ctx *c, double *q, double *ql, int B)
 
 int lp_launch_conserve_from_parts(lpgpu_ctx *c, double *q, const double *part, int B)
 {
-  k_conserve_apply<<<dim3(B, LP_CONS_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, part, c->N3, c->p.N);
+  k_conserve_apply<<<dim3(B, LP_APPLY_CH), 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), c->d_C5, c->d_CCt, part, c->N3, c->p.N);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
