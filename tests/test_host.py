@@ -32,6 +32,24 @@ def test_no_cpu_fallback(pkg):
         pkg.LPGpu(4, 8, 8, 5.25, 12.5, 0.05, 0.01)
 
 
+def test_init_refuses_bad_parameters(pkg):
+    """Error behaviour of the boundary: the reference prints and exit(1)s on bad input (InputParsing.cpp); the ABI returns
+    LPGPU_EINVAL with a message, before any device call, so this runs without a GPU."""
+    base = dict(Nx=4, Nv=8, N=8, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
+    bad = [dict(base, N=7), dict(base, N=34), dict(base, Nv=7), dict(base, dt=0.), dict(base, Lv=-1.), dict(base, gamma=2),
+           dict(base, gamma=0, full_and_linear=True), dict(base, linear_landau=True, full_and_linear=True),
+           dict(base, x_begin=2, x_count=3), dict(base, doping=dict(NL=0.001, NH=1., eps=0., T_L=0.4, T_R=0.4))]
+    for kw in bad:
+        with pytest.raises(pkg.lpgpu.LPGpuError) as e:
+            pkg.LPGpu(**kw)
+        assert "lpgpu_init" in str(e.value), (kw, str(e.value))
+    import ctypes as C
+    L = pkg.lpgpu.load_library()
+    assert L.lpgpu_finalize(None) == 0                       # finalize(NULL) is a no-op, like free(NULL)
+    assert L.lpgpu_step(None, 1) != 0 and b"null context" in L.lpgpu_last_error()
+    assert L.lpgpu_peer_export(None, None) != 0
+
+
 def test_product_never_imports_oracle():
     pkgdir = os.path.join(ROOT, "landau-poisson-solver_b200")
     for dirpath, _, files in os.walk(pkgdir):
