@@ -408,8 +408,8 @@ static int group_count(lpgpu_ctx *c)
   static const int knob = getenv("LPGPU_GROUPS") ? atoi(getenv("LPGPU_GROUPS")) : 0;   // developer knob; 1 = one chain
   if (c->is_view || c->prof_on || c->p.full_and_linear || !lp_fc3_available(c) || c->ncell < 16) return 1;
   if (lp_fc_prepare(c) != LPGPU_OK || c->fc_chunk < c->ncell) return 1;    // chunked ComputeQ reuses one set of work arrays
-  int g = knob > 0 ? knob : 4;             // measured, 32 cells at N = Nv = 32: 1.646 / 1.649 / 1.599 / 1.586 ms per step for 1 / 2 / 3 / 4 groups
-  while (g > 1 && c->ncell < 8 * g) g--;   // a group should still fill the GPU on its own
+  int g = knob > 0 ? knob : 4;             // measured, 32 cells at N = Nv = 32: 1.646 / 1.649 / 1.599 / 1.586 ms per step for 1 / 2 / 3 / 4 groups; later build: 1.544 / 1.558 / 1.560 / 1.888 for 4 / 6 / 8 / 16
+  while (g > 1 && c->ncell < (knob > 0 ? 2 : 8) * g) g--;   // a group should still fill the GPU on its own (the knob may go further)
   return g;
 }
 // a view shares the parent's device arrays and keeps the scalars of the host tables; the table vectors themselves (MBs,

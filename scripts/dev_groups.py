@@ -20,7 +20,7 @@ print("groups=%s: %.4f ms/step  checksum %.17g" % (os.environ.get("LPGPU_GROUPS"
 '''
 nc = sys.argv[1] if len(sys.argv) > 1 else "32"
 steps = sys.argv[2] if len(sys.argv) > 2 else "20"
-for g in ("1", "2", "3", "4"):
+for g in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("1", "2", "3", "4")):
     env = dict(os.environ, LPGPU_GROUPS=g)
     r = subprocess.run([sys.executable, "-c", CHILD, nc, steps], env=env, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr[-800:])
