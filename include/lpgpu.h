@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define LPGPU_OK 0
-#define LPGPU_EINVAL 1   /* bad argument / unsupported option (e.g. gamma != -3) */
+#define LPGPU_EINVAL 1   /* bad argument / unsupported option (e.g. gamma outside {-3, 0, 1}) */
 #define LPGPU_ENODEV 2   /* no usable CUDA device */
 #define LPGPU_ECUDA 3    /* CUDA runtime error */
 #define LPGPU_ENOMEM 4
@@ -35,7 +35,8 @@ typedef struct lpgpu_ctx lpgpu_ctx;
 typedef struct lpgpu_params {
   int Nx, Nv, N;
   double Lv, Lx, nu, dt;
-  int gamma;        /* only -3 (Landau/Coulomb) is implemented */
+  int gamma;        /* collision kernel, as ReadGamma (InputParsing.cpp:202-238): -3 Landau/Coulomb, 0 Maxwell molecules,
+                       1 hard spheres (generate_conv_weights(conv_weights, gamma), LP_ompi.cpp:424) */
   int homogeneous;  /* reference flag Homogeneous */
   int x_begin, x_count;
   int device;       /* CUDA device ordinal */
@@ -87,8 +88,8 @@ int lpgpu_download_U_async(lpgpu_ctx *c, double *U_host);
 int lpgpu_set_maxwellian(lpgpu_ctx *c);
 
 /* ---- whole phases ----------------------------------------------------------------------- */
-/* RK3(U), LP_ompi.cpp:666 / advection_1.cpp:412-576.  Single-shard contexts only
- * (x_count == Nx); sharded runs drive the three calls below once per stage. */
+/* RK3(U), LP_ompi.cpp:666 / advection_1.cpp:412-576.  A context that owns all of x, or a shard whose peers are mapped
+ * (lpgpu_peer_import below); other sharded runs drive the three per-stage calls below around their own exchange. */
 int lpgpu_advect_rk3(lpgpu_ctx *c);
 /* setInit_spectral + for every local cell ComputeQ, conserveMoments, RK4 + the scatter of the 5
  * updated coefficients into U: LP_ompi.cpp:671-754. */
@@ -96,7 +97,8 @@ int lpgpu_collide_step(lpgpu_ctx *c);
 /* Same work, enqueued only: the sharded driver queues the next stage's exchange behind it instead of stalling the
  * host once per phase.  lpgpu_synchronize (or any synchronous call) before reading results. */
 int lpgpu_collide_step_async(lpgpu_ctx *c);
-/* nsteps passes of the while(t<nT) body without diagnostics (single shard). */
+/* nsteps passes of the while(t<nT) body without diagnostics (all of x, or a shard whose peers are mapped).  From the
+ * second execution on a timestep is a CUDA graph replay. */
 int lpgpu_step(lpgpu_ctx *c, int nsteps);
 /* Same, enqueued only (lpgpu_synchronize before reading results). */
 int lpgpu_step_async(lpgpu_ctx *c, int nsteps);
