@@ -6,10 +6,44 @@
 #include <cstring>
 #include <vector>
 #include "../../landau-poisson-solver_b200/csrc/fc3.cuh"
+#include "../../landau-poisson-solver_b200/csrc/fc3h.cuh"
 
 // mhat (nullable): the linear operator Q(f, M) -- the u arrays come from the stored Maxwellian transform
+// the y/x stage of one (cell, kz) plane on two-thread thirds (fc3h.cuh, L = 16): the shuffle exchange of a pair is the
+// partner's Ex::send read between the `_a` and the `_b` phase
+static void f2_half_plane(int cell, int kz, const double2 *Z, const double *E, double2 *C)
+{
+  using namespace fc3;
+  typedef F2<16> K;
+  typedef F2H H;
+  std::vector<double2> IN(K::IN_C2), Y(K::Y_C2);
+  std::vector<double> sE(E, E + K::N);
+  struct A8 { double2 a[8]; };
+  std::vector<H::Ex> ex(H::NT);
+  std::vector<A8> acc(H::NT), uh(H::NT);
+  std::memset(acc.data(), 0, sizeof(A8) * acc.size());
+  auto got_of = [&](int t, double2 (&g)[4]) { for (int j = 0; j < 4; j++) g[j] = ex[t ^ 1].send[j]; };
+  double2 g[4];
+  for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, 0, Z, IN.data());
+  for (int p = 0; p < 7; p++) {
+    for (int t = 0; t < H::NT; t++) H::ystage_a(t, p, IN.data(), sE.data(), ex[t]);
+    for (int t = 0; t < H::NT; t++) { got_of(t, g); H::ystage_b(t, p, sE.data(), ex[t], g, Y.data()); }
+    if (p + 1 < 7) for (int t = 0; t < K::NT; t++) K::issue_loads(t, cell, kz, p + 1, Z, IN.data());
+    for (int t = 0; t < 288; t++) H::xfwd_a(t, 0, Y.data(), ex[t]);
+    for (int t = 0; t < 288; t++) { got_of(t, g); H::xfwd_b(t, ex[t], g, uh[t].a); }
+    for (int t = 0; t < 288; t++) H::xfwd_a(t, 1, Y.data(), ex[t]);
+    for (int t = 0; t < 288; t++) { got_of(t, g); double2 vh[8]; H::xfwd_b(t, ex[t], g, vh); H::product(uh[t].a, vh, acc[t].a); }
+  }
+  for (int t = 0; t < 288; t++) H::xinv_a(t, acc[t].a, ex[t]);
+  for (int t = 0; t < 288; t++) { got_of(t, g); H::xinv_b(t, ex[t], g, Y.data()); }
+  for (int t = 0; t < 192; t++) H::yinv_a(t, Y.data(), ex[t]);
+  for (int t = 0; t < 192; t++) { got_of(t, g); H::yinv_b(t, ex[t], g, IN.data()); }
+  for (int t = 0; t < K::NT; t++) K::store(t, cell, kz, IN.data(), C);
+}
+
 template <int L>
-static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr)
+static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr,
+                    bool half = false)
 {
   using namespace fc3;
   constexpr int N = 2 * L, M = 3 * L;
@@ -41,6 +75,7 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
     for (int cell = 0; cell < B; cell++)
       for (int kz = 0; kz < M; kz++)
         for (int sp = 0; sp < nsplit; sp++) {
+          if constexpr (L == 16) { if (half) { f2_half_plane(cell, kz, Z.data(), E, C.data()); continue; } }
           int p0, p1;
           K::psplit(sp, nsplit, p0, p1);
           std::memset(acc.data(), 0, sizeof(Acc) * acc.size());
@@ -94,6 +129,14 @@ extern "C" int fc3_emulate_linear(int N, int B, const double *fhat, const double
     case 32: emulate<16>(B, f, G7, E, o, 1, m); return 0;
   }
   return 1;
+}
+
+// N = 32 with the y/x stage on two-thread thirds (fc3h.cuh)
+extern "C" int fc3_emulate_half(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+{
+  if (N != 32) return 1;
+  emulate<16>(B, reinterpret_cast<const double2 *>(fhat), G7, E, reinterpret_cast<double2 *>(q), 1, nullptr, true);
+  return 0;
 }
 
 extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
