@@ -12,6 +12,7 @@
 // Sizes whose M has another prime factor use the tiled direct kernel (computeq.cu).
 #include "lpgpu_internal.h"
 #include "fc3.cuh"
+#include "fc3h.cuh"
 
 #define LP_LAUNCHED(c)                                  \
   do {                                                  \
@@ -465,6 +466,108 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   __syncthreads();
   K::store(tid, cell, kz, IN, C);
 }
+// ---- F2 on two-thread thirds (fc3h.cuh): 384 threads, accumulators and the waiting u transform in tensor memory ----
+// EXPERIMENTAL, off by default (LPGPU_F2_HALF=1 selects it): the task algebra is checked by the CPU emulator
+// (tests/test_fc3_emul.py::test_two_thread_thirds_match_direct_sum); the kernel itself has not run on hardware yet.
+// A pair of adjacent lanes shares every 16-point third and exchanges four complex values by shuffles; the compile-only
+// probe gives ~80 registers, i.e. two CTAs of twelve warps per SM instead of two of six.
+__device__ __forceinline__ void pair_exchange(const double2 (&send)[4], double2 (&got)[4])
+{
+  #pragma unroll
+  for (int j = 0; j < 4; j++) got[j] = make_double2(__shfl_xor_sync(0xffffffffu, send[j].x, 1), __shfl_xor_sync(0xffffffffu, send[j].y, 1));
+}
+__global__ void __launch_bounds__(384, 2) k_fc3_f2h_tmem(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
+{
+  typedef fc3::F2<16> K;
+  typedef fc3::F2H H;
+  constexpr int XW = 9;                      // x-stage warps: 288 tasks, every lane busy
+  constexpr unsigned PER = 64, COLS = 256;   // per thread: 32 columns of accumulators + 32 of the parked u transform; 3 column groups
+  extern __shared__ double2 smf[];
+  __shared__ unsigned s_tmem;
+  double2 *IN = smf, *Y = IN + K::IN_C2;
+  double *sE = reinterpret_cast<double *>(Y + K::Y_C2);
+  const int kz = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tmem);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(dst), "r"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  auto issue = [&](int p) {
+    const double2 *su = K::plane(Z, cell, p, kz), *sv = K::plane(Z, cell, 7 + fc3::zpow_of(p), kz);
+    const int lim = (p == 1) ? K::N * K::N : 2 * K::N * K::N;
+    for (int idx = tid; idx < lim; idx += H::NT) fc3::cp16(IN + idx, (idx < K::N * K::N ? su : sv) + idx % (K::N * K::N));
+  };
+  issue(0);
+  for (int i = tid; i < K::N; i += H::NT) sE[i] = E[i];
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const unsigned tbase = s_tmem;
+  const unsigned tacc = tbase + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(warp >> 2) * PER;
+  H::Ex e;
+  double2 got[4];
+  #pragma unroll 1
+  for (int p = 0; p < 7; p++) {
+    fc3::cp_wait_all();
+    __syncthreads();                         // planes of p landed; every x-stage read of Y from p-1 is done
+    H::ystage_a(tid, p, IN, sE, e);
+    pair_exchange(e.send, got);
+    H::ystage_b(tid, p, sE, e, got, Y);
+    __syncthreads();                         // Y complete; IN consumed
+    if (p + 1 < 7) issue(p + 1);
+    if (warp < XW) {
+      double2 w8[8];
+      H::xfwd_a(tid, 0, Y, e);
+      pair_exchange(e.send, got);
+      H::xfwd_b(tid, e, got, w8);
+      #pragma unroll
+      for (int c4 = 0; c4 < 2; c4++) { double2 t4[4] = {w8[4 * c4], w8[4 * c4 + 1], w8[4 * c4 + 2], w8[4 * c4 + 3]}; tmem_st4c(tacc + 32 + 16 * c4, t4); }
+      tmem_wait_st();
+      H::xfwd_a(tid, 1, Y, e);
+      pair_exchange(e.send, got);
+      H::xfwd_b(tid, e, got, w8);
+      #pragma unroll
+      for (int c4 = 0; c4 < 2; c4++) {
+        double2 a[4], u4[4];
+        if (p > 0) tmem_ld4c(tacc + 16 * c4, a);
+        else { a[0] = a[1] = a[2] = a[3] = make_double2(0., 0.); }
+        tmem_ld4c(tacc + 32 + 16 * c4, u4);
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const double2 v = w8[4 * c4 + i];
+          a[i].x += u4[i].x * v.x - u4[i].y * v.y;
+          a[i].y += u4[i].x * v.y + u4[i].y * v.x;
+        }
+        tmem_st4c(tacc + 16 * c4, a);
+      }
+      tmem_wait_st();
+    }
+  }
+  __syncthreads();                           // every x-stage read of Y is done: T may overwrite it
+  if (warp < XW) {
+    double2 acc[8];
+    #pragma unroll
+    for (int c4 = 0; c4 < 2; c4++) {
+      double2 a[4];
+      tmem_ld4c(tacc + 16 * c4, a);
+      #pragma unroll
+      for (int i = 0; i < 4; i++) acc[4 * c4 + i] = a[i];
+    }
+    H::xinv_a(tid, acc, e);
+    pair_exchange(e.send, got);
+    H::xinv_b(tid, e, got, Y);               // T aliases Y
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"(COLS) : "memory");
+  if (warp < 6) {                            // 192 tasks (ry, xo, h)
+    H::yinv_a(tid, Y, e);
+    pair_exchange(e.send, got);
+    H::yinv_b(tid, e, got, IN);              // T2 aliases IN
+  }
+  __syncthreads();
+  if (tid < K::NT) K::store(tid, cell, kz, IN, C);
+}
 // part (nullable): per (cell, xo) partial dot products of the conservation rows with the stored spectrum,
 // [cell][xo][5]; folded in a fixed order by the kernels that apply the correction (collision.cu)
 template <int L, int NSPLIT>
@@ -525,7 +628,16 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   const int nsplit = (nb * M * 2 <= 148) ? 3 : 1;
   const long long split_stride = (long long)nb * M * N * N;
   const dim3 g2(M, nb, nsplit);
-  if (L == 16 && !no_tmem && nsplit == 3) k_fc3_f2_tmem<true, 3><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
+  static const bool half_thirds = getenv("LPGPU_F2_HALF") != nullptr;    // experimental two-thread thirds (see k_fc3_f2h_tmem)
+  if constexpr (L == 16) {
+    if (half_thirds && !no_tmem && nsplit == 1) {
+      static bool attr = false;
+      if (!attr) { LP_CUDA(cudaFuncSetAttribute(k_fc3_f2h_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr = true; }
+      k_fc3_f2h_tmem<<<g2, fc3::F2H::NT, smem2, c->stream>>>(Z, E, C);
+    }
+  }
+  if (L == 16 && half_thirds && !no_tmem && nsplit == 1) { /* launched above */ }
+  else if (L == 16 && !no_tmem && nsplit == 3) k_fc3_f2_tmem<true, 3><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else if (L == 16 && !no_tmem && park_uh) k_fc3_f2_tmem<true, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else if (L == 16 && !no_tmem) k_fc3_f2_tmem<false, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else k_fc3_f2<L><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
