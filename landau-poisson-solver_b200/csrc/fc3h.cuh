@@ -1,7 +1,8 @@
 // Two-thread thirds for the y/x stage kernel of the FFT-convolution ComputeQ (L = 16, N = 32, M = 48).
 //
 // STATUS: groundwork for the next version of k_fc3_f2_tmem.  The task algebra below is
-// checked on the CPU by the thread-loop emulator (tests/emul, tests/test_fc3_emul.py); no kernel uses it yet.
+// checked on the CPU by the thread-loop emulator (tests/emul, tests/test_fc3_emul.py); the experimental kernel
+// k_fc3_f2h_tmem (fftconv.cu, LPGPU_F2_HALF=1, off by default) uses it: correct on hardware, not yet faster.
 //
 // Why: one thread per 16-point third (fc3.cuh) needs 168 registers, so 12 warps fit an SM and the FP64 pipe idles half
 // the time.  Here a PAIR of adjacent threads shares a third.  With n = 4 n1 + n2 and k = k1 + 4 k2,

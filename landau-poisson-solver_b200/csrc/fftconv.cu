@@ -468,7 +468,9 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
 }
 // ---- F2 on two-thread thirds (fc3h.cuh): 384 threads, accumulators and the waiting u transform in tensor memory ----
 // EXPERIMENTAL, off by default (LPGPU_F2_HALF=1 selects it): the task algebra is checked by the CPU emulator
-// (tests/test_fc3_emul.py::test_two_thread_thirds_match_direct_sum); the kernel itself has not run on hardware yet.
+// (tests/test_fc3_emul.py::test_two_thread_thirds_match_direct_sum).  First hardware run (scripts/dev_f2_half_check.py):
+// correct (6e-15 against the direct sum at N = 32) but 429 us per 32-cell launch against 220 us for k_fc3_f2_tmem -- the
+// per-lane twiddle lookups (the owned residue classes depend on the lane parity) and the spills eat the occupancy gain.
 // A pair of adjacent lanes shares every 16-point third and exchanges four complex values by shuffles; the compile-only
 // probe gives ~80 registers, i.e. two CTAs of twelve warps per SM instead of two of six.
 __device__ __forceinline__ void pair_exchange(const double2 (&send)[4], double2 (&got)[4])
