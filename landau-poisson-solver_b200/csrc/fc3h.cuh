@@ -23,12 +23,15 @@ namespace fc3 {
 
 struct Half16 {
   static constexpr int L = 16, M = 48;
-  // w_M^(SIGN t) for a run-time t (the residue class depends on h): table lookup instead of a folded constant
+  // v * w_M^(SIGN t), t = t0 for the h = 0 thread of a pair and t1 for the h = 1 thread.  Both are compile-time
+  // constants once the callers' loops are unrolled, so the factor is a select between two immediates -- the first
+  // version looked t up in the constant bank with a per-lane index (two addresses per warp, serialised) and ran at
+  // half the speed of the one-thread kernel
   template <int SIGN>
-  static LP_HD double2 tw(double2 v, int t)
+  static LP_HD double2 tw2(double2 v, int t0, int t1, int h)
   {
-    t %= M;
-    const double c = Tw<M>::c(t), s = SIGN > 0 ? Tw<M>::s(t) : -Tw<M>::s(t);
+    t0 %= M; t1 %= M;
+    const double c = h ? Tw<M>::c(t1) : Tw<M>::c(t0), sp = h ? Tw<M>::s(t1) : Tw<M>::s(t0), s = SIGN > 0 ? sp : -sp;
     return make_double2(v.x * c - v.y * s, v.x * s + v.y * c);
   }
   // input slot i = 4 c + n1 of thread h  <->  line index l = 4 n1 + 2 h + c   (c = 0, 1; n1 = 0..3)
@@ -42,22 +45,24 @@ struct Half16 {
   {
     #pragma unroll
     for (int c = 0; c < 2; c++) {
-      const int n2 = 2 * h + c;
       double2 v[4];
       #pragma unroll
       for (int n1 = 0; n1 < 4; n1++) {
         const double2 p = a0[4 * c + n1], q = a1[4 * c + n1];
+        const int l0 = 4 * n1 + c, l1 = l0 + 2;               // the line index of this slot for h = 0 / h = 1
         if (r == 0) v[n1] = cadd(p, q);
-        else {
-          const double sg = r == 1 ? LP_SQ3H : -LP_SQ3H;      // w3^r = -1/2 -/+ i sqrt(3)/2
-          const double2 b = make_double2(p.x - 0.5 * q.x + sg * q.y, p.y - 0.5 * q.y - sg * q.x);
-          v[n1] = tw<-1>(b, r * (4 * n1 + n2));
+        else if (r == 1) {                                    // w3^r = -1/2 -/+ i sqrt(3)/2
+          const double2 b = make_double2(p.x - 0.5 * q.x + LP_SQ3H * q.y, p.y - 0.5 * q.y - LP_SQ3H * q.x);
+          v[n1] = tw2<-1>(b, l0, l1, h);
+        } else {
+          const double2 b = make_double2(p.x - 0.5 * q.x - LP_SQ3H * q.y, p.y - 0.5 * q.y + LP_SQ3H * q.x);
+          v[n1] = tw2<-1>(b, 2 * l0, 2 * l1, h);
         }
       }
       dft4<-1>(v[0], v[1], v[2], v[3]);
       #pragma unroll
       for (int k1 = 0; k1 < 4; k1++) {
-        const double2 y = tw<-1>(v[k1], 3 * n2 * k1);         // w16^(n2 k1) = w48^(3 n2 k1)
+        const double2 y = tw2<-1>(v[k1], 3 * c * k1, 3 * (2 + c) * k1, h);   // w16^(n2 k1) = w48^(3 n2 k1), n2 = 2 h + c
         const int kk = k1 & 1;
         if ((k1 >> 1) == h) keep[2 * kk + c] = y; else send[2 * kk + c] = y;
       }
@@ -86,7 +91,7 @@ struct Half16 {
       const double2 v[4] = {v0, v1, v2, v3};
       #pragma unroll
       for (int n2 = 0; n2 < 4; n2++) {
-        const double2 y = tw<+1>(v[n2], 3 * n2 * k1);
+        const double2 y = tw2<+1>(v[n2], 3 * n2 * kk, 3 * n2 * (2 + kk), h);    // k1 = 2 h + kk
         const int c = n2 & 1;
         if ((n2 >> 1) == h) keep[2 * c + kk] = y; else send[2 * c + kk] = y;
       }
@@ -102,7 +107,10 @@ struct Half16 {
       dft4<+1>(m0, m1, m2, m3);                               // index n1 = 0..3
       const double2 m[4] = {m0, m1, m2, m3};
       #pragma unroll
-      for (int n1 = 0; n1 < 4; n1++) out[4 * c + n1] = r == 0 ? m[n1] : tw<+1>(m[n1], r * (4 * n1 + 2 * h + c));
+      for (int n1 = 0; n1 < 4; n1++) {
+        const int l0 = 4 * n1 + c, l1 = l0 + 2;
+        out[4 * c + n1] = r == 0 ? m[n1] : r == 1 ? tw2<+1>(m[n1], l0, l1, h) : tw2<+1>(m[n1], 2 * l0, 2 * l1, h);
+      }
     }
   }
 };
