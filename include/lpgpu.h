@@ -132,10 +132,13 @@ int lpgpu_advect_apply(lpgpu_ctx *c, int stage);
  * All ranks must then execute the same sequence of steps, with one peer-mapped context in flight per process (the
  * waits of two independent contexts could block each other across hardware queues); synchronise the ranks before
  * lpgpu_finalize.
- * lpgpu_peer_status returns an error if a bounded wait (10 s) for a peer ever timed out. */
+ * Waits for a peer are bounded (default 60 s, or LPGPU_PEER_TIMEOUT_S; lpgpu_peer_set_timeout before the first timestep).
+ * Fail-stop: a wait that times out poisons the state with NaN on the device, and every later lpgpu_step / _synchronize /
+ * _advect_rk3 / _download_U of this context returns LPGPU_ECUDA; lpgpu_peer_status reports the count at any time. */
 #define LPGPU_PEER_HANDLE_BYTES 256
 int lpgpu_peer_export(lpgpu_ctx *c, void *blob);
 int lpgpu_peer_import(lpgpu_ctx *c, int rank, int world, const void *blobs);
+int lpgpu_peer_set_timeout(lpgpu_ctx *c, double seconds);
 int lpgpu_peer_status(lpgpu_ctx *c, long long *timeouts);
 
 /* ---- fine-grained entry points (host buffers, B cells per call) -------------------------- */

@@ -146,7 +146,12 @@ int lp_launch_field_scan(lpgpu_ctx *c)
 {
   const double dx = c->p.Lx / c->p.Nx;
   DopingParams D = {c->p.doping, c->p.Nx / 3 - 1, 2 * c->p.Nx / 3 - 1, c->p.NL, c->p.NH, c->p.eps};   // a_i, b_i: LP_ompi.cpp:160-161
-  k_field_scan<<<1, 256, (size_t)3 * c->p.Nx * sizeof(double), c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx, D);
+  const size_t scan_smem = (size_t)3 * c->p.Nx * sizeof(double);
+  if (scan_smem > 48 * 1024 && !c->scan_attr) {       // Nx > 2048 (lpgpu_init bounds Nx so that this fits an SM)
+    LP_CUDA(cudaFuncSetAttribute(k_field_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    c->scan_attr = true;
+  }
+  k_field_scan<<<1, 256, scan_smem, c->stream>>>(c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell, dx, c->p.Lx, D);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -308,8 +313,9 @@ int lp_launch_local_halo(lpgpu_ctx *c, double *planes)
 // peers' flag words after its data (release at system scope); a consumer waits until every flag has reached its own
 // epoch -- all ranks execute the same sequence of stages.  A rank can be at most one stage ahead of a peer (its next
 // stage needs that peer's next densities), hence two density buffers selected by the epoch's parity; the halo planes
-// belong to three different stage buffers.  Waits are bounded (10 s): on a timeout the kernel counts it in the mailbox
-// and goes on, so that a dead peer gives wrong numbers and an error from lpgpu_peer_status, not a hung GPU.
+// belong to three different stage buffers.  Waits are bounded (lpgpu_peer_set_timeout, default 60 s): on a timeout the
+// kernel counts it in the mailbox and poisons the state with NaN, so that a dead peer gives an error from the next host
+// call and NaN, neither a hung GPU nor plausible wrong numbers.
 typedef unsigned long long ull;
 __device__ __forceinline__ void st_release_sys(ull *p, ull v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ ull ld_acquire_sys(const ull *p) { ull v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
@@ -353,8 +359,11 @@ __global__ void __launch_bounds__(256) k_peer_publish_density(const double *__re
   if (threadIdx.x < world) st_release_sys(pb.box[threadIdx.x] + LP_MB_DFLAG + rank, e);
   if (threadIdx.x == 0) mine[LP_MB_EPOCH_D] = e;
 }
-// wait for every rank's densities and both halo planes of this stage; gather the densities into ms_all
-__global__ void __launch_bounds__(256) k_peer_wait(ull *mbox, int world, double *__restrict__ ms_all, int Nx2)
+// wait for every rank's densities and both halo planes of this stage; gather the densities into ms_all.
+// A wait that exceeds timeout_ns is counted in the mailbox, and the state is poisoned: ms_all is filled with NaN, so the
+// field, this stage and everything after it turn into NaN instead of plausible numbers computed from stale halos; the
+// host calls (lpgpu_step, lpgpu_synchronize, lpgpu_download_U ...) return an error from then on (api.cu, peer_check).
+__global__ void __launch_bounds__(256) k_peer_wait(ull *mbox, int world, double *__restrict__ ms_all, int Nx2, ull timeout_ns)
 {
   const ull ed = mbox[LP_MB_EPOCH_D], eh = mbox[LP_MB_EPOCH_H];
   if (threadIdx.x < world + 2) {
@@ -363,12 +372,13 @@ __global__ void __launch_bounds__(256) k_peer_wait(ull *mbox, int world, double 
     const ull t0 = global_ns();
     while (ld_acquire_sys(flag) < want) {
       __nanosleep(200);
-      if (global_ns() - t0 > 10000000000ULL) { atomicAdd(mbox + LP_MB_ERR, 1ULL); break; }
+      if (global_ns() - t0 > timeout_ns) { atomicAdd(mbox + LP_MB_ERR, 1ULL); break; }
     }
   }
   __syncthreads();
+  const bool poisoned = *reinterpret_cast<volatile ull *>(mbox + LP_MB_ERR) != 0;     // sticky: this wait or an earlier one
   const double *src = reinterpret_cast<const double *>(mbox + LP_MB_MS) + (ed & 1) * Nx2;
-  for (int i = threadIdx.x; i < Nx2; i += blockDim.x) ms_all[i] = __ldcg(src + i);
+  for (int i = threadIdx.x; i < Nx2; i += blockDim.x) ms_all[i] = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : __ldcg(src + i);
 }
 int lp_launch_peer_put_halo(lpgpu_ctx *c, int stage)
 {
@@ -392,7 +402,7 @@ int lp_launch_peer_publish_density(lpgpu_ctx *c)
 }
 int lp_launch_peer_wait(lpgpu_ctx *c)
 {
-  k_peer_wait<<<1, 256, 0, c->stream>>>(c->d_mbox, c->peer_world, c->d_ms_all, 2 * c->p.Nx);
+  k_peer_wait<<<1, 256, 0, c->stream>>>(c->d_mbox, c->peer_world, c->d_ms_all, 2 * c->p.Nx, (ull)(c->peer_timeout_s * 1e9));
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }

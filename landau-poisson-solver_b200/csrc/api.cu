@@ -53,6 +53,7 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   if (!(p->Lv > 0) || !(p->dt > 0) || p->nu < 0) { lp_set_error("lpgpu_init: need Lv > 0, dt > 0, nu >= 0"); return LPGPU_EINVAL; }
   if (!p->homogeneous) {
     if (p->Nx < 1 || !(p->Lx > 0)) { lp_set_error("lpgpu_init: need Nx >= 1 and Lx > 0"); return LPGPU_EINVAL; }
+    if (p->Nx > 8192) { lp_set_error("lpgpu_init: Nx must be <= 8192 (the field scan keeps 3 Nx doubles in one SM's shared memory)"); return LPGPU_EINVAL; }
     if (p->x_begin < 0 || p->x_count < 1 || p->x_begin + p->x_count > p->Nx) { lp_set_error("lpgpu_init: bad shard [x_begin, x_begin + x_count)"); return LPGPU_EINVAL; }
   }
   if (p->doping && (p->homogeneous || !(p->eps > 0) || !(p->T_L > 0) || !(p->T_R > 0))) { lp_set_error("lpgpu_init: Doping needs an inhomogeneous run, eps > 0, T_L > 0, T_R > 0"); return LPGPU_EINVAL; }
@@ -72,6 +73,8 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   c->ncell = c->p.x_count;
   c->stream = 0;
   c->launches = 0;
+  c->peer_timeout_s = getenv("LPGPU_PEER_TIMEOUT_S") ? atof(getenv("LPGPU_PEER_TIMEOUT_S")) : 60.;
+  if (!(c->peer_timeout_s > 0.)) c->peer_timeout_s = 60.;
   lp_build_tables(c->p, c->tab);
   if (p->linear_landau && !lp_fc3_available(c)) {
     lp_set_error("lpgpu_init: LinearLandau runs through the FFT-convolution pipeline only (N = 8, 16, 24 or 32, computeq_variant 0 or 2)");
@@ -169,7 +172,20 @@ int lpgpu_finalize(lpgpu_ctx *c)
 }
 
 int lpgpu_set_stream(lpgpu_ctx *c, void *s) { if (!c) return LPGPU_EINVAL; c->stream = (cudaStream_t)s; return LPGPU_OK; }
-int lpgpu_synchronize(lpgpu_ctx *c) { if (!c) return LPGPU_EINVAL; LP_CUDA(cudaSetDevice(c->p.device)); LP_CUDA(cudaStreamSynchronize(c->stream)); return LPGPU_OK; }
+} // extern "C"
+// Fail-stop for the peer exchange: once a wait for a peer's flag has timed out (k_peer_wait poisons the state with NaN),
+// every host call that hands results to the caller returns an error.  Called after the stream has been synchronised.
+static int peer_check(lpgpu_ctx *c)
+{
+  if (!c->peer_ready || !c->d_mbox) return LPGPU_OK;
+  unsigned long long v = 0;
+  LP_CUDA(cudaMemcpyAsync(&v, c->d_mbox + LP_MB_ERR, sizeof(v), cudaMemcpyDeviceToHost, c->stream));   // on the context's stream: no device-wide sync
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  if (v) { lp_set_error("peer exchange: a wait for a peer's flag timed out (a rank died or fell more than the timeout behind); the state is poisoned (NaN)"); return LPGPU_ECUDA; }
+  return LPGPU_OK;
+}
+extern "C" {
+int lpgpu_synchronize(lpgpu_ctx *c) { if (!c) return LPGPU_EINVAL; LP_CUDA(cudaSetDevice(c->p.device)); LP_CUDA(cudaStreamSynchronize(c->stream)); return peer_check(c); }
 long long lpgpu_launch_count(const lpgpu_ctx *c) { return c ? c->launches : 0; }
 
 #define LP_ENTER(c)                                                        \
@@ -194,7 +210,7 @@ int lpgpu_download_U(lpgpu_ctx *c, double *U)
   LP_TRY(lp_launch_planes_to_aos(c, c->d_U[0], c->d_aos));
   LP_CUDA(cudaMemcpyAsync(U, c->d_aos, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   LP_CUDA(cudaStreamSynchronize(c->stream));
-  return LPGPU_OK;
+  return peer_check(c);
 }
 // Enqueue-only forms: the copy and the layout kernel are ordered on the context's stream, the host returns at once.
 // The AoS staging buffer is shared by both directions; stream order keeps an upload behind the previous download.
@@ -281,7 +297,7 @@ int lpgpu_advect_rk3(lpgpu_ctx *c)
   LP_TRY(check_stage(c, 0));
   LP_TRY(advect_rk3_async(c));
   LP_CUDA(cudaStreamSynchronize(c->stream));
-  return LPGPU_OK;
+  return peer_check(c);
 }
 
 // ---- peer-memory exchange (CUDA IPC, one process per GPU on one node) ---------------------------
@@ -332,6 +348,14 @@ int lpgpu_peer_import(lpgpu_ctx *c, int rank, int world, const void *blobs)
       }
   }
   c->peer_rank = rank; c->peer_world = world; c->peer_ready = true;
+  return LPGPU_OK;
+}
+int lpgpu_peer_set_timeout(lpgpu_ctx *c, double seconds)
+{
+  LP_ENTER(c);
+  if (!(seconds > 0.)) { lp_set_error("lpgpu_peer_set_timeout: seconds must be > 0"); return LPGPU_EINVAL; }
+  if (c->gexec[0] || c->gexec[1]) { lp_set_error("lpgpu_peer_set_timeout: call before the first timestep (the bound is baked into the captured graph)"); return LPGPU_EINVAL; }
+  c->peer_timeout_s = seconds;
   return LPGPU_OK;
 }
 int lpgpu_peer_status(lpgpu_ctx *c, long long *timeouts)
@@ -542,7 +566,7 @@ int lpgpu_step(lpgpu_ctx *c, int nsteps)
   LP_ENTER(c);
   LP_TRY(step_enqueue(c, nsteps));
   LP_CUDA(cudaStreamSynchronize(c->stream));
-  return LPGPU_OK;
+  return peer_check(c);
 }
 int lpgpu_step_async(lpgpu_ctx *c, int nsteps)
 {

@@ -687,9 +687,16 @@ int lp_fc_prepare(lpgpu_ctx *c)
     // (7.9 MB per cell at N = 32), 14 of N M^2 for the shared-memory fallback
     const bool fc3_size = (N == 32 || N == 24 || N == 16 || N == 8) && !fc3_knobs_off();
     const size_t per_cell = fc3_size ? (size_t)10 * N * N * M * sizeof(double2) : (size_t)14 * N * M * M * sizeof(double2);
-    // 1 GB of transformed planes per chunk.  Measured: chunks small enough for F2 to read F1's output out of the
-    // 126 MB L2 (96 MB) are 15 % slower than one big launch -- the kernels are not HBM-limited, launch tails are.
-    const size_t budget_mb = getenv("LPGPU_FC_CHUNK_MB") ? (size_t)atoi(getenv("LPGPU_FC_CHUNK_MB")) : 1024;
+    // Transformed planes of one chunk: up to a third of the free device memory, 64 GB at most (7.9 MB per cell at N = 32:
+    // the 512 cells of the largest BASELINE config take 4 GB), so that in practice one launch covers every local cell.
+    // Measured in round 1: chunks small enough for F2 to read F1's output out of the 126 MB L2 (96 MB) are 15 % slower
+    // than one big launch -- the kernels are not HBM-limited, launch tails are.  LPGPU_FC_CHUNK_MB overrides (tests).
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    size_t auto_mb = (free_b / 3) >> 20;
+    if (auto_mb > 65536) auto_mb = 65536;
+    if (auto_mb < 256) auto_mb = 256;
+    const size_t budget_mb = getenv("LPGPU_FC_CHUNK_MB") ? (size_t)atoi(getenv("LPGPU_FC_CHUNK_MB")) : auto_mb;
     size_t chunk = (budget_mb << 20) / per_cell;
     if (chunk < 1) chunk = 1;
     if (chunk > c->cap_cells) chunk = c->cap_cells;

@@ -94,6 +94,8 @@ struct lpgpu_ctx {
   //      its densities into all ranks' mailboxes and its boundary planes into its neighbours' halo planes, then raises a
   //      flag; replaces the NCCL all-gather + send/recv, so the whole sharded timestep is one stream of kernels (one graph)
   bool peer_ready;
+  double peer_timeout_s;                  // bound of a flag wait (k_peer_wait); a timeout poisons the state and fails the host calls
+  bool scan_attr;                         // k_field_scan opted in to more than 48 KB of shared memory (Nx > 2048)
   int peer_rank, peer_world;
   unsigned long long *d_mbox;            // own mailbox (layout: LP_MB_* below)
   unsigned long long *peer_mbox[LP_MAX_PEERS];   // every rank's mailbox as mapped here ([peer_rank] = d_mbox)

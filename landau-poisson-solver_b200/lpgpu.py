@@ -47,7 +47,7 @@ EXPORTS = [
     "lpgpu_get_stage_spectrum", "lpgpu_field", "lpgpu_moments_partial", "lpgpu_eleE_from_ms",
     "lpgpu_profile_computeQ", "lpgpu_profile_read", "lpgpu_fp64_peak", "lpgpu_diagnostics_partial", "lpgpu_marginal_sums",
     "lpgpu_diagnostics_begin", "lpgpu_diagnostics_end",
-    "lpgpu_peer_export", "lpgpu_peer_import", "lpgpu_peer_status",
+    "lpgpu_peer_export", "lpgpu_peer_import", "lpgpu_peer_status", "lpgpu_peer_set_timeout",
 ]
 PEER_HANDLE_BYTES = 256
 
@@ -85,6 +85,7 @@ def load_library():
     L.lpgpu_peer_export.argtypes = [C.c_void_p, C.c_void_p]
     L.lpgpu_peer_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.lpgpu_peer_status.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    L.lpgpu_peer_set_timeout.argtypes = [C.c_void_p, C.c_double]
     L.lpgpu_diagnostics_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpgpu_profile_computeQ.argtypes = [C.c_void_p, C.c_int]
     L.lpgpu_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
@@ -289,6 +290,10 @@ class LPGpu:
         blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
         assert blobs.size == world * PEER_HANDLE_BYTES
         self._check(self.L.lpgpu_peer_import(self.h, int(rank), int(world), _ptr(blobs)))
+
+    def peer_set_timeout(self, seconds):
+        """Bound of a wait for a peer's flag (default 60 s); call before the first timestep."""
+        self._check(self.L.lpgpu_peer_set_timeout(self.h, float(seconds)))
 
     def peer_status(self):
         """Raises if a bounded wait for a peer's flag ever timed out."""

@@ -452,9 +452,19 @@ class ShardedSolver:
 
     def close(self):
         if self.world > 1 and not self.homogeneous and self.exchange == "peer":
-            self.g.synchronize()
-            self.g.peer_status()                 # raises if a wait for a peer ever timed out
-            self.dist.barrier()                  # nobody unmaps or frees while a peer may still write
+            # every rank learns whether any rank's wait for a peer timed out BEFORE anybody raises: a rank that raised
+            # alone would leave the others hanging in the barrier
+            try:
+                self.g.synchronize()
+                bad = 0
+            except lpgpu.LPGpuError:
+                bad = 1
+            t = self.torch.tensor([bad], dtype=self.torch.int32, device="cuda" if self.dist.get_backend() == "nccl" else "cpu")
+            self.dist.all_reduce(t)                # also the barrier: nobody unmaps or frees while a peer may still write
+            self.g.close()
+            if int(t.item()):
+                raise lpgpu.LPGpuError("peer exchange: a wait for a peer's flag timed out on %d rank(s); the run's results are poisoned (NaN)" % int(t.item()))
+            return
         self.g.close()
 
 
@@ -465,7 +475,19 @@ def run_from_input_file(path="LPsolver-input.txt", outdir=".", device=0, quiet=F
     s = ShardedSolver(cfg.Nx, cfg.Nv, cfg.N, cfg.Lv, cfg.Lx, cfg.nu, cfg.dt, homogeneous=cfg.homogeneous, device=device,
                       full_and_linear=cfg.full_and_linear, doping=cfg.doping, linear_landau=cfg.linear_landau,
                       mass_cons_only=cfg.mass_cons_only, gamma=cfg.gamma)
-    s.upload(cfg.initial_condition())
+    if cfg.second:
+        # LP_ompi.cpp:529-571: pick up from the last record of Data/<Second/Name> (raw doubles, 6*size per record)
+        if not cfg.second_name:
+            raise ValueError("Please set the name of the file from the previous run under Second/Name")
+        need = 6 * (1 if cfg.homogeneous else cfg.Nx) * cfg.Nv ** 3
+        path = os.path.join(outdir, "Data", cfg.second_name)
+        nbytes = os.path.getsize(path)
+        if nbytes < 8 * need or nbytes % (8 * need):
+            raise ValueError("Error reading file %s: its size does not match records of 6*size doubles" % path)
+        U0 = np.fromfile(path, dtype=np.float64, count=need, offset=nbytes - 8 * need)
+    else:
+        U0 = cfg.initial_condition()
+    s.upload(U0)
     if cfg.linear_landau and cfg.nu > 0:
         s.set_maxwellian()
     out = os.path.join(outdir, cfg.moments_filename())

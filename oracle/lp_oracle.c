@@ -349,6 +349,14 @@ void lpo_get_grids(const lpo_ctx *c, double *v, double *eta, double *wt)
   memcpy(eta, c->eta, sizeof(double) * c->N);
   memcpy(wt, c->wt, sizeof(double) * c->N);
 }
+void lpo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int lpo_num_threads(void)
 {
 #ifdef _OPENMP

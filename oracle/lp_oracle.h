@@ -77,6 +77,8 @@ void lpo_diagnostics(const lpo_ctx *c, const double *U, double *out4);
 /* whole time step (advection then collision), LP_ompi.cpp:662-813 */
 void lpo_step(const lpo_ctx *c, double *U);
 int lpo_num_threads(void);
+/* launchers such as torchrun export OMP_NUM_THREADS=1: bench.py sets the thread count explicitly */
+void lpo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

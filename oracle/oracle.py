@@ -37,6 +37,30 @@ def have_ref():
     return os.path.exists(REF_LIB)
 
 
+def host_cores():
+    """Cores this process may run on (the affinity mask, not the machine's total)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_num_threads(n=None):
+    """OpenMP thread count of both checkers (default: every core this process may use).  torchrun exports
+    OMP_NUM_THREADS=1, which would silently time a one-thread reference; callers that time the CPU path set it."""
+    n = int(n or host_cores())
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    if os.path.exists(PORT_LIB):
+        L = C.CDLL(PORT_LIB)
+        if hasattr(L, "lpo_set_num_threads"):
+            L.lpo_set_num_threads(n)
+    if os.path.exists(REF_LIB):
+        L = C.CDLL(REF_LIB)
+        if hasattr(L, "ref_set_num_threads"):
+            L.ref_set_num_threads(n)
+    return n
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 

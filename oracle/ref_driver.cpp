@@ -212,4 +212,6 @@ void ref_diagnostics(const double *U_in, double *out4)
   out4[2] = n; out4[3] = 0.;
 }
 int ref_num_threads(void) { return omp_get_max_threads(); }
+/* launchers such as torchrun export OMP_NUM_THREADS=1: bench.py sets the thread count explicitly (before ref_setup, which sizes the FFT plans) */
+void ref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 }

@@ -639,7 +639,7 @@ def test_against_committed_reference_vectors(pkg):
     gh.close()
 
 
-@pytest.mark.parametrize("case,homog", [("test0", False), ("test4", True), ("test3", False), ("test1", False)])
+@pytest.mark.parametrize("case,homog", [("test0", False), ("test4", True), ("test3", False), ("test1", False), ("test2", False)])
 def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
     """The reference's own end-to-end test (tests/LPsolver_tests + moment_differ.sh): run the driver in a
     directory holding LPsolver-input.txt and compare row 6 of the Moments file it writes with the golden."""
@@ -654,6 +654,7 @@ def test_cpp_driver_reproduces_reference_goldens(case, homog, tmp_path):
     name = {"test0": "Data/Moments_nu0.05A0.2k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test0.dc",
             "test3": "Data/Moments_nu0.05A0.2k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test3.dc",
             "test1": "Data/Moments_nu0.05A0k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test1.dc",
+            "test2": "Data/Moments_nu0.05A0k0.5Nx16Lx12.5664Nv16Lv5.25SpectralN8dt0.01nT5_Test2.dc",   # tests/LPsolver_tests:69
             "test4": "Data/Moments_nu0.05A0k0.5Nv16Lv5.25SpectralN8dt0.01nT5_Test4.dc"}[case]
     rows = [[float(x) for x in line.split()] for line in open(tmp_path / name) if line.strip()]
     gold = json.load(open(os.path.join(here, "golden", "reference_moments.json")))["Moments_T%s.dc" % case[1:]]
@@ -713,3 +714,52 @@ def test_other_collision_kernels(pkg, gamma, variant):
     f = f * (1 + 0.1 * np.sin(np.arange(f.size)))
     assert relerr(g16.ComputeQ(f)[0], ora.ComputeQ(f)) < TOL_SPEC
     g16.close()
+
+
+def test_second_restart_against_the_reference(tmp_path):
+    """`Second = True` (LP_ompi.cpp:529-571): the driver run for 3 steps, then restarted from the last record of its own
+    Data/U_*.dc checkpoint for 2 more -- against what the unmodified reference wrote doing the same
+    (tests/golden/ref_outputs.npz, restart_*; generator make_output_goldens.py) and, bit for bit, against an
+    uninterrupted 5-step run of the driver."""
+    import os, shutil, subprocess
+    here = os.path.dirname(__file__)
+    exe = os.path.join(os.path.dirname(here), "landau-poisson-solver_b200", "host", "lpsolver")
+    if not os.path.exists(exe):
+        pytest.skip("host driver not built")
+    ref = np.load(os.path.join(here, "golden", "ref_outputs.npz"))
+    deck = open(os.path.join(here, "golden", "LPsolver-input-test0.txt")).read()
+
+    def run(text):
+        open(tmp_path / "LPsolver-input.txt", "w").write(text)
+        out = subprocess.run([exe, "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+
+    a = deck.replace("flag     = Test0", "flag     = RestartA").replace("nT       = 5 ", "nT       = 3 ")
+    run(a)
+    name_a = str(ref["restart_name_a"])
+    assert os.path.exists(tmp_path / "Data" / name_a)                      # the reference's file name, byte for byte
+    b = deck.replace("flag     = Test0", "flag     = RestartB").replace("nT       = 5 ", "nT       = 2 ")
+    b = b.replace("First            = True", "First            = False").replace("Second           = False", "Second           = True")
+    run(b + "\n[Second]\nName = %s\n" % name_a)
+    Ub = np.fromfile(tmp_path / "Data" / name_a.replace("nT3_RestartA", "nT2_RestartB"))
+    assert relerr(Ub[::5], ref["restart_U_sample"]) < TOL_U
+    assert abs(Ub.sum() - float(ref["restart_U_sum"])) < 1e-11 * float(ref["restart_U_abs"])
+    rows = np.array([[float(x) for x in line.split()] for line in open(tmp_path / "Data" / name_a.replace("U_", "Moments_").replace("nT3_RestartA", "nT2_RestartB")) if line.strip()])
+    want = ref["restart_Moments"]
+    assert rows.shape == want.shape
+    for col in (0, 4, 5, 6, 7, 8):
+        assert np.all(np.abs(rows[:, col] - want[:, col]) <= 1.5e-7 * np.maximum(1.0, np.abs(want[:, col]))), col
+    run(deck.replace("flag     = Test0", "flag     = Straight"))
+    Uc = np.fromfile(tmp_path / "Data" / name_a.replace("nT3_RestartA", "nT5_Straight"))
+    assert np.array_equal(Ub, Uc)
+    # the Python mirror restarts from the same checkpoint and writes the same rows
+    from lpsolver_b200 import solver
+    open(tmp_path / "LPsolver-input.txt", "w").write(b.replace("RestartB", "RestartPy") + "\n[Second]\nName = %s\n" % name_a)
+    out = solver.run_from_input_file(str(tmp_path / "LPsolver-input.txt"), outdir=str(tmp_path), quiet=True)
+    rows_py = np.array([[float(x) for x in line.split()] for line in open(out) if line.strip()])
+    assert rows_py.shape == rows.shape and np.allclose(rows_py[:, [0, 4, 5, 8]], rows[:, [0, 4, 5, 8]], rtol=1e-7)
+    # a checkpoint of the wrong size is refused, as LP_ompi.cpp:553-563 does
+    open(tmp_path / "Data" / "short.dc", "wb").write(b"\0" * 800)
+    open(tmp_path / "LPsolver-input.txt", "w").write(b + "\n[Second]\nName = short.dc\n")
+    out = subprocess.run([exe, "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0

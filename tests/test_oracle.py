@@ -185,3 +185,24 @@ def test_port_matches_reference_for_other_kernels(gamma):
         R = RefOracle(gamma=gamma, **cfg)
         f = z[t + "f"] * (1 + 0.05 * np.cos(0.3 * np.arange(z[t + "f"].size)))
         assert relerr(P.ComputeQ(f), R.ComputeQ(f)) < 1e-14
+
+
+def test_port_matches_reference_at_headline_size():
+    """N = Nv = 32 (BASELINE configs 2, 4, 5): the C restatement against tests/golden/ref_n32.npz, outputs of the
+    unmodified reference at that size (make_n32_golden.py: its 8.6 GB weight table, ~9 minutes on 8 threads)."""
+    z = np.load(os.path.join(GOLD, "ref_n32.npz"))
+    cfg = json.loads(str(z["cfg_h"]))
+    P = PortOracle(homogeneous=True, **cfg)
+    Uh = P.SetInit_4H_Homo()
+    assert relerr(Uh, z["Uh0"]) < 1e-14
+    f = P.setInit_spectral(z["Uh0"])[0]
+    assert relerr(f, z["f_h"]) < 1e-15
+    fa = z["f_h"] * (1 + 0.1 * np.sin(np.arange(f.size)))
+    q = P.ComputeQ(fa)
+    assert relerr(q, z["qHat"]) < 1e-14
+    assert relerr(P.conserveMoments(z["qHat"]), z["qHat_conserved"]) < 1e-13
+    got = P.collide_step(z["Uh0"])
+    assert relerr(got, z["Uh_collide"]) < 1e-13
+    assert relerr(got - z["Uh0"], z["Uh_collide"] - z["Uh0"]) < 1e-10
+    m = P.moments(got)
+    assert np.allclose(m[[0, 4]], z["moments_h1"][[0, 4]], rtol=1e-12) and np.all(np.abs(m[1:4] - z["moments_h1"][1:4]) < 1e-12)
