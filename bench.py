@@ -8,8 +8,8 @@ is reported beside it.
 
 Workload (default): BASELINE config 5 -- Nx = 512, Nv = N = 32, the "scaling sweep 1/2/4/8" -- run as such at every
 GPU count: the 512 x-cells are sharded over the N GPUs (strong scaling; one GPU holds all 512 cells, 11 GB).  The
-reference has no bump-on-tail initial condition; the two-stream deck values are used (A = 0.5, Lx = 4,
-Lv = 5.25, nu = 0.05, dt = 0.01): throughput does not depend on the data.
+reference has no bump-on-tail initial condition; the two-stream deck values are used (A = 0.5, Lv = 5.25,
+nu = 0.05, dt = 0.01, and the deck's cell size dx = 0.125, i.e. Lx = Nx / 8: see lx_of): throughput does not depend on the data.
   --scaling weak   : BASELINE config 4 cut to its per-GPU shard, 32 x-cells per GPU (Nx = 256 on 8 GPUs).
 Also measured on one GPU and reported in the same line: config 3 (Landau damping, Nx = 64, Nv = 24, N = 16 and 24)
 and config 2 (one homogeneous cell, Nv = N = 32).
@@ -34,10 +34,19 @@ NX_STRONG = 512                                      # BASELINE config 5
 CELLS_PER_GPU_WEAK = 32                              # BASELINE config 4: Nx = 256 on 8 GPUs
 NV = 32
 NSPEC = 32
-PHYS = dict(Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)     # [TwoStream] section of the reference input deck
+PHYS = dict(Lv=5.25, nu=0.05, dt=0.01)              # [TwoStream] section of the reference input deck; Lx: see lx_of
+LX_DECK = 4.0
 A_AMP, K_WAVE = 0.5, 2 * np.pi / 4.
 OUT = sys.stdout
 METRIC, UNIT = "collision_cell_evals_per_s", "evals/s"
+
+
+def lx_of(Nx):
+    """Domain length for Nx cells.  The deck's Lx = 4 with dt = 0.01 is stable for its own mesh (dx = 0.125: CFL = Lv dt / dx
+    = 0.42) but not for Nx = 512 (CFL 6.7: the explicit SSP-RK3 DG advection blows up to NaN within 20 steps); the cell
+    size of the deck is kept instead and the periodic box grows with Nx (Lx = Nx / 8, a whole number of the k = 2 pi / 4
+    perturbation's wavelengths), dt = 0.01 as in every deck of the reference."""
+    return max(LX_DECK, Nx / 8.)
 
 
 def pairs_per_eval(N):
@@ -101,7 +110,7 @@ def cpu_reference(reps, warm, slices):
     step-versus-step figure exists next to the isolated-operator one (LP_ompi.cpp:883-886 prints the whole loop)."""
     from oracle import oracle as orc
     threads = orc.set_num_threads()                   # torchrun exports OMP_NUM_THREADS=1: set it explicitly
-    cfg = dict(Nx=1, Nv=NV, N=NSPEC, homogeneous=True, **PHYS)
+    cfg = dict(Nx=1, Nv=NV, N=NSPEC, homogeneous=True, Lx=LX_DECK, **PHYS)
     kind, t_init = "port", time.time()
     ora = None
     if orc.have_ref():
@@ -150,7 +159,7 @@ def cpu_reference(reps, warm, slices):
 
 
 def po_ld(orc, nx):
-    p = orc.PortOracle(Nx=nx, Nv=NV, N=NSPEC, **PHYS)
+    p = orc.PortOracle(Nx=nx, Nv=NV, N=NSPEC, Lx=LX_DECK, **PHYS)
     return p.SetInit_LD(A_AMP, K_WAVE, True)
 
 
@@ -171,7 +180,7 @@ def workload_config(world, scaling):
     else:
         name = ("BASELINE config 5: Landau-Poisson timestep (SSP-RK3 DG advection + RK4 spectral Landau collision), Nx=%d, Nv=%d^3, N=%d, "
                 "sharded over %d GPU(s); two-stream deck values (the reference has no bump-on-tail IC)" % (Nx, NV, NSPEC, world))
-    return {"workload": name, "Nx": Nx, "Nv": NV, "N": NSPEC, "cells_per_gpu": per, "evals_per_step": 4 * Nx,
+    return {"workload": name, "Nx": Nx, "Nv": NV, "N": NSPEC, "Lx": lx_of(Nx), "dt": PHYS["dt"], "nu": PHYS["nu"], "cells_per_gpu": per, "evals_per_step": 4 * Nx,
             "parallelism": "x-cells sharded over %d GPU(s)" % world}
 
 
@@ -228,10 +237,10 @@ def main():
     assert world == args.gpus, "--gpus must equal the number of launched ranks"
 
     Nx, per_gpu = shape(world, args.scaling)
-    s = solver.ShardedSolver(Nx, NV, NSPEC, homogeneous=False, rank=rank, world=world, device=local, dist=dist, **PHYS)
+    s = solver.ShardedSolver(Nx, NV, NSPEC, homogeneous=False, rank=rank, world=world, device=local, dist=dist, Lx=lx_of(Nx), **PHYS)
     g = s.g
     g.set_stream(torch.cuda.current_stream().cuda_stream)
-    U0 = solver.set_init_ld(Nx, NV, PHYS["Lv"], PHYS["Lx"], A_AMP, K_WAVE, True, s.x_begin, s.x_count)
+    U0 = solver.set_init_ld(Nx, NV, PHYS["Lv"], lx_of(Nx), A_AMP, K_WAVE, True, s.x_begin, s.x_count)
     host = torch.from_numpy(U0).pin_memory()
     host_np = host.numpy()
     back = torch.empty_like(host).pin_memory()
@@ -422,7 +431,7 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) * 1e-3
         # config 2: one homogeneous cell
-        h = solver.ShardedSolver(1, NV, NSPEC, homogeneous=True, device=local, **PHYS)
+        h = solver.ShardedSolver(1, NV, NSPEC, homogeneous=True, device=local, Lx=LX_DECK, **PHYS)
         h.g.set_stream(torch.cuda.current_stream().cuda_stream)
         h.upload(solver.set_init_4h_homo(NV, PHYS["Lv"]))
         nh = 200
@@ -445,9 +454,9 @@ def main():
         # the north star's direct O(N^6) sum (k_computeQ_tiled, computeq_variant = 3) on 32 cells: FP64-pipe bound, 10 flop per pair
         try:
             nd = 32
-            d = pkg.LPGpu(nd, NV, NSPEC, homogeneous=False, device=local, computeq_variant=3, **PHYS)
+            d = pkg.LPGpu(nd, NV, NSPEC, homogeneous=False, device=local, computeq_variant=3, Lx=LX_DECK, **PHYS)
             d.set_stream(torch.cuda.current_stream().cuda_stream)
-            d.upload_U(solver.set_init_ld(nd, NV, PHYS["Lv"], PHYS["Lx"], A_AMP, K_WAVE, True))
+            d.upload_U(solver.set_init_ld(nd, NV, PHYS["Lv"], LX_DECK, A_AMP, K_WAVE, True))
             d.sample_device()
             for _ in range(2):
                 d.eval_device(nd)
@@ -470,8 +479,8 @@ def main():
         try:
             NFLIGHT, nxp = 3, 64
             streams = [torch.cuda.Stream() for _ in range(NFLIGHT)]
-            ctxs = [solver.ShardedSolver(nxp, NV, NSPEC, homogeneous=False, device=local, stream=st, **PHYS) for st in streams]
-            Up = solver.set_init_ld(nxp, NV, PHYS["Lv"], PHYS["Lx"], A_AMP, K_WAVE, True)
+            ctxs = [solver.ShardedSolver(nxp, NV, NSPEC, homogeneous=False, device=local, stream=st, Lx=lx_of(nxp), **PHYS) for st in streams]
+            Up = solver.set_init_ld(nxp, NV, PHYS["Lv"], lx_of(nxp), A_AMP, K_WAVE, True)
             hosts = [torch.from_numpy(Up.copy()).pin_memory() for _ in range(NFLIGHT)]
             backs = [torch.empty_like(hosts[0]).pin_memory() for _ in range(NFLIGHT)]
 
