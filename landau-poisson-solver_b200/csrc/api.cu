@@ -73,6 +73,8 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   c->ncell = c->p.x_count;
   c->stream = 0;
   c->launches = 0;
+  c->num_sms = 148;
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) c->num_sms = v; }
   c->peer_timeout_s = getenv("LPGPU_PEER_TIMEOUT_S") ? atof(getenv("LPGPU_PEER_TIMEOUT_S")) : 60.;
   if (!(c->peer_timeout_s > 0.)) c->peer_timeout_s = 60.;
   lp_build_tables(c->p, c->tab);

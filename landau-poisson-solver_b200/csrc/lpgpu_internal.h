@@ -44,6 +44,7 @@ struct lpgpu_ctx {
   lpgpu_params p;
   LpTables tab;
   int N3, sv, ncell;       // N^3, Nv^3, local cells (x_count or 1)
+  int num_sms;             // multiprocessors of the device (grid of the persistent kernels)
   cudaStream_t stream;
   long long launches;
   // ---- device tables

@@ -57,6 +57,30 @@ __global__ void __launch_bounds__(NT, MINB) k_thirds(double2 *out, int iters)
       fwd_third<L>(a0, a1, r, y);
       #pragma unroll
       for (int q = 0; q < L; q++) mine[q * N + lane] = make_double2(y[q].x * 0.25, y[q].y * 0.25);
+    } else if (MODE == 3 || (MODE == 5 && warp >= 4)) {
+      // y-like with every load live: the two halves of the region swap roles every iteration
+      const int o = (it & 1) * 16 * N;
+      #pragma unroll
+      for (int l = 0; l < L; l++) { a0[l] = mine[(o + l * N + lane) % (32 * N)]; a1[l] = mine[(o + (l + L) * N + lane) % (32 * N)]; }
+      fwd_third<L>(a0, a1, r, y);
+      #pragma unroll
+      for (int q = 0; q < L; q++) mine[((o ^ (16 * N)) + q * N + lane) % (32 * N)] = make_double2(y[q].x * 0.25, y[q].y * 0.25);
+    } else if (MODE == 4 || MODE == 5) {
+      // x-like: two thirds from 64 live loads, products folded into one complex accumulator (no register pressure from acc)
+      double2 u[L];
+      const int o = (it & 1) * N;
+      #pragma unroll
+      for (int l = 0; l < L; l++) { a0[l] = mine[o + l * N + lane]; a1[l] = mine[o + (l + L - 1) * N + lane]; }
+      fwd_third<L>(a0, a1, r, u);
+      #pragma unroll
+      for (int l = 0; l < L; l++) { a0[l] = mine[N - o + l * N + lane]; a1[l] = mine[N - o + (l + L - 1) * N + lane]; }
+      fwd_third<L>(a0, a1, r, y);
+      #pragma unroll
+      for (int q = 0; q < L; q++) {
+        acc[0].x += u[q].x * y[q].x - u[q].y * y[q].y;
+        acc[0].y += u[q].x * y[q].y + u[q].y * y[q].x;
+      }
+      mine[(it & 15) * N + lane] = acc[0];
     } else {
       double2 u[L];
       #pragma unroll
@@ -108,7 +132,7 @@ void run(const char *name, int iters, double2 *d, int nsm)
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     if (ms < best) best = ms;
   }
-  const double thirds = (double)grid * NT * iters * (MODE == 2 ? 2 : 1);
+  const double thirds = (double)grid * NT * iters * (MODE == 2 || MODE == 4 ? 2. : MODE == 5 ? 1.5 : 1.);
   // textbook flop of a third: a 48-point line is 5 M log2 M = 1340 flop -> 447 per third
   printf("%-40s regs %3d occ %d warps/SM %2d : %8.3f ms  %7.2f Gthirds/s  %6.2f TFLOP/s(textbook)\n", name, fa.numRegs, occ, occ * NT / 32, best,
          thirds / best * 1e-6, thirds * 446.8 / best * 1e-9);
@@ -146,6 +170,13 @@ int main()
   run<0, 384, 1>("regs  384x1", it, d, nsm);
   run<0, 256, 2>("regs  256x2 (<=128 regs)", it, d, nsm);
   run<0, 512, 1>("regs  512x1 (<=128 regs)", it, d, nsm);
+  run<3, 128, 1>("ylive 128x1", it, d, nsm);
+  run<3, 256, 1>("ylive 256x1", it, d, nsm);
+  run<3, 384, 1>("ylive 384x1", it, d, nsm);
+  run<4, 128, 1>("xlive 128x1", it / 2, d, nsm);
+  run<4, 256, 1>("xlive 256x1", it / 2, d, nsm);
+  run<4, 384, 1>("xlive 384x1", it / 2, d, nsm);
+  run<5, 256, 1>("mixed 256x1 (warps 0-3 x, 4-7 y)", it / 2, d, nsm);
   run<1, 256, 1>("ylike 256x1", it, d, nsm);
   run<1, 192, 2>("ylike 192x2", it, d, nsm);
   run<1, 384, 1>("ylike 384x1", it, d, nsm);
