@@ -763,3 +763,35 @@ def test_second_restart_against_the_reference(tmp_path):
     open(tmp_path / "LPsolver-input.txt", "w").write(b + "\n[Second]\nName = short.dc\n")
     out = subprocess.run([exe, "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert out.returncode != 0
+
+
+@pytest.mark.parametrize("case", ["test0", "test1", "test2", "test3", "test4"])
+def test_reference_main_linked_against_the_library(case, tmp_path):
+    """The drop-in boundary exercised by the reference's OWN driver: oracle/_ref/solver_gpu is /root/reference's
+    LP_ompi.cpp with oracle/ref_gpu.patch applied (RK3, setInit_spectral, ComputeQ, conserveMoments, RK4
+    and the N^6 weight tables replaced by include/lpgpu.h calls), compiled with the rest of the reference's sources and
+    linked against liblpgpu.so.  Its parsing, initial conditions, host diagnostics and file output are the reference's;
+    every deck of the reference's test suite must reproduce its golden Moments file (tests/LPsolver_tests,
+    moment_differ.sh) -- all printed digits of the non-noise columns, in fact."""
+    import json, os, shutil, subprocess
+    here = os.path.dirname(__file__)
+    exe = os.path.join(os.path.dirname(here), "oracle", "_ref", "solver_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/solver_gpu not built (needs /root/reference at build time)")
+    shutil.copy(os.path.join(here, "golden", "LPsolver-input-%s.txt" % case), tmp_path / "LPsolver-input.txt")
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    files = [f for f in os.listdir(tmp_path / "Data") if f.startswith("Moments_")]
+    assert len(files) == 1, files
+    rows = [[float(x) for x in line.split()] for line in open(tmp_path / "Data" / files[0]) if line.strip()]
+    gold = json.load(open(os.path.join(here, "golden", "reference_moments.json")))["Moments_T%s.dc" % case[1:]]
+    assert len(rows) == 6
+    r, g = rows[5], gold[5]
+    assert abs(r[0] - g[0]) <= 2e-6                                      # moment_differ.sh:9,30
+    assert all(abs(r[d] - g[d]) <= 1e-10 for d in (1, 2, 3))              # :10-12
+    last = len(g) - 1
+    assert r[last] - g[last] <= 3e-5 and g[last] - r[last] <= (1e-7 if g[last] < 10 else 1e-6)
+    homog = case == "test4"
+    for row, grow in zip(rows, gold):
+        for col in ([0, 7] if homog else [0, 1, 4, 5, 6, 7, 8] if case == "test1" else [0, 4, 5, 6, 7, 8]):
+            assert abs(row[col] - grow[col]) <= 1.5e-7 * max(1.0, abs(grow[col])), (row, grow, col)
