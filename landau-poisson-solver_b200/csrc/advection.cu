@@ -96,12 +96,11 @@ int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes)
 // Doping = True: computePhi_x_0_Doping, Int_E_Doping, Int_E1st_Doping, Int_E2nd_Doping (FieldCalculations.cpp:427-450,
 // 585-676) with the step profile ND(i) = NH for i <= a_i or i > b_i, NL between (:413-425)
 struct DopingParams { int on, a_i, b_i; double NL, NH, eps; };
-__global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
-                                                    double dx, double Lx, DopingParams D)
+// body of the scan, shared by k_field_scan and the fused k_field_finish; every thread of the (single) block calls it
+__device__ __forceinline__ void field_scan_body(const double *ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
+                                                double dx, double Lx, const DopingParams &D, double *sms, double *s_ce)
 {
-  extern __shared__ double sms[];          // m[Nx] | s/12 [Nx] | prefix P[Nx]
   double *sm = sms, *s12 = sms + Nx, *sP = sms + 2 * Nx;
-  __shared__ double s_ce;
   for (int q = threadIdx.x; q < Nx; q += blockDim.x) { sm[q] = ms_all[2 * q]; s12[q] = ms_all[2 * q + 1] / 12.; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -110,15 +109,15 @@ __global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ m
     for (int q = 0; q < Nx; q++) { sP[q] = P; acc += P + 0.5 * sm[q] - s12[q]; P += sm[q]; }
     if (D.on) {
       const double a_val = (D.a_i + 1) * dx, b_val = (D.b_i + 1) * dx, Phi_Lx = 1, tmp = acc * dx * dx;
-      s_ce = Phi_Lx / Lx + 0.5 * D.NH * Lx / D.eps + (D.NL - D.NH) * (b_val - a_val) / D.eps
+      *s_ce = Phi_Lx / Lx + 0.5 * D.NH * Lx / D.eps + (D.NL - D.NH) * (b_val - a_val) / D.eps
              - (0.5 * (D.NL - D.NH) * (b_val * b_val - a_val * a_val) + tmp) / (Lx * D.eps);
     } else {
-      s_ce = 0.5 * Lx - acc * dx * dx / Lx;
+      *s_ce = 0.5 * Lx - acc * dx * dx / Lx;
     }
-    fld[0] = s_ce;
+    fld[0] = *s_ce;
   }
   __syncthreads();
-  const double ce = s_ce;
+  const double ce = *s_ce;
   for (int q = x_begin + threadIdx.x; q < x_begin + x_count; q += blockDim.x) {
     const double m = sm[q], s = ms_all[2 * q + 1], P = sP[q];
     const double xi = (q + 0.5) * dx, xl = ((q - 0.5) + 0.5) * dx, c2 = s * dx / 2., cp = dx * P;
@@ -141,6 +140,13 @@ __global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ m
     o[2] = (1 - m) * dx * dx / 12.;
     o[3] = (-cp - ce + (m * xl + 0.25 * c2)) * dx / 12. + (1 - m) * dx * xi / 12. - c2 * dx / 80.;
   }
+}
+__global__ void __launch_bounds__(256) k_field_scan(const double *__restrict__ ms_all, double *__restrict__ fld, int Nx, int x_begin, int x_count,
+                                                    double dx, double Lx, DopingParams D)
+{
+  extern __shared__ double sms[];          // m[Nx] | s/12 [Nx] | prefix P[Nx]
+  __shared__ double s_ce;
+  field_scan_body(ms_all, fld, Nx, x_begin, x_count, dx, Lx, D, sms, &s_ce);
 }
 int lp_launch_field_scan(lpgpu_ctx *c)
 {
@@ -379,6 +385,91 @@ __global__ void __launch_bounds__(256) k_peer_wait(ull *mbox, int world, double 
   const bool poisoned = *reinterpret_cast<volatile ull *>(mbox + LP_MB_ERR) != 0;     // sticky: this wait or an earlier one
   const double *src = reinterpret_cast<const double *>(mbox + LP_MB_MS) + (ed & 1) * Nx2;
   for (int i = threadIdx.x; i < Nx2; i += blockDim.x) ms_all[i] = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : __ldcg(src + i);
+}
+// ---------------------------------------------------------------------------------------------------------------------
+// The serial tail of an SSP-RK3 stage's field solve in ONE single-block kernel (it was four launches and a copy): fold the
+// per-cell partial density sums in their fixed order; PEER: store them into every rank's mailbox and raise the flags, wait
+// for every rank's densities and for both halo planes of this stage, gather; then the Nx-long scan.  The boundary planes
+// travel meanwhile (k_peer_put_halo on the context's side stream, api.cu), so a stage's exchange costs one small kernel on
+// the critical path instead of the chain put -> reduce -> fold -> publish -> wait -> scan.
+template <bool PEER>
+__global__ void __launch_bounds__(256) k_field_finish(const double *__restrict__ part, int nchunk, double scalev, double *ms_local, double *ms_all,
+                                                      double *__restrict__ fld, int Nx, int x_begin, int ncell, double dx, double Lx, DopingParams D,
+                                                      PeerBoxes pb, int world, int rank, ull timeout_ns)
+{
+  extern __shared__ double sms[];
+  __shared__ double s_ce;
+  for (int cell = threadIdx.x; cell < ncell; cell += blockDim.x) {
+    double a, b;
+    if (nchunk > 0) {
+      a = 0.; b = 0.;
+      for (int k = 0; k < nchunk; k++) { a += part[2 * (cell * nchunk + k)]; b += part[2 * (cell * nchunk + k) + 1]; }
+      a *= scalev; b *= scalev;
+      ms_local[2 * cell] = a; ms_local[2 * cell + 1] = b;
+    } else {                                   // small velocity grids: k_field_reduce has written ms_local
+      a = ms_local[2 * cell]; b = ms_local[2 * cell + 1];
+    }
+    if (!PEER) { ms_all[2 * (x_begin + cell)] = a; ms_all[2 * (x_begin + cell) + 1] = b; }
+  }
+  __syncthreads();
+  if (PEER) {
+    ull *mine = pb.box[rank];
+    const ull e = mine[LP_MB_EPOCH_D] + 1, eh = mine[LP_MB_EPOCH_H];
+    const int n2 = 2 * ncell, Nx2 = 2 * Nx;
+    for (int t = threadIdx.x; t < n2 * world; t += blockDim.x) {
+      const int r = t / n2, i = t % n2;
+      reinterpret_cast<double *>(pb.box[r] + LP_MB_MS)[(e & 1) * Nx2 + 2 * x_begin + i] = ms_local[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) st_release_sys(pb.box[threadIdx.x] + LP_MB_DFLAG + rank, e);
+    if (threadIdx.x == 0) mine[LP_MB_EPOCH_D] = e;
+    if (threadIdx.x < world + 2) {
+      const ull *flag = threadIdx.x < world ? mine + LP_MB_DFLAG + threadIdx.x : mine + LP_MB_HFLAG + (threadIdx.x - world);
+      const ull want = threadIdx.x < world ? e : eh;
+      const ull t0 = global_ns();
+      while (ld_acquire_sys(flag) < want) {
+        __nanosleep(100);
+        if (global_ns() - t0 > timeout_ns) { atomicAdd(mine + LP_MB_ERR, 1ULL); break; }
+      }
+    }
+    __syncthreads();
+    const bool poisoned = *reinterpret_cast<volatile ull *>(mine + LP_MB_ERR) != 0;
+    const double *src = reinterpret_cast<const double *>(mine + LP_MB_MS) + (e & 1) * Nx2;
+    for (int i = threadIdx.x; i < Nx2; i += blockDim.x) ms_all[i] = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : __ldcg(src + i);
+  }
+  __syncthreads();
+  field_scan_body(ms_all, fld, Nx, x_begin, ncell, dx, Lx, D, sms, &s_ce);
+}
+// reduce + the fused tail; peer = false needs a context that owns all of x
+int lp_launch_field_stage(lpgpu_ctx *c, const double *planes, bool peer)
+{
+  int nchunk = 0;
+  if (c->sv < 8192) {
+    k_field_reduce<<<c->ncell, 256, 0, c->stream>>>(planes, c->d_ms_local, c->sv, c->tab.scalev);
+  } else {
+    k_field_reduce_part<<<dim3(c->ncell, LP_FR_CH), 256, 0, c->stream>>>(planes, c->d_ms_part, c->sv);
+    nchunk = LP_FR_CH;
+  }
+  LP_LAUNCHED(c);
+  const double dx = c->p.Lx / c->p.Nx;
+  DopingParams D = {c->p.doping, c->p.Nx / 3 - 1, 2 * c->p.Nx / 3 - 1, c->p.NL, c->p.NH, c->p.eps};
+  const size_t smem = (size_t)3 * c->p.Nx * sizeof(double);
+  PeerBoxes pb;
+  for (int r = 0; r < LP_MAX_PEERS; r++) pb.box[r] = (peer && r < c->peer_world) ? c->peer_mbox[r] : nullptr;
+  if (smem > 48 * 1024 && !c->finish_attr) {
+    LP_CUDA(cudaFuncSetAttribute(k_field_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LP_CUDA(cudaFuncSetAttribute(k_field_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->finish_attr = true;
+  }
+  if (peer)
+    k_field_finish<true><<<1, 256, smem, c->stream>>>(c->d_ms_part, nchunk, c->tab.scalev, c->d_ms_local, c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell,
+                                                      dx, c->p.Lx, D, pb, c->peer_world, c->peer_rank, (ull)(c->peer_timeout_s * 1e9));
+  else
+    k_field_finish<false><<<1, 256, smem, c->stream>>>(c->d_ms_part, nchunk, c->tab.scalev, c->d_ms_local, c->d_ms_all, c->d_fld, c->p.Nx, c->p.x_begin, c->ncell,
+                                                       dx, c->p.Lx, D, pb, 1, 0, 0ULL);
+  LP_LAUNCHED(c);
+  return LPGPU_OK;
 }
 int lp_launch_peer_put_halo(lpgpu_ctx *c, int stage)
 {

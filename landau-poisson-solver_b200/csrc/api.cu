@@ -158,6 +158,9 @@ int lpgpu_finalize(lpgpu_ctx *c)
   if (c->gstream) cudaStreamDestroy(c->gstream);
   for (void *p : c->peer_opened) cudaIpcCloseMemHandle(p);
   if (c->d_mbox) cudaFree(c->d_mbox);
+  if (c->halo_stream) cudaStreamDestroy(c->halo_stream);
+  if (c->halo_fork) cudaEventDestroy(c->halo_fork);
+  if (c->halo_join) cudaEventDestroy(c->halo_join);
   if (c->diag_view) delete c->diag_view;
   if (c->d_snap) cudaFree(c->d_snap);
   if (c->d_diag_scratch) cudaFree(c->d_diag_scratch);
@@ -271,14 +274,25 @@ int lpgpu_advect_apply(lpgpu_ctx *c, int stage)
 static int advect_rk3_async(lpgpu_ctx *c)
 {
   if (c->ncell != c->p.Nx && c->peer_ready) {
-    // sharded, peers mapped: the exchange is kernels on this stream (advection.cu), no host or NCCL call per stage
+    // sharded, peers mapped: the exchange is kernels (advection.cu), no host or NCCL call per stage.  The boundary planes
+    // go out on a side stream while the densities are reduced, published, awaited and scanned on the main one.
+    if (!c->halo_stream) {
+      LP_CUDA(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
+      LP_CUDA(cudaEventCreateWithFlags(&c->halo_fork, cudaEventDisableTiming));
+      LP_CUDA(cudaEventCreateWithFlags(&c->halo_join, cudaEventDisableTiming));
+    }
+    cudaStream_t main = c->stream;
     for (int s = 0; s < 3; s++) {
-      LP_TRY(lp_launch_peer_put_halo(c, s));
-      LP_TRY(lp_launch_field_reduce(c, c->d_U[s]));
-      LP_TRY(lp_launch_peer_publish_density(c));
-      LP_TRY(lp_launch_peer_wait(c));
+      LP_CUDA(cudaEventRecord(c->halo_fork, main));
+      LP_CUDA(cudaStreamWaitEvent(c->halo_stream, c->halo_fork, 0));
+      c->stream = c->halo_stream;
+      int rc = lp_launch_peer_put_halo(c, s);
+      c->stream = main;
+      LP_TRY(rc);
+      LP_CUDA(cudaEventRecord(c->halo_join, c->halo_stream));
+      LP_TRY(lp_launch_field_stage(c, c->d_U[s], true));
+      LP_CUDA(cudaStreamWaitEvent(main, c->halo_join, 0));
       LP_TRY(lp_launch_wall_halo(c, c->d_U[s]));
-      LP_TRY(lp_launch_field_scan(c));
       LP_TRY(lp_launch_dg_stage(c, s));
     }
     return LPGPU_OK;
@@ -286,9 +300,7 @@ static int advect_rk3_async(lpgpu_ctx *c)
   if (c->ncell != c->p.Nx) { lp_set_error("lpgpu_advect_rk3: context is a shard; map the peers (lpgpu_peer_import) or drive the per-stage calls"); return LPGPU_EINVAL; }
   for (int s = 0; s < 3; s++) {
     LP_TRY(lp_launch_local_halo(c, c->d_U[s]));
-    LP_TRY(lp_launch_field_reduce(c, c->d_U[s]));
-    LP_CUDA(cudaMemcpyAsync(c->d_ms_all, c->d_ms_local, (size_t)2 * c->ncell * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    LP_TRY(lp_launch_field_scan(c));
+    LP_TRY(lp_launch_field_stage(c, c->d_U[s], false));
     LP_TRY(lp_launch_dg_stage(c, s));
   }
   return LPGPU_OK;

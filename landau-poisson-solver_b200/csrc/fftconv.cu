@@ -12,7 +12,6 @@
 // Sizes whose M has another prime factor use the tiled direct kernel (computeq.cu).
 #include "lpgpu_internal.h"
 #include "fc3.cuh"
-#include "fc3p.cuh"
 
 #define LP_LAUNCHED(c)                                  \
   do {                                                  \
@@ -232,6 +231,34 @@ __global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ C
   }
 }
 
+// ---- mbarrier / bulk-copy (TMA) helpers.  The precomputed kernel symbols of F1 (seven N x N slabs per CTA) and the
+// planes of k_fc3_f2_tmem (two 16 KB planes per product) arrive as cp.async.bulk copies issued by ONE thread and completed
+// on an mbarrier in bytes, instead of thousands of 16-byte cp.async spread over the CTA's threads.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
+{
+  asm volatile("{\n"
+               ".reg .pred P1;\n"
+               "LAB_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+               "@P1 bra DONE;\n"
+               "bra LAB_WAIT;\n"
+               "DONE:\n"
+               "}\n" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// one contiguous block global -> shared through the TMA unit; completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Register-resident pipeline (fc3.cuh): F1 z-lines -> F2 (y, x, product, inverse x, inverse y) -> F3 inverse z.
 // FUSED: `in` is the output of the first fft3D pass (lp_launch_fft3d_jk); the N lines along i of this y slab are
@@ -246,12 +273,20 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
 {
   typedef fc3::F1<L> K;
   constexpr int N = K::N;
-  extern __shared__ double2 smf[];
+  extern __shared__ __align__(128) double2 smf[];
   double2 *FS = smf;
   double *Gs = reinterpret_cast<double *>(FS + K::SMEM_C2), *sE = Gs + 7 * N * N;
   double2 *FM = mhat ? reinterpret_cast<double2 *>(sE + N) : nullptr;
   const int y = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x;
-  K::issue_g(tid, y, Gt, Gs);
+  __shared__ __align__(8) unsigned long long s_bar;
+  if (tid == 0) {                            // the seven symbol slabs Gt[a][y][.][.] of this y: one bulk copy (TMA) each
+    constexpr unsigned SLAB_BYTES = N * N * sizeof(double);
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_expect_tx(&s_bar, 7 * SLAB_BYTES);
+    for (int a = 0; a < 7; a++) bulk_load(Gs + a * N * N, Gt + ((long long)a * N + y) * N * N, SLAB_BYTES, &s_bar);
+  }
   if (mhat) K::load_slab(tid, cell, y, mhat, FM);
   if (FUSED) {
     // the N lines along i of this slab, four threads per line: thread (j, k) forms the decimated sequence
@@ -297,8 +332,8 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
   } else {
     K::load(tid, cell, y, in, E, FS, sE);
   }
-  fc3::cp_wait_all();
-  __syncthreads();
+  __syncthreads();                           // the fhat slab is complete (and s_bar initialised)
+  mbar_wait(&s_bar, 0u);                     // the symbols have landed
   if (gridDim.z == 1) K::lines(tid, cell, y, Gs, N * N, FS, sE, Z, 0, 5, FM);
   else K::lines(tid, cell, y, Gs, N * N, FS, sE, Z, blockIdx.z, blockIdx.z + 1, FM);     // few cells: one round per CTA
 }
@@ -379,6 +414,7 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   typedef fc3::F2<L> K;
   extern __shared__ double2 smf[];
   __shared__ unsigned s_tmem;
+  __shared__ __align__(8) unsigned long long s_bar;        // completion of the bulk loads of one product's planes
   double2 *IN = smf, *Y = IN + K::IN_C2;
   double *sE = reinterpret_cast<double *>(Y + K::Y_C2);
   const int kz = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
@@ -390,7 +426,19 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   int p_begin, p_end;
   K::psplit(blockIdx.z, NSPLIT, p_begin, p_end);       // gridDim.z = 3: the seven products split over three CTAs
   C += blockIdx.z * split_stride;
-  K::issue_loads(tid, cell, kz, p_begin, Z, IN);
+  // the planes u_p and (p != 1) the v source of p: one 16 KB bulk copy (TMA) each into IN, completed on s_bar in bytes
+  constexpr unsigned PLANE_BYTES = K::N * K::N * sizeof(double2);
+  auto issue_planes = [&](int p) {
+    mbar_expect_tx(&s_bar, p == 1 ? PLANE_BYTES : 2 * PLANE_BYTES);
+    bulk_load(IN, K::plane(Z, cell, p, kz), PLANE_BYTES, &s_bar);
+    if (p != 1) bulk_load(IN + K::N * K::N, K::plane(Z, cell, 7 + fc3::zpow_of(p), kz), PLANE_BYTES, &s_bar);   // p = 1 reuses the y-transformed v of p = 0
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    issue_planes(p_begin);
+  }
   for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -404,11 +452,11 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   const bool xok = K::xtask(tid, r, ky);
   #pragma unroll 1
   for (int p = p_begin; p < p_end; p++) {
-    fc3::cp_wait_all();
-    __syncthreads();                       // planes of p landed; every x-stage read of Y from p-1 is done
+    mbar_wait(&s_bar, (unsigned)(p - p_begin) & 1u);   // planes of p landed
+    __syncthreads();                       // every x-stage read of Y from p-1 is done
     K::ystage(tid, p, IN, sE, Y);
     __syncthreads();                       // Y complete; IN consumed
-    if (p + 1 < p_end) K::issue_loads(tid, cell, kz, p + 1, Z, IN);
+    if (p + 1 < p_end && tid == 0) issue_planes(p + 1);
     if (warp < XW) {
       double2 a0[L], a1[L], uh[L], vh[L];
       #pragma unroll
@@ -465,201 +513,6 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   K::yinverse(tid, Y, IN);                 // T2 aliases IN
   __syncthreads();
   K::store(tid, cell, kz, IN, C);
-}
-// ---- F2, warp-specialised and persistent (fc3p.cuh): k_fc3_f2s, the y/x-stage kernel for N = 32 and few cells -------
-// In k_fc3_f2_tmem every warp runs the y stage, then (five of six) the x stage, between CTA-wide barriers (ncu,
-// profiles/r01s: barrier stalls 25 %, FP64 pipe 48 % busy).  Here the two stages are different warps of one persistent CTA
-// per SM, coupled only by mbarriers:
-//   * y-warps (lane = x) run one product AHEAD of the x-warps through a double-buffered Y; the planes they read are staged
-//     by bulk copies (TMA: cp.async.bulk + mbarrier complete_tx) in a ring of four 16 KB slots;
-//   * x-warps (144 tasks (r, ky)) transform the two lines of each task, multiply and accumulate; the u transform and the
-//     accumulators wait in tensor memory;
-//   * at the end of a plane the x-warps write the inverse x transform into T, and the y-warps -- after the first two
-//     products of the NEXT plane, so that the x-warps never wait -- run the inverse y transform and store C.
-// The CTA loops over the planes blockIdx.x, blockIdx.x + gridDim.x, ...  What it buys and what it does not is measured
-// in profiles/r02_f2_kernels.md: the barrier stalls are gone, but the kernel needs its shared-memory -> register
-// bandwidth (19.3 k wavefront cycles per plane at 128 B per clock) about as long as its FP64 pipe (17.9 k cycles), and
-// warps that hand planes to each other do not overlap the two the way free-running warps do.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
-{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(b)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
-{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(b)) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
-{
-  asm volatile("{\n"
-               ".reg .pred P1;\n"
-               "LAB_WAIT:\n"
-               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-               "@P1 bra DONE;\n"
-               "bra LAB_WAIT;\n"
-               "DONE:\n"
-               "}\n" :: "r"(smem_u32(b)), "r"(parity) : "memory");
-}
-// one contiguous block global -> shared through the TMA unit; completion is counted in bytes on `bar`
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
-
-#define LP_F2P_STAGES 4
-// Twelve warps (<= 168 registers).  A first version with eight (three y-warps doing both arrays, accumulators in
-// registers, 242 registers) had the y-warps on the critical path -- two transforms per product each, then the inverse y and
-// the store -- with the x-warps waiting a third of the time (profiles/r02d_f2p_ncu_summary.txt).  Here every y-warp owns
-// ONE (array, r): warps 4-6 the u planes, warps 8-10 the v planes; the v-warps run the inverse y at the end of a plane
-// (their p = 1 item is only a rescale), the u-warps store C; warp 7 does nothing but issue the bulk loads; x-warps 0-3, 11.
-// Per sub-partition (warp id mod 4): X + Yu + Yv = 2.2 + 1 + 1 transform units per product on three of them, X + X/2 on
-// the fourth.  The accumulators live in tensor memory (168 registers per thread leave no room for them).
-__global__ void __launch_bounds__(384, 1) k_fc3_f2s(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C, int nplanes)
-{
-  typedef fc3::F2P K;
-  constexpr int L = K::L, N = K::N, M = K::M, NS = LP_F2P_STAGES;
-  constexpr unsigned PER = 128, COLS = 256, PLANE_BYTES = K::PLANE_C2 * sizeof(double2);
-  extern __shared__ __align__(128) double2 smf[];
-  __shared__ unsigned s_tmem;
-  __shared__ __align__(8) unsigned long long bars[2 * NS + 8];
-  double2 *INs = smf, *Ys = INs + NS * K::PLANE_C2, *T = Ys + 2 * K::YBUF_C2;
-  double *sE = reinterpret_cast<double *>(T + K::T_C2);
-  unsigned long long *in_full = bars, *in_empty = bars + NS, *y_full = bars + 2 * NS, *y_empty = y_full + 2, *t_full = y_empty + 2, *t_empty = t_full + 1,
-                     *t2_full = t_empty + 1;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < NS; s++) { mbar_init(in_full + s, 1); mbar_init(in_empty + s, K::NYT); }
-    for (int b = 0; b < 2; b++) { mbar_init(y_full + b, 2 * K::NYT); mbar_init(y_empty + b, K::NXT); }
-    mbar_init(t_full, K::NXT); mbar_init(t_empty, K::NYT); mbar_init(t2_full, K::NYT);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  }
-  if (warp == 0) {
-    const unsigned dst = smem_u32(&s_tmem);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(dst), "r"(COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  for (int i = tid; i < N; i += 384) sE[i] = E[i];
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const unsigned tbase = s_tmem;
-  const int nmine = ((int)blockIdx.x < nplanes) ? (nplanes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-  if (warp < 4 || warp == 11) {
-    // ================================ x role ================================
-    const int xt = warp < 4 ? tid : 128 + lane;
-    int r, ky;
-    const bool ok = K::xtask(xt, r, ky);
-    const unsigned tq = tbase + ((unsigned)((warp & 3) * 32) << 16) + (warp == 11 ? PER : 0u);
-    int item = 0;
-    #pragma unroll 1
-    for (int k = 0; k < nmine; k++) {
-      #pragma unroll 1
-      for (int p = 0; p < 7; p++, item++) {
-        const int buf = item & 1;
-        mbar_wait(y_full + buf, (unsigned)(item >> 1) & 1u);
-        const double2 *Yb = Ys + buf * K::YBUF_C2;
-        double2 a0[L], a1[L], uh[L], vh[L];
-        K::xload(Yb, ky, a0, a1);
-        fc3::fwd_third<L>(a0, a1, r, uh);
-        __syncwarp();
-        #pragma unroll
-        for (int c4 = 0; c4 < L / 4; c4++) { double2 t4[4] = {uh[4 * c4], uh[4 * c4 + 1], uh[4 * c4 + 2], uh[4 * c4 + 3]}; tmem_st4c(tq + 64 + 16 * c4, t4); }
-        tmem_wait_st();
-        K::xload(Yb + K::YARR_C2, ky, a0, a1);
-        mbar_arrive(y_empty + buf);
-        fc3::fwd_third<L>(a0, a1, r, vh);
-        __syncwarp();
-        #pragma unroll
-        for (int c4 = 0; c4 < L / 4; c4++) {
-          double2 u4[4], a[4];
-          tmem_ld4c(tq + 64 + 16 * c4, u4);
-          if (p > 0) tmem_ld4c(tq + 16 * c4, a);
-          else { a[0] = a[1] = a[2] = a[3] = make_double2(0., 0.); }
-          #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int q = 4 * c4 + i;
-            a[i].x += u4[i].x * vh[q].x - u4[i].y * vh[q].y;
-            a[i].y += u4[i].x * vh[q].y + u4[i].y * vh[q].x;
-          }
-          tmem_st4c(tq + 16 * c4, a);
-        }
-        tmem_wait_st();
-      }
-      double2 acc[L];
-      #pragma unroll
-      for (int c4 = 0; c4 < L / 4; c4++) {
-        double2 a[4];
-        tmem_ld4c(tq + 16 * c4, a);
-        #pragma unroll
-        for (int i = 0; i < 4; i++) acc[4 * c4 + i] = a[i];
-      }
-      if (k >= 1) mbar_wait(t_empty, (unsigned)(k - 1) & 1u);
-      K::xinverse_store(ok, r, ky, acc, T);
-      mbar_arrive(t_full);
-    }
-  } else if (warp == 7) {
-    // ================================ load role (one lane) ================================
-    if (lane == 0) {
-      const int total_loads = nmine * K::LOADS_PER_PLANE;
-      #pragma unroll 1
-      for (int hi = 0; hi < total_loads; hi++) {
-        const int st = hi % NS, use = hi / NS;
-        if (use >= 1) mbar_wait(in_empty + st, (unsigned)(use - 1) & 1u);
-        const int k = hi / K::LOADS_PER_PLANE;
-        int p, arr;
-        K::load_of(hi % K::LOADS_PER_PLANE, p, arr);
-        const int w = (int)blockIdx.x + k * (int)gridDim.x;
-        mbar_expect_tx(in_full + st, PLANE_BYTES);
-        bulk_load(INs + st * K::PLANE_C2, K::load_src(Z, w / M, w % M, p, arr), PLANE_BYTES, in_full + st);
-      }
-    }
-  } else {
-    // ================================ y role: warp = (array, r) ================================
-    const int myarr = warp >= 8 ? 1 : 0, j = (warp & 3), x = lane, yt = j * 32 + lane;
-    auto finish_plane = [&](int kk) {
-      if (myarr == 1) {                        // inverse y of plane kk out of T, T2 written over T
-        mbar_wait(t_full, (unsigned)kk & 1u);
-        double2 c[L];
-        K::yinv_a(yt, T, c);
-        bar_sync_named(1, K::NYT);
-        K::yinv_b(yt, c, T);
-        mbar_arrive(t2_full);
-      } else {                                 // store C
-        mbar_wait(t2_full, (unsigned)kk & 1u);
-        const long long w = (long long)blockIdx.x + (long long)kk * gridDim.x;
-        K::store(yt, T, C + w * (N * N));
-        mbar_arrive(t_empty);
-      }
-    };
-    int h = 0, item = 0;
-    #pragma unroll 1
-    for (int k = 0; k < nmine; k++) {
-      #pragma unroll 1
-      for (int p = 0; p < 7; p++, item++) {
-        const int buf = item & 1;
-        if (item >= 2) mbar_wait(y_empty + buf, (unsigned)((item >> 1) - 1) & 1u);
-        double2 *Yb = Ys + buf * K::YBUF_C2;
-        const int hu = h, hv = h + 1;         // slots of this product's u plane and (p != 1) v plane
-        h += (p == 1) ? 1 : 2;
-        if (myarr == 1 && p == 1) {
-          K::yrescale(j, x, sE, Ys + (buf ^ 1) * K::YBUF_C2, Yb);
-        } else {
-          const int hh = myarr ? hv : hu, st = hh % NS;
-          mbar_wait(in_full + st, (unsigned)(hh / NS) & 1u);
-          K::ythird(myarr, j, x, p, INs + st * K::PLANE_C2, sE, Yb);
-          mbar_arrive(in_empty + st);
-        }
-        mbar_arrive(y_full + buf);
-        if (p == 1 && k >= 1) finish_plane(k - 1);
-      }
-    }
-    if (nmine > 0) finish_plane(nmine - 1);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"(COLS) : "memory");
 }
 // part (nullable): per (cell, xo) partial dot products of the conservation rows with the stored spectrum,
 // [cell][xo][5]; folded in a fixed order by the kernels that apply the correction (collision.cu)
@@ -721,27 +574,6 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   const int nsplit = (nb * M * 2 <= 148) ? 3 : 1;
   const long long split_stride = (long long)nb * M * N * N;
   const dim3 g2(M, nb, nsplit);
-  // N = 32: two kernels for the y/x stage.  k_fc3_f2s (persistent, warp-specialised, bulk-copy loads, one CTA per SM)
-  // has no partial last wave: measured 209.6 us against 217.2 us for k_fc3_f2_tmem on the 32-cell shard (1536 planes =
-  // 5.2 waves of 296 CTAs), but 6.29 against 6.05 us per cell once the grid is many waves deep (128 cells and more):
-  // its steady state is 4 % slower (profiles/r02_f2_kernels.md).  Hence the cell-count switch.  LPGPU_F2_MODE: 1 forces
-  // k_fc3_f2_tmem, 3 forces k_fc3_f2s (developer knob; both paths are parity-tested).
-  static const int f2_mode = getenv("LPGPU_F2_MODE") ? atoi(getenv("LPGPU_F2_MODE")) : 0;
-  if constexpr (L == 16) {
-    if (!no_tmem && nsplit == 1 && f2_mode != 1 && (f2_mode == 3 || nb <= 48)) {
-      typedef fc3::F2P KP;
-      const size_t smemp = (size_t)(LP_F2P_STAGES * KP::PLANE_C2 + 2 * KP::YBUF_C2 + KP::T_C2) * sizeof(double2) + N * sizeof(double);
-      static bool attr = false;
-      if (!attr) { LP_CUDA(cudaFuncSetAttribute(k_fc3_f2s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp)); attr = true; }
-      const int nplanes = nb * M, grid = nplanes < c->num_sms ? nplanes : c->num_sms;
-      k_fc3_f2s<<<grid, 384, smemp, c->stream>>>(Z, E, C, nplanes);
-      LP_LAUNCHED(c);
-      if (prof2) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
-      k_fc3_f3<L, 1><<<dim3(N, nb), fc3::F3<L>::NT, 0, c->stream>>>(C, qo, c->d_C5, part, split_stride);
-      LP_LAUNCHED(c);
-      return LPGPU_OK;
-    }
-  }
   if (L == 16 && !no_tmem && nsplit == 3) k_fc3_f2_tmem<true, 3><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else if (L == 16 && !no_tmem && park_uh) k_fc3_f2_tmem<true, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else if (L == 16 && !no_tmem) k_fc3_f2_tmem<false, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);

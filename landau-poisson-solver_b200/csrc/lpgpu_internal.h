@@ -96,7 +96,9 @@ struct lpgpu_ctx {
   //      flag; replaces the NCCL all-gather + send/recv, so the whole sharded timestep is one stream of kernels (one graph)
   bool peer_ready;
   double peer_timeout_s;                  // bound of a flag wait (k_peer_wait); a timeout poisons the state and fails the host calls
-  bool scan_attr;                         // k_field_scan opted in to more than 48 KB of shared memory (Nx > 2048)
+  bool scan_attr, finish_attr;            // k_field_scan / k_field_finish opted in to more than 48 KB of shared memory (Nx > 2048)
+  cudaStream_t halo_stream;               // the boundary planes of a stage travel here while the densities are reduced and exchanged
+  cudaEvent_t halo_fork, halo_join;
   int peer_rank, peer_world;
   unsigned long long *d_mbox;            // own mailbox (layout: LP_MB_* below)
   unsigned long long *peer_mbox[LP_MAX_PEERS];   // every rank's mailbox as mapped here ([peer_rank] = d_mbox)
@@ -173,6 +175,8 @@ int lp_launch_project(lpgpu_ctx *c, double *planes, int B);
 // ---- advection.cu
 int lp_launch_field_reduce(lpgpu_ctx *c, const double *planes);
 int lp_launch_field_scan(lpgpu_ctx *c);
+// density reduction + one single-block kernel for the rest of a stage's field solve (fold, [peer: publish, wait, gather], scan)
+int lp_launch_field_stage(lpgpu_ctx *c, const double *planes, bool peer);
 int lp_launch_dg_stage(lpgpu_ctx *c, int stage);
 int lp_launch_local_halo(lpgpu_ctx *c, double *planes);
 // peer-memory exchange of one stage: boundary planes into the neighbours' halos; densities into every mailbox;

@@ -6,68 +6,10 @@
 #include <cstring>
 #include <vector>
 #include "../../landau-poisson-solver_b200/csrc/fc3.cuh"
-#include "../../landau-poisson-solver_b200/csrc/fc3p.cuh"
 
 // mhat (nullable): the linear operator Q(f, M) -- the u arrays come from the stored Maxwellian transform
-// the y/x stage of one (cell, kz) plane as the warp-specialised persistent kernel cuts it (fc3p.cuh, k_fc3_f2s): the
-// tasks of the y role and of the x role run here in dependency order -- Y double-buffered by product, the staged planes
-// in a ring of four slots in the order load_of() prescribes, T2 written over T after every read of T
-static void f2p_plane(int cell, int kz, const double2 *Z, const double *E, double2 *C)
-{
-  using namespace fc3;
-  typedef F2P K;
-  constexpr int L = K::L, NS = 4;
-  std::vector<double2> IN((size_t)NS * K::PLANE_C2), Y((size_t)2 * K::YBUF_C2), T(K::T_C2);
-  std::vector<double> sE(E, E + K::N);
-  struct Acc { double2 a[L]; };
-  std::vector<Acc> acc(K::NXT);
-  std::memset(acc.data(), 0, sizeof(Acc) * acc.size());
-  int h = 0;
-  auto stage_load = [&](int hh) {                 // what the producer lane's bulk copy delivers
-    int p, arr;
-    K::load_of(hh, p, arr);
-    const double2 *src = K::load_src(Z, cell, kz, p, arr);
-    std::memcpy(IN.data() + (size_t)(hh % NS) * K::PLANE_C2, src, sizeof(double2) * K::PLANE_C2);
-  };
-  for (int p = 0; p < 7; p++) {
-    double2 *Yb = Y.data() + (size_t)(p & 1) * K::YBUF_C2;
-    for (int arr = 0; arr < 2; arr++) {
-      if (arr == 1 && p == 1) {
-        for (int t = 0; t < K::NYT; t++) K::yrescale(t / 32, t % 32, sE.data(), Y.data() + (size_t)((p & 1) ^ 1) * K::YBUF_C2, Yb);
-        break;
-      }
-      int pp, aa;
-      K::load_of(h, pp, aa);
-      if (pp != p || aa != arr) { std::memset(C, 0xff, sizeof(double2)); return; }   // the consumption order must match load_of
-      stage_load(h);
-      for (int t = 0; t < K::NYT; t++) K::ythird(arr, t / 32, t % 32, p, IN.data() + (size_t)(h % NS) * K::PLANE_C2, sE.data(), Yb);
-      h++;
-    }
-    for (int t = 0; t < K::NXT; t++) {
-      int r, ky;
-      K::xtask(t, r, ky);
-      double2 a0[L], a1[L], uh[L], vh[L];
-      K::xload(Yb, ky, a0, a1);
-      fwd_third<L>(a0, a1, r, uh);
-      K::xload(Yb + K::YARR_C2, ky, a0, a1);
-      fwd_third<L>(a0, a1, r, vh);
-      for (int q = 0; q < L; q++) {
-        acc[t].a[q].x += uh[q].x * vh[q].x - uh[q].y * vh[q].y;
-        acc[t].a[q].y += uh[q].x * vh[q].y + uh[q].y * vh[q].x;
-      }
-    }
-  }
-  if (h != K::LOADS_PER_PLANE) { std::memset(C, 0xff, sizeof(double2)); return; }
-  for (int t = 0; t < K::NXT; t++) { int r, ky; const bool ok = K::xtask(t, r, ky); K::xinverse_store(ok, r, ky, acc[t].a, T.data()); }
-  std::vector<Acc> c(K::NYT);
-  for (int t = 0; t < K::NYT; t++) K::yinv_a(t, T.data(), c[t].a);
-  for (int t = 0; t < K::NYT; t++) K::yinv_b(t, c[t].a, T.data());
-  for (int t = 0; t < K::NYT; t++) K::store(t, T.data(), C + ((long long)cell * K::M + kz) * (K::N * K::N));
-}
-
 template <int L>
-static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr,
-                    int f2kind = 0)
+static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr)
 {
   using namespace fc3;
   constexpr int N = 2 * L, M = 3 * L;
@@ -99,9 +41,6 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
     for (int cell = 0; cell < B; cell++)
       for (int kz = 0; kz < M; kz++)
         for (int sp = 0; sp < nsplit; sp++) {
-          if constexpr (L == 16) {
-            if (f2kind == 2) { f2p_plane(cell, kz, Z.data(), E, C.data()); continue; }
-          }
           int p0, p1;
           K::psplit(sp, nsplit, p0, p1);
           std::memset(acc.data(), 0, sizeof(Acc) * acc.size());
@@ -155,14 +94,6 @@ extern "C" int fc3_emulate_linear(int N, int B, const double *fhat, const double
     case 32: emulate<16>(B, f, G7, E, o, 1, m); return 0;
   }
   return 1;
-}
-
-// N = 32 with the y/x stage cut into the tasks of the warp-specialised persistent kernel (fc3p.cuh)
-extern "C" int fc3_emulate_roles(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
-{
-  if (N != 32) return 1;
-  emulate<16>(B, reinterpret_cast<const double2 *>(fhat), G7, E, reinterpret_cast<double2 *>(q), 1, nullptr, 2);
-  return 0;
 }
 
 extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)

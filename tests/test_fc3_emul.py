@@ -14,13 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emul", "fc3_emul.cpp")
 LIB = os.path.join(HERE, "emul", "libfc3_emul.so")
 HDR = os.path.join(HERE, "..", "landau-poisson-solver_b200", "csrc", "fc3.cuh")
-HDR_P = os.path.join(HERE, "..", "landau-poisson-solver_b200", "csrc", "fc3p.cuh")
 P = ctypes.POINTER(ctypes.c_double)
 
 
 @pytest.fixture(scope="module")
 def emul():
-    stale = not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(p) for p in (SRC, HDR, HDR_P))
+    stale = not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(p) for p in (SRC, HDR))
     if stale:
         subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
     return ctypes.CDLL(LIB)
@@ -66,24 +65,6 @@ def test_linear_operator_pipeline_matches_direct_sum(emul, N, B):
     assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
     assert emul.fc3_direct(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), got.ctypes.data_as(P)) == 0
     assert np.abs(got - want).max() > 1e-3 * np.abs(want).max()        # and it is a different operator
-
-
-def test_warp_role_tasks_match_direct_sum(emul):
-    """fc3p.cuh: the y/x stage cut into the tasks of the warp-specialised persistent kernel k_fc3_f2s (y role: one
-    sub-transform of a column per thread and array, Y double-buffered by product, staged planes in the ring order of
-    load_of(); x role: 144 (r, ky) tasks; inverse y with T2 written over T).  The emulator runs the tasks in dependency
-    order; the pipeline must reproduce the O(N^6) sum and the one-kernel-phase form."""
-    N, B = 32, 1
-    rng = np.random.default_rng(78)
-    fh = rng.standard_normal((B, N ** 3, 2))
-    G = rng.standard_normal((N ** 3, 7))
-    E = (np.arange(N) - N / 2) * 0.37
-    got, ref, want = np.zeros_like(fh), np.zeros_like(fh), np.zeros_like(fh)
-    assert emul.fc3_emulate_roles(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), got.ctypes.data_as(P)) == 0
-    assert emul.fc3_emulate(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), ref.ctypes.data_as(P)) == 0
-    assert emul.fc3_direct(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), want.ctypes.data_as(P)) == 0
-    assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
-    assert np.abs(got - ref).max() < 1e-13 * np.abs(want).max()
 
 
 def test_unsupported_size_is_refused(emul):
