@@ -297,11 +297,18 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
       const double2 *src = in + (((long long)cell * N) * N + y) * N + k;
       double2 v[Q], ph[Q];
       #pragma unroll
-      for (int q = 0; q < Q; q++) ph[q] = post[((4 * q + j) * N + y) * N + k];     // issued with the data loads, not after the transform
+      for (int q = 0; q < Q; q++) ph[q] = __ldg(post + ((4 * q + j) * N + y) * N + k);     // issued with the data loads, not after the transform
+      // every load of the line in flight before the first use: ONE memory round trip per CTA instead of Q dependent ones
+      // (ncu r02m: the adds below held 25 % of the kernel's warp samples on the long scoreboard, eight loads at a time)
+      double2 xin[4][Q];
       #pragma unroll
       for (int n = 0; n < Q; n++) {
-        const double2 x0 = src[(long long)n * N * N], x1 = src[(long long)(n + Q) * N * N], x2 = src[(long long)(n + 2 * Q) * N * N],
-                      x3 = src[(long long)(n + 3 * Q) * N * N];
+        #pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) xin[s4][n] = __ldg(src + (long long)(n + s4 * Q) * N * N);
+      }
+      #pragma unroll
+      for (int n = 0; n < Q; n++) {
+        const double2 x0 = xin[0][n], x1 = xin[1][n], x2 = xin[2][n], x3 = xin[3][n];
         double2 t;
         if (j == 0) t = fc3::cadd(fc3::cadd(x0, x2), fc3::cadd(x1, x3));
         else if (j == 2) t = fc3::csub(fc3::cadd(x0, x2), fc3::cadd(x1, x3));
