@@ -48,7 +48,9 @@ typedef struct lpgpu_params {
                            2 = FFT convolutions; 3 = register-tiled direct sum (the O(N^6) form of the reference) */
   int full_and_linear;  /* reference flag FullandLinear (test 3): electron-ion term next to Q(f,f) -- ComputeQ_FandL,
                            conserveAllMoments_FandL, RK4_FandL (collisionRoutines_1.cpp:605-689, 800-901, 987-1085;
-                           conservationRoutines.cpp:102-129).  Runs through the direct-sum kernel (correct, not tuned). */
+                           conservationRoutines.cpp:102-129).  With N = 8, 16, 24, 32 and computeq_variant 0 / 2 the linear part runs
+                           through the FFT-convolution pipeline too (fixed symbols convolved with monomials of e times fhat);
+                           variants 1 / 3 and other N use the direct O(N^6) sum. */
   /* ---- reference test 1 options (appended: older callers that zero the struct keep their behaviour) ---- */
   int doping;           /* reference flag Doping: step doping profile ND(x) (NH outside, NL inside the middle third,
                            FieldCalculations.cpp:413-425), the *_Doping field integrals (:427-676) and Dirichlet walls in

@@ -136,6 +136,25 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_alloc(&c->d_cpart, (size_t)5 * p->N * c->cap_cells));
   if (p->linear_landau) A_(dev_alloc(&c->d_mhat, 2 * n3));
   if (p->full_and_linear) A_(dev_alloc(&c->d_ql, 2 * n3));   // conservation partials: 8 chunks x 5 per cell
+  if (p->full_and_linear && lp_fc3_available(c)) {
+    // ComputeQ_FandL through the FFT-convolution pipeline (collision.cu, lp_launch_computeQ_fandl): four symbol tables in
+    // the pipeline's layout [a][y][z][x] -- {0, scale3 G_1..6} and, for j = 1..3, {-Gl_j, 0..0} -- and a spectrum of ones
+    const int N = p->N;
+    const size_t N3 = (size_t)c->N3;
+    std::vector<double> gt((size_t)4 * 7 * N3, 0.), ones(2 * N3, 0.);
+    for (size_t w = 0; w < N3; w++) ones[2 * w] = 1.;
+    for (int x = 0; x < N; x++)
+      for (int y = 0; y < N; y++)
+        for (int z = 0; z < N; z++) {
+          const size_t w = (size_t)z + N * ((size_t)y + N * (size_t)x), o = (((size_t)y) * N + z) * N + x;
+          for (int a = 1; a < 7; a++) gt[a * N3 + o] = t.scale3 * t.G[7 * w + a];
+          for (int j = 0; j < 3; j++) gt[(size_t)(1 + j) * 7 * N3 + o] = -t.Gl[3 * w + j];
+        }
+    A_(dev_upload(&c->d_GtLin, gt));
+    A_(dev_upload(&c->d_ones, ones));
+    A_(dev_alloc(&c->d_fl_tmp, 2 * n3));
+    A_(dev_alloc(&c->d_fl_g, 2 * n3));
+  }
   A_(dev_alloc(&c->d_B, (size_t)2 * c->cap_cells * p->N * 4 * p->Nv * p->Nv));
 #undef A_
   if (rc != LPGPU_OK) { lpgpu_finalize(c); return rc; }
@@ -150,7 +169,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   cudaDeviceSynchronize();
   double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
-                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart, c->d_Gl, c->d_ql, c->d_CCt_lin, c->d_dirichlet, c->d_mhat};
+                    c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart, c->d_Gl, c->d_ql, c->d_CCt_lin, c->d_dirichlet, c->d_mhat, c->d_GtLin, c->d_ones, c->d_fl_tmp, c->d_fl_g};
   for (double *q : ptrs) if (q) cudaFree(q);
   if (c->d_node_cell) cudaFree(c->d_node_cell);
   for (auto &e : c->prof_ev) cudaEventDestroy(e);
@@ -446,7 +465,12 @@ static int group_count(lpgpu_ctx *c)
   static const int knob = getenv("LPGPU_GROUPS") ? atoi(getenv("LPGPU_GROUPS")) : 0;   // developer knob; 1 = one chain
   if (c->is_view || c->prof_on || c->p.full_and_linear || !lp_fc3_available(c) || c->ncell < 16) return 1;
   if (lp_fc_prepare(c) != LPGPU_OK || c->fc_chunk < c->ncell) return 1;    // chunked ComputeQ reuses one set of work arrays
-  int g = knob > 0 ? knob : 4;             // measured, 32 cells at N = Nv = 32: 1.646 / 1.649 / 1.599 / 1.586 ms per step for 1 / 2 / 3 / 4 groups; later build: 1.544 / 1.558 / 1.560 / 1.888 for 4 / 6 / 8 / 16
+  // measured at N = Nv = 32 (ms per step for 1 / 2 / 4 / 8 groups): 32 cells 1.646 / 1.649 / 1.586 / 1.560 (round 1);
+  // 64 cells 2.807 / 2.788 / 2.797 / 2.797; 128 cells 5.453 / 5.474 / 5.488 / 5.517; 512 cells 20.98 / 21.63 / 21.65 / 21.66
+  // (profiles/r02r_groups.txt): the chains only pay while a kernel of one chain leaves SMs idle -- from ~100 cells on
+  // every grid is many waves deep and one chain is best
+  if (knob <= 0 && c->ncell >= 96) return 1;
+  int g = knob > 0 ? knob : 4;
   while (g > 1 && c->ncell < (knob > 0 ? 2 : 8) * g) g--;   // a group should still fill the GPU on its own (the knob may go further)
   return g;
 }

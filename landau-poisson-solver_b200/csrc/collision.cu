@@ -10,6 +10,11 @@
     (c)->launches++;                                    \
     LP_CUDA(cudaGetLastError());                        \
   } while (0)
+#define LP_TRY_RC(expr)                                 \
+  do {                                                  \
+    int rc_ = (expr);                                   \
+    if (rc_ != LPGPU_OK) return rc_;                    \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // complex helpers (double2 = (re, im))
@@ -532,7 +537,7 @@ int lp_launch_conserve(lpgpu_ctx *c, double *q, int B)
 // ---------------------------------------------------------------------------------------------
 // FullandLinear variant (reference test 3).  ComputeQ_FandL (collisionRoutines_1.cpp:605-689): next to the
 // quadratic sum, qHat_linear[xi] = sum_w h_eta^3 wt(w) scale3 gHat3_linear(xi, w) fhat[xi + N/2 - w]; qHat receives
-// both.  One thread per xi (the direct form; this variant is a parity row, not a tuned path).
+// both.  One thread per xi: the direct form, kept for sizes without an FFT-convolution pipeline and as the cross-check.
 __global__ void __launch_bounds__(128) k_computeQ_fandl(const double2 *__restrict__ fhat, double2 *__restrict__ q, double2 *__restrict__ ql,
                                                         const double *__restrict__ G, const double *__restrict__ Gl,
                                                         const double *__restrict__ eta, int N, double scale3, long long total)
@@ -567,9 +572,49 @@ __global__ void __launch_bounds__(128) k_computeQ_fandl(const double2 *__restric
   q[t] = make_double2(t0, t1);
   ql[t] = make_double2(t01, t11);
 }
+// ComputeQ_FandL through the FFT-convolution pipeline (N = 8, 16, 24, 32).  With e = xi - omega,
+//   gHat3_linear(xi, omega) = - sum_ij S_ij(omega) e_i e_j - sum_j (sum_i S_ij(omega) omega_i) e_j      (collisionRoutines_1.cpp:193-218)
+// and the sum ComputeQ_FandL takes over omega has NO fhat(omega) factor (:662), so qHat_linear is a sum of convolutions of
+// FIXED symbols with monomials of e times fhat -- the pipeline with a first factor of ones instead of fhat:
+//   pass A   symbols {0, scale3 G_1 .. scale3 G_6}, second factor fhat:         - scale3 sum_p G_p mono_p(e)
+//   pass B_j symbols {-Gl_j, 0 .. 0}, second factor E_j fhat (j = 1, 2, 3):     - Gl_j e_j
+// qHat = ComputeQ(f) + qHat_linear.  Five pipeline passes instead of one O(N^6) sum per evaluation.
+__global__ void k_mul_E(const double2 *__restrict__ fhat, double2 *__restrict__ out, const double *__restrict__ E, int N, int axis, long long total)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int w = (int)(t % ((long long)N * N * N));
+  const int idx = axis == 0 ? w / (N * N) : axis == 1 ? (w / N) % N : w % N;
+  const double e = E[idx];
+  const double2 v = fhat[t];
+  out[t] = make_double2(e * v.x, e * v.y);
+}
+__global__ void k_add_to(double2 *__restrict__ acc, const double2 *__restrict__ x, long long total)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) { const double2 a = acc[t], b = x[t]; acc[t] = make_double2(a.x + b.x, a.y + b.y); }
+}
 int lp_launch_computeQ_fandl(lpgpu_ctx *c, const double *fhat, double *q, double *ql, int B)
 {
   const long long total = (long long)B * c->N3;
+  const bool direct_only = c->p.computeq_variant == 1 || c->p.computeq_variant == 3;   // the O(N^6) kernel on request (cross-check)
+  if (!direct_only && c->d_GtLin && lp_fc3_available(c)) {
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    const size_t tab = (size_t)7 * c->N3;
+    const double *E = c->d_Etab + LP_ETAB_PAD;
+    LP_TRY_RC(lp_launch_computeQ_fftconv(c, fhat, q, B, false, nullptr));
+    LP_TRY_RC(lp_launch_fftconv_with(c, fhat, ql, B, c->d_GtLin, c->d_ones, 0));
+    for (int j = 0; j < 3; j++) {
+      k_mul_E<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(fhat), reinterpret_cast<double2 *>(c->d_fl_g), E, c->p.N, j, total);
+      LP_LAUNCHED(c);
+      LP_TRY_RC(lp_launch_fftconv_with(c, c->d_fl_g, c->d_fl_tmp, B, c->d_GtLin + (1 + j) * tab, c->d_ones, 0));
+      k_add_to<<<grid, 256, 0, c->stream>>>(reinterpret_cast<double2 *>(ql), reinterpret_cast<const double2 *>(c->d_fl_tmp), total);
+      LP_LAUNCHED(c);
+    }
+    k_add_to<<<grid, 256, 0, c->stream>>>(reinterpret_cast<double2 *>(q), reinterpret_cast<const double2 *>(ql), total);
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
   k_computeQ_fandl<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(
       reinterpret_cast<const double2 *>(fhat), reinterpret_cast<double2 *>(q), reinterpret_cast<double2 *>(ql), c->d_G, c->d_Gl, c->d_eta,
       c->p.N, c->tab.scale3, total);

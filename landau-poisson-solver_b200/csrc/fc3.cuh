@@ -280,9 +280,10 @@ struct F1 {
     for (int i = tid; i < N; i += NT) sE[i] = E[i];
   }
   // the y slab of a stored spectrum (the Maxwellian of the linear operator) into FM[x][z]
-  static LP_HD void load_slab(int tid, int cell, int y, const double2 *spec, double2 *FM)
+  // cell_stride: N^3 for one spectrum per cell, 0 when every cell uses the same one
+  static LP_HD void load_slab(int tid, int cell, int y, const double2 *spec, double2 *FM, long long cell_stride = (long long)N * N * N)
   {
-    const double2 *src = spec + (long long)cell * N * N * N;
+    const double2 *src = spec + (long long)cell * cell_stride;
     for (int idx = tid; idx < N * N; idx += NT) {
       const int x = idx / N, z = idx % N;
       FM[x * P + z] = src[((long long)x * N + y) * N + z];

@@ -269,7 +269,7 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsig
 template <int L, bool FUSED>
 __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__restrict__ in, const double *__restrict__ Gt,
                                                            const double *__restrict__ E, double2 *__restrict__ Z, const double2 *__restrict__ post,
-                                                           const double2 *__restrict__ mhat)
+                                                           const double2 *__restrict__ mhat, long long mstride)
 {
   typedef fc3::F1<L> K;
   constexpr int N = K::N;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(fc3::F1<L>::NT, 2) k_fc3_f1(const double2 *__r
     mbar_expect_tx(&s_bar, 7 * SLAB_BYTES);
     for (int a = 0; a < 7; a++) bulk_load(Gs + a * N * N, Gt + ((long long)a * N + y) * N * N, SLAB_BYTES, &s_bar);
   }
-  if (mhat) K::load_slab(tid, cell, y, mhat, FM);
+  if (mhat) K::load_slab(tid, cell, y, mhat, FM, mstride);
   if (FUSED) {
     // the N lines along i of this slab, four threads per line: thread (j, k) forms the decimated sequence
     // y_j[n] = (sum_s x[n + s N/4] (-i)^(j s)) w_N^(j n) and transforms it (N/4 points): X[4q + j]
@@ -548,7 +548,8 @@ __global__ void __launch_bounds__(fc3::F3<L>::NT) k_fc3_f3(const double2 *__rest
   }
 }
 template <int L>
-int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb, bool fused_i, double *part, const double2 *mhat)
+int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 *qo, int nb, bool fused_i, double *part, const double2 *mhat,
+               const double *Gt, long long mstride)
 {
   typedef fc3::F2<L> K2;
   constexpr int N = 2 * L, M = 3 * L;
@@ -569,8 +570,8 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   const double *E = c->d_Etab + LP_ETAB_PAD;
   const double2 *post = reinterpret_cast<const double2 *>(c->d_post_fwd);
   const dim3 g1(N, nb, nb * N * 2 <= 148 ? 5 : 1);
-  if (fused_i) k_fc3_f1<L, true><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post, mhat);
-  else k_fc3_f1<L, false><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, c->d_Gt, E, Z, post, mhat);
+  if (fused_i) k_fc3_f1<L, true><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, Gt, E, Z, post, mhat, mstride);
+  else k_fc3_f1<L, false><<<g1, fc3::F1<L>::NT, smem1, c->stream>>>(fh, Gt, E, Z, post, mhat, mstride);
   LP_LAUNCHED(c);
   static const bool no_tmem = getenv("LPGPU_FC_NO_TMEM") != nullptr;   // developer knob: accumulators in registers, 1 CTA per SM
   const bool prof2 = c->prof_on == 2 && c->prof_used + 2 <= c->prof_ev.size();
@@ -666,7 +667,20 @@ int lp_fc_prepare(lpgpu_ctx *c)
   }
   return LPGPU_OK;
 }
+// The pipeline with another set of symbols and another first factor (register-resident pipeline only, unfused):
+//   q[xi] = sum_p ( (Gt_p FU) (*) v_p )[xi + N/2],  v_p the seven monomials of E times fhat,  FU = `first` (one spectrum shared by
+// all cells when first_stride = 0).  ComputeQ_FandL's linear part is built from such passes (collision.cu).
+static int fftconv_run(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part, const double *Gt, const double *first, long long first_stride);
+int lp_launch_fftconv_with(lpgpu_ctx *c, const double *fhat, double *q, int B, const double *Gt, const double *first, long long first_stride)
+{
+  if (!lp_fc3_available(c) || !Gt || !first) { lp_set_error("lp_launch_fftconv_with: needs the fc3 pipeline, a symbol table and a first factor"); return LPGPU_EINVAL; }
+  return fftconv_run(c, fhat, q, B, false, nullptr, Gt, first, first_stride);
+}
 int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part)
+{
+  return fftconv_run(c, fhat, q, B, fused_i, part, nullptr, nullptr, 0);
+}
+static int fftconv_run(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part, const double *Gt_other, const double *first, long long first_stride)
 {
   if ((fused_i || part) && !lp_fc3_available(c)) { lp_set_error("fused ComputeQ needs the fc3 pipeline"); return LPGPU_EINVAL; }
   const int N = c->p.N, M = 3 * N / 2;
@@ -688,8 +702,11 @@ int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int 
       double *pp = part ? part + (size_t)b0 * N * 5 : nullptr;
       // LinearLandau: cell b of this call pairs with cell b of the context's stored Maxwellian transforms
       const double2 *mh = (c->p.linear_landau && c->have_mhat) ? reinterpret_cast<const double2 *>(c->d_mhat) + (size_t)b0 * c->N3 : nullptr;
-      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb, fused_i, pp, mh) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb, fused_i, pp, mh)
-             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb, fused_i, pp, mh) : launch_fc3<4>(c, fh, F1, F2, qo, nb, fused_i, pp, mh);
+      long long ms = c->N3;
+      const double *Gt = c->d_Gt;
+      if (first) { mh = reinterpret_cast<const double2 *>(first) + (size_t)b0 * first_stride; ms = first_stride; Gt = Gt_other; }
+      int rc = N == 32 ? launch_fc3<16>(c, fh, F1, F2, qo, nb, fused_i, pp, mh, Gt, ms) : N == 24 ? launch_fc3<12>(c, fh, F1, F2, qo, nb, fused_i, pp, mh, Gt, ms)
+             : N == 16 ? launch_fc3<8>(c, fh, F1, F2, qo, nb, fused_i, pp, mh, Gt, ms) : launch_fc3<4>(c, fh, F1, F2, qo, nb, fused_i, pp, mh, Gt, ms);
       if (rc != LPGPU_OK) return rc;
       continue;
     }

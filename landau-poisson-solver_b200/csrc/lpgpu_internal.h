@@ -65,6 +65,7 @@ struct lpgpu_ctx {
   double *d_q[4];                          // complex N^3: qHat, Q1_fft..Q3_fft
   double *d_lam;                           // 5 per cell
   double *d_Gl, *d_ql, *d_CCt_lin;          // FullandLinear: linear symbols, qHat_linear work array, 2x2 inverse
+  double *d_GtLin, *d_ones, *d_fl_tmp, *d_fl_g;   // FullandLinear through the FFT-convolution pipeline: 4 symbol tables [4][7][y][z][x], a spectrum of ones, two work spectra
   double *d_dirichlet;                     // Doping: the two wall planes (2 * 6 * sv)
   double *d_mhat;                          // LinearLandau: DFTMaxwell, ncell * N^3 complex
   bool have_mhat;
@@ -158,6 +159,8 @@ int lp_launch_fft3d_jk(lpgpu_ctx *c, const double *in, bool in_real, int B);
 bool lp_fc3_available(const lpgpu_ctx *c);
 // part (nullable, fc3 only): receives the [cell][N][5] partial conservation dot products of the unconserved spectrum
 int lp_launch_computeQ_fftconv(lpgpu_ctx *c, const double *fhat, double *q, int B, bool fused_i, double *part);
+// the same pipeline with other symbols Gt[7][y][z][x] and another first factor (first_stride = 0: one spectrum for all cells)
+int lp_launch_fftconv_with(lpgpu_ctx *c, const double *fhat, double *q, int B, const double *Gt, const double *first, long long first_stride);
 // allocates the pipeline's work arrays on first use (idempotent); -1 when the size has no FFT-convolution form
 int lp_fc_prepare(lpgpu_ctx *c);
 // conservation correction from those partials (in place)

@@ -10,8 +10,8 @@ import __graft_entry__ as graft
 pkg = graft.load_package()
 from lpsolver_b200 import solver
 nc, steps = int(sys.argv[1]), int(sys.argv[2])
-s = solver.ShardedSolver(nc, 32, 32, Lv=5.25, Lx=4.0, nu=0.05, dt=0.01)
-U0 = solver.set_init_ld(nc, 32, 5.25, 4.0, 0.5, np.pi / 2, True)
+s = solver.ShardedSolver(nc, 32, 32, Lv=5.25, Lx=max(4.0, nc / 8.), nu=0.05, dt=0.01)
+U0 = solver.set_init_ld(nc, 32, 5.25, max(4.0, nc / 8.), 0.5, np.pi / 2, True)
 s.upload(U0); s.step(4)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); e0.record(); s.step(steps); e1.record(); torch.cuda.synchronize()

@@ -795,3 +795,27 @@ def test_reference_main_linked_against_the_library(case, tmp_path):
     for row, grow in zip(rows, gold):
         for col in ([0, 7] if homog else [0, 1, 4, 5, 6, 7, 8] if case == "test1" else [0, 4, 5, 6, 7, 8]):
             assert abs(row[col] - grow[col]) <= 1.5e-7 * max(1.0, abs(grow[col])), (row, grow, col)
+
+
+@pytest.mark.parametrize("N,Nv", [(16, 16), (32, 32)])
+def test_full_and_linear_through_the_convolution_pipeline(pkg, N, Nv):
+    """ComputeQ_FandL (collisionRoutines_1.cpp:605-689) as FFT convolutions: its linear part is a sum of convolutions of
+    fixed symbols with monomials of e times fhat (lp_launch_computeQ_fandl, collision.cu).  A homogeneous RK4_FandL step
+    against the oracle at N = 16, and at the headline size against the direct O(N^6) kernel of the same library
+    (computeq_variant = 3), which test_full_and_linear_variant and the Test3 golden pin at N = 8."""
+    cfg = dict(Nx=1, Nv=Nv, N=N, Lv=5.25, Lx=4 * np.pi, nu=0.05, dt=0.01)
+    out = {}
+    ora = PortOracle(homogeneous=True, **cfg)
+    Uh = ora.SetInit_4H_Homo()
+    for variant in (0, 3):
+        g = pkg.LPGpu(homogeneous=True, full_and_linear=True, computeq_variant=variant, **cfg)
+        g.upload_U(Uh)
+        g.collide_step()
+        out[variant] = (g.download_U(), g.stage_spectrum(0)[0], g.stage_spectrum(3)[0])
+        g.close()
+    assert relerr(out[0][1], out[3][1]) < 1e-11 and relerr(out[0][2], out[3][2]) < 1e-11
+    assert relerr(out[0][0] - Uh, out[3][0] - Uh) < 1e-9
+    if N == 16:
+        ora.set_fandl(True)
+        want = ora.collide_step(Uh)
+        assert relerr(out[0][0], want) < TOL_U and relerr(out[0][0] - Uh, want - Uh) < TOL_DU
