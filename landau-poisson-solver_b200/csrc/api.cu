@@ -438,10 +438,11 @@ static int collide_cells(lpgpu_ctx *c)
     // fused chain: per stage  fft3D(j,k) -> [fft3D(i) + z-lines] -> F2 -> [inverse z + conservation dots]
     //                         -> [conservation correction + FS(i)] -> FS(j,k) + RK stage update
     LP_TRY(lp_launch_sample(c, c->d_U[0], c->d_f, B));
+    LP_TRY(lp_launch_fft3d_jk(c, c->d_f, true, B));
     for (int s = 0; s <= 3; s++) {
-      LP_TRY(lp_launch_fft3d_jk(c, s == 0 ? c->d_f : c->d_f1, true, B));
       LP_TRY(lp_launch_computeQ_fftconv(c, c->d_tmp, c->d_q[s], B, true, c->d_cpart));
-      if (s < 3) LP_TRY(lp_launch_fs_conserving(c, c->d_q[s], c->d_cpart, s + 1, B));
+      // FS + the RK stage update + the first fft3D pass of the next stage: one kernel, the stage input is never stored
+      if (s < 3) LP_TRY(lp_launch_fs_conserving(c, c->d_q[s], c->d_cpart, s + 1, B, true));
       else LP_TRY(lp_launch_conserve_from_parts(c, c->d_q[s], c->d_cpart, B));
     }
     return lp_launch_project(c, c->d_U[0], B);

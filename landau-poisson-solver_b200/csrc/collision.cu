@@ -265,6 +265,59 @@ __global__ void __launch_bounds__(N) k_tf_i(const double2 *__restrict__ in, doub
     out[((cell * N + i) * N + j) * N + t] = acc;
   }
 }
+// FS's last two passes, the RK stage update and fft3D's first two passes of the NEXT stage in one kernel: both work on the
+// slab (cell, i) and thread t owns the same elements (j, t) at the end of the inverse transform and at the start of the
+// forward one, so the stage input f1 never goes to memory (it was 8 B written + 8 B read per node and a launch per stage).
+// in/out: the FS spectrum after its i pass / the forward spectrum before its i pass; the same buffer, slab by slab.
+template <int N, int EPI>
+__global__ void __launch_bounds__(N) k_tf_jk_fs_fft(const double2 *__restrict__ in, double2 *__restrict__ out, PhaseTabs inv, PhaseTabs fwd, FsEpilogue ep)
+{
+  constexpr int P = N + 1;
+  __shared__ double2 X[N * P];
+  const long long slab = blockIdx.x;                 // cell*N + i
+  const int i = (int)(slab % N), t = threadIdx.x;
+  #pragma unroll 16
+  for (int j = 0; j < N; j++) X[j * P + t] = __ldg(in + slab * N * N + j * N + t);
+  __syncthreads();
+  double2 v[N];
+  #pragma unroll
+  for (int k = 0; k < N; k++) v[k] = X[t * P + k];          // row j = t
+  fc3::fftN<N, +1, N>(v);
+  #pragma unroll
+  for (int k = 0; k < N; k++) X[t * P + k] = v[k];
+  __syncthreads();
+  #pragma unroll
+  for (int j = 0; j < N; j++) v[j] = X[j * P + t];          // column k = t
+  fc3::fftN<N, +1, N>(v);
+  __syncthreads();                                          // every column is in registers: X may be refilled
+  #pragma unroll
+  for (int j = 0; j < N; j++) {
+    const long long g = slab * N * N + j * N + t;
+    const double2 acc = phase_mul(__ldg(inv.post + (i * N + j) * N + t), v[j]);
+    const double Q = acc.x * ep.inv;
+    double f1;
+    if (EPI == 1) { ep.Qv[g] = Q; f1 = __ldg(ep.f + g) + ep.dt * Q * ep.nu; }
+    else if (EPI == 2) f1 = __ldg(ep.f + g) + 0.5 * ep.dt * __ldg(ep.Qv + g) * ep.nu + 0.5 * ep.dt * Q * ep.nu;
+    else f1 = __ldg(ep.f + g) + 0.5 * __ldg(ep.Qv + g) * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
+    // fft3D's pre-phase and quadrature weights on the new stage input, exactly as k_tf_jk<fwd> applies them
+    double2 x = phase_mul(__ldg(fwd.pre + i + j + t), make_double2(f1, 0.));
+    const double fac = fwd.c3 * fwd.wt[i] * fwd.wt[j] * fwd.wt[t];
+    x.x = __dmul_rn(fac, x.x); x.y = __dmul_rn(fac, x.y);
+    X[j * P + t] = x;
+  }
+  __syncthreads();
+  #pragma unroll
+  for (int k = 0; k < N; k++) v[k] = X[t * P + k];
+  fc3::fftN<N, -1, N>(v);
+  #pragma unroll
+  for (int k = 0; k < N; k++) X[t * P + k] = v[k];
+  __syncthreads();
+  #pragma unroll
+  for (int j = 0; j < N; j++) v[j] = X[j * P + t];
+  fc3::fftN<N, -1, N>(v);
+  #pragma unroll
+  for (int j = 0; j < N; j++) out[slab * N * N + j * N + t] = v[j];
+}
 static bool lp_reg_lines(int N)
 {
   static const bool dense_only = getenv("LPGPU_DFT_DENSE") != nullptr;   // developer knob: the shared-memory DFT kernels
@@ -715,12 +768,16 @@ static int launch_fs_second(lpgpu_ctx *c, int mode, double *out_complex, int B, 
   lp_set_error("lp_launch_fs: bad mode");
   return LPGPU_EINVAL;
 }
-int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mode, int B)
+// next_fwd: the caller's next kernel is the fused ComputeQ on c->d_tmp (the next RK stage): run FS's last passes, the stage
+// update and fft3D's first passes as one kernel and leave the forward spectrum in c->d_tmp (f1 is not stored)
+int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mode, int B, bool next_fwd)
 {
   const int N = c->p.N;
   if (!lp_reg_lines(N)) {          // dense transforms: correction and FS as separate launches
     int rc = lp_launch_conserve_from_parts(c, q, part, B);
-    return rc ? rc : lp_launch_fs(c, q, mode, nullptr, B);
+    if (!rc) rc = lp_launch_fs(c, q, mode, nullptr, B);
+    if (rc != LPGPU_OK || !next_fwd) return rc;
+    return lp_launch_fft3d_jk(c, c->d_f1, true, B);
   }
   FsEpilogue ep;
   ep.scaleL = c->tab.scaleL; ep.scale3 = c->tab.scale3; ep.inv = 1. / c->tab.scaleL / c->tab.scale3;
@@ -732,7 +789,21 @@ int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mod
   else if (N == 16) k_tf_i_conserve<16><<<B * 16, 16, 0, c->stream>>>(q2, o2, pre, c->d_C5, c->d_CCt, part);
   else k_tf_i_conserve<8><<<B * 8, 8, 0, c->stream>>>(q2, o2, pre, c->d_C5, c->d_CCt, part);
   LP_LAUNCHED(c);
-  return launch_fs_second(c, mode, nullptr, B, ep);
+  static const bool unfused = getenv("LPGPU_FS_UNFUSED") != nullptr;   // developer knob
+  if (next_fwd && !unfused && mode >= 1 && mode <= 3) {
+    PhaseTabs inv = {nullptr, reinterpret_cast<const double2 *>(c->d_post_inv), nullptr, 0.};
+    PhaseTabs fwd = {reinterpret_cast<const double2 *>(c->d_pre_fwd), nullptr, c->d_wt, c->tab.c3_fwd};
+#define LP_FSFFT(NN, EE) k_tf_jk_fs_fft<NN, EE><<<B * NN, NN, 0, c->stream>>>(o2, o2, inv, fwd, ep)
+#define LP_FSFFT_N(NN) do { if (mode == 1) LP_FSFFT(NN, 1); else if (mode == 2) LP_FSFFT(NN, 2); else LP_FSFFT(NN, 3); } while (0)
+    if (N == 32) LP_FSFFT_N(32); else if (N == 24) LP_FSFFT_N(24); else if (N == 16) LP_FSFFT_N(16); else LP_FSFFT_N(8);
+#undef LP_FSFFT_N
+#undef LP_FSFFT
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
+  int rc = launch_fs_second(c, mode, nullptr, B, ep);
+  if (rc != LPGPU_OK || !next_fwd) return rc;
+  return lp_launch_fft3d_jk(c, c->d_f1, true, B);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -166,7 +166,7 @@ int lp_fc_prepare(lpgpu_ctx *c);
 // conservation correction from those partials (in place)
 int lp_launch_conserve_from_parts(lpgpu_ctx *c, double *q, const double *part, int B);
 // FS whose first pass also applies the conservation correction from `part` to q (in place) before transforming
-int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mode, int B);
+int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mode, int B, bool next_fwd);
 // FS + RK-stage epilogue.  mode 0: plain (writes complex out, imag 0); 1..3: stage updates of f1
 int lp_launch_fs(lpgpu_ctx *c, const double *q, int mode, double *out_complex, int B);
 int lp_launch_computeQ(lpgpu_ctx *c, const double *fhat, double *q, int B);
