@@ -8,7 +8,13 @@
 // Homogeneous, FullandLinear, LinearLandau, MassConsOnly; gamma = -3, 0, 1); TwoHump stops with an error, as the
 // reference does for bad input (exit(1)).
 //
-// usage: lpsolver [input-file] [--device k] [--quiet]
+// usage: lpsolver [input-file] [--device k] [--quiet] [--ranks R]
+//
+// --ranks R: R processes, one GPU each (rank r on device (k + r) mod #devices), forked before any CUDA call; rank r owns
+// the x cells [r Nx/R, (r+1) Nx/R) -- the reference's chunk_Nx split (LP_ompi.cpp:208-220) without MPI: the ranks exchange
+// their CUDA IPC handles once over socket pairs (lpgpu_peer_export / _import), after which every timestep's halo planes
+// and densities travel between the GPUs inside the kernels; per step only the diagnostics' partial sums (a few doubles
+// per cell) go to rank 0, which writes every file.
 #include "../../include/lpgpu.h"
 #include <chrono>
 #include <cmath>
@@ -18,7 +24,10 @@
 #include <fstream>
 #include <map>
 #include <string>
+#include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <vector>
 
 namespace {
@@ -171,6 +180,58 @@ void make_parent_dir(const std::string &path)
   for (size_t pos = path.find('/'); pos != std::string::npos; pos = path.find('/', pos + 1))
     if (pos > 0) mkdir(path.substr(0, pos).c_str(), 0755);
 }
+// ---- the ranks of a --ranks R run: rank 0 is the parent and talks to every child over a socket pair ----
+struct Team {
+  int rank = 0, world = 1;
+  std::vector<int> fd;                       // rank 0: fd[r] to child r; child: fd[0] to the parent
+  static void wr(int f, const void *b, size_t n)
+  {
+    const char *p = (const char *)b;
+    while (n) { ssize_t k = write(f, p, n); if (k <= 0) die("a rank of the run has died (write)"); p += k; n -= (size_t)k; }
+  }
+  static void rd(int f, void *b, size_t n)
+  {
+    char *p = (char *)b;
+    while (n) { ssize_t k = read(f, p, n); if (k <= 0) die("a rank of the run has died (read)"); p += k; n -= (size_t)k; }
+  }
+  void start(int R)
+  {
+    world = R; fd.assign(R, -1);
+    for (int r = 1; r < R; r++) {
+      int sp[2];
+      if (socketpair(AF_UNIX, SOCK_STREAM, 0, sp) != 0) die("socketpair failed");
+      const pid_t pid = fork();
+      if (pid < 0) die("fork failed");
+      if (pid == 0) {                        // child r
+        for (int q = 1; q < r; q++) close(fd[q]);
+        close(sp[0]);
+        rank = r; fd.assign(1, sp[1]);
+        return;
+      }
+      close(sp[1]); fd[r] = sp[0];
+    }
+  }
+  // concatenation of every rank's n doubles in rank order (on rank 0; children only send)
+  void gather(const double *local, size_t n, std::vector<double> &all)
+  {
+    if (rank) { wr(fd[0], local, n * sizeof(double)); return; }
+    all.resize(n * world);
+    memcpy(all.data(), local, n * sizeof(double));
+    for (int r = 1; r < world; r++) rd(fd[r], all.data() + n * r, n * sizeof(double));
+  }
+  void bcast(void *buf, size_t bytes)
+  {
+    if (rank) { rd(fd[0], buf, bytes); return; }
+    for (int r = 1; r < world; r++) wr(fd[r], buf, bytes);
+  }
+  void barrier() { double x = 0; std::vector<double> all; gather(&x, 1, all); bcast(&x, sizeof x); }
+  void finish()
+  {
+    if (rank) { _exit(0); }
+    for (int r = 1; r < world; r++) { int st = 0; wait(&st); }
+  }
+};
+
 #define CHECK(call)                                                                          \
   do { int rc_ = (call); if (rc_ != LPGPU_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, lpgpu_last_error()); exit(1); } } while (0)
 
@@ -179,9 +240,10 @@ void make_parent_dir(const std::string &path)
 int main(int argc, char **argv)
 {
   std::string input = "./LPsolver-input.txt";
-  int device = 0; bool quiet = false;
+  int device = 0, nranks = 1; bool quiet = false;
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "--device") && a + 1 < argc) device = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "--ranks") && a + 1 < argc) nranks = atoi(argv[++a]);
     else if (!strcmp(argv[a], "--quiet")) quiet = true;
     else input = argv[a];
   }
@@ -210,7 +272,15 @@ int main(int argc, char **argv)
   if (ic == "TwoStream") { if (!d.has("TwoStream/Lx")) die("Please set TwoStream/Lx."); p.Lx = d.num("TwoStream/Lx", 0.); k_wave = 2 * M_PI / 4.; }
   else p.Lx = d.num(ic + "/Lx", 2 * M_PI / k_wave);
   if (p.homogeneous && ic != "FourHump") die("Trying to run the space homogeneous code, but current IC is not available (only FourHump).");
-  p.x_begin = 0; p.x_count = p.homogeneous ? 1 : p.Nx; p.device = device; p.computeq_variant = 0;
+  if (nranks < 1 || nranks > 8) die("--ranks must be between 1 and 8");
+  if (nranks > 1 && (p.homogeneous || p.Nx % nranks != 0)) die("--ranks needs an inhomogeneous run with Nx divisible by the number of ranks");
+  Team team;
+  if (nranks > 1) team.start(nranks);                                 // forks: no CUDA call has been made yet
+  if (team.rank) quiet = true;
+  const int ndev = lpgpu_device_count();
+  p.x_count = p.homogeneous ? 1 : p.Nx / team.world;
+  p.x_begin = p.homogeneous ? 0 : team.rank * p.x_count;
+  p.device = ndev > 0 ? (device + team.rank) % ndev : device; p.computeq_variant = 0;
   p.full_and_linear = d.flag("FullandLinear");
   p.linear_landau = d.flag("LinearLandau");
   p.mass_cons_only = d.flag("MassConsOnly");
@@ -238,8 +308,8 @@ int main(int argc, char **argv)
   snprintf(name, sizeof name, "Data/FieldVals_%s", tail);
   const std::string fE_name = name;
 
-  const int sv = p.Nv * p.Nv * p.Nv, ncell = p.x_count;
-  std::vector<double> U((size_t)6 * sv * ncell);
+  const int sv = p.Nv * p.Nv * p.Nv, ncell = p.x_count, ncell_all = p.homogeneous ? 1 : p.Nx;
+  std::vector<double> U((size_t)6 * sv * ncell_all);                   // every rank sets the whole initial state and keeps its shard
   Grid g = {p.Nx, p.Nv, p.Lv, p.Lx, 2. * p.Lv / p.Nv, p.homogeneous ? 1. : p.Lx / p.Nx};
   if (d.flag("Second")) {
     if (!d.has("Second/Name")) die("Please set the name of the file from the previous run under Second/Name.");
@@ -255,18 +325,43 @@ int main(int argc, char **argv)
   else if (ic == "FourHump") ic_four_hump(g, p.homogeneous, U);
   else ic_perturbed(g, ic == "TwoStream", A_amp, k_wave, U);
 
+  const size_t shard = (size_t)6 * sv * ncell;
+  if (team.world > 1) { std::vector<double> mine(U.begin() + (size_t)team.rank * shard, U.begin() + (size_t)(team.rank + 1) * shard); U.swap(mine); }
   lpgpu_ctx *ctx = nullptr;
   CHECK(lpgpu_init(&p, &ctx));
   CHECK(lpgpu_upload_U(ctx, U.data()));
+  if (team.world > 1) {
+    // the ranks map each other's stage buffers and mailboxes once; from then on lpgpu_step works on the shard
+    std::vector<double> blob(LPGPU_PEER_HANDLE_BYTES / sizeof(double)), blobs;
+    CHECK(lpgpu_peer_export(ctx, blob.data()));
+    team.gather(blob.data(), blob.size(), blobs);
+    blobs.resize(blob.size() * team.world);
+    team.bcast(blobs.data(), blobs.size() * sizeof(double));
+    CHECK(lpgpu_peer_import(ctx, team.rank, team.world, blobs.data()));
+  }
   if (p.linear_landau && p.nu > 0.) CHECK(lpgpu_set_maxwellian(ctx));   // ComputeDFTofMaxwellian(U, f, DFTMaxwell), LP_ompi.cpp:516, :541
-  make_parent_dir(fmom_name);
-  FILE *fmom = fopen(fmom_name.c_str(), "w");
+  const bool root = team.rank == 0;
+  if (root) make_parent_dir(fmom_name);
+  FILE *fmom = fopen(root ? fmom_name.c_str() : "/dev/null", "w");
   if (!fmom) die("cannot open " + fmom_name);
-  FILE *fent = fopen(fent_name.c_str(), "w");
+  FILE *fent = fopen(root ? fent_name.c_str() : "/dev/null", "w");
   if (!fent) die("cannot open " + fent_name);
 
   // the rows of one step from the numbers lpgpu_diagnostics_end (or the synchronous pair) returns
-  auto report = [&](int step, const double *m5, const std::vector<double> &ms, const double *d4) {
+  auto report = [&](int step, const double *m5_loc, const std::vector<double> &ms_loc, const double *d4_loc) {
+    // the partial sums of every rank (MPI_Reduce / MPI_Gather in the reference's terms): moments and diagnostics add up,
+    // the per-cell densities concatenate in rank order = x order
+    double m5[5], d4[4];
+    std::vector<double> ms;
+    if (team.world > 1) {
+      double loc[9]; memcpy(loc, m5_loc, sizeof m5); memcpy(loc + 5, d4_loc, sizeof d4);
+      std::vector<double> all;
+      team.gather(loc, 9, all);
+      team.gather(ms_loc.data(), ms_loc.size(), ms);
+      if (!root) return;
+      for (int k = 0; k < 5; k++) { m5[k] = 0.; for (int r = 0; r < team.world; r++) m5[k] += all[9 * r + k]; }
+      for (int k = 0; k < 4; k++) { d4[k] = 0.; for (int r = 0; r < team.world; r++) d4[k] += all[9 * r + 5 + k]; }
+    } else { memcpy(m5, m5_loc, sizeof m5); memcpy(d4, d4_loc, sizeof d4); ms = ms_loc; }
     double ele = 0.;                                // d4: entropy, KiE over positive / negative cells, #negative cells
     if (!p.homogeneous) CHECK(lpgpu_eleE_from_ms(&p, ms.data(), &ele));
     const double ent = d4[0], lent = log(fabs(ent));
@@ -298,7 +393,8 @@ int main(int argc, char **argv)
   // and one every 20 steps (LP_ompi.cpp:648-655, :868-875).  The GPU reduces over the integrated-out velocity
   // directions (lpgpu_marginal_sums) and over whole velocity space ((m_i, s_i) of lpgpu_moments_partial); the host
   // evaluates the reference's closed forms at its 4 sub-points per cell.
-  FILE *fmarg = fopen(fmarg_name.c_str(), "w"), *fphi = fopen(fphi_name.c_str(), "w"), *fE = fopen(fE_name.c_str(), "w");
+  FILE *fmarg = fopen(root ? fmarg_name.c_str() : "/dev/null", "w"), *fphi = fopen(root ? fphi_name.c_str() : "/dev/null", "w"),
+       *fE = fopen(root ? fE_name.c_str() : "/dev/null", "w");
   if (!fmarg || !fphi || !fE) die("cannot open the Marginals/PhiVals/FieldVals files under Data/");
   const int np = 4, Nv = p.Nv;
   const double dv = g.dv, dx = g.dx, ddv = dv / np, ddx = dx / np;
@@ -322,9 +418,17 @@ int main(int argc, char **argv)
     }
     fprintf(fphi, "\n"); fprintf(fE, "\n");
   }
-  std::vector<double> msum((size_t)4 * (p.homogeneous ? Nv * Nv : ncell * Nv));
+  std::vector<double> msum_loc((size_t)4 * (p.homogeneous ? Nv * Nv : ncell * Nv)), msum;
   auto print_marginal_and_field = [&]() {
-    CHECK(lpgpu_marginal_sums(ctx, msum.data()));
+    CHECK(lpgpu_marginal_sums(ctx, msum_loc.data()));
+    double m5[5];
+    std::vector<double> ms_loc((size_t)2 * ncell), ms;
+    if (!p.homogeneous) CHECK(lpgpu_moments_partial(ctx, m5, ms_loc.data()));
+    if (team.world > 1) {                                            // every rank's sums to rank 0, in x order
+      team.gather(msum_loc.data(), msum_loc.size(), msum);
+      team.gather(ms_loc.data(), ms_loc.size(), ms);
+      if (!root) return;
+    } else { msum = msum_loc; ms = ms_loc; }
     if (p.homogeneous) {                                             // PrintMarginal_Homo :196-219 with f_marg_Homo :43-59
       for (int j1 = 0; j1 < Nv; j1++) for (int n1 = 0; n1 < np; n1++) for (int j2 = 0; j2 < Nv; j2++) for (int n2 = 0; n2 < np; n2++) {
         const double d1 = gridv(j1 - 0.5) + n1 * ddv - gridv(j1), d2 = gridv(j2 - 0.5) + n2 * ddv - gridv(j2);
@@ -342,9 +446,6 @@ int main(int argc, char **argv)
     fprintf(fmarg, "\n");
     // PrintFieldData_Normal (FieldCalculations.cpp:331-355): phi at 4 points per cell; computePhi_Normal (:244-329) in
     // terms of m_q = scalev sum(U0 + U5/4), s_q = scalev sum U1 and computePhi_x_0 (:223-243)
-    double m5[5];
-    std::vector<double> ms((size_t)2 * ncell);
-    CHECK(lpgpu_moments_partial(ctx, m5, ms.data()));
     double P = 0., acc = 0.;
     std::vector<double> Pq(p.Nx), Sq(p.Nx);                           // P_q = sum_{q' < q} m_q',  S_q = sum_{q' < q} (P_q' + m_q'/2 - s_q'/12)
     for (int q = 0; q < p.Nx; q++) { Pq[q] = P; Sq[q] = acc; acc += P + 0.5 * ms[2 * q] - ms[2 * q + 1] / 12.; P += ms[2 * q]; }
@@ -390,13 +491,20 @@ int main(int argc, char **argv)
   }
   if (nT > 0) collect(nT);
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  printf("\nTime duration for %d time steps is %gs\n\n", nT, secs);
+  if (root) printf("\nTime duration for %d time steps is %gs\n\n", nT, secs);
   fclose(fmom);
   fclose(fent);
   fclose(fmarg); fclose(fphi); fclose(fE);
   CHECK(lpgpu_download_U(ctx, U.data()));
-  FILE *fu = fopen(fu_name.c_str(), "wb");
-  if (fu) { fwrite(U.data(), sizeof(double), U.size(), fu); fclose(fu); }
+  std::vector<double> Uall;
+  if (team.world > 1) team.gather(U.data(), U.size(), Uall);          // the shards in rank order are the reference's U
+  if (root) {
+    const std::vector<double> &Uw = team.world > 1 ? Uall : U;
+    FILE *fu = fopen(fu_name.c_str(), "wb");
+    if (fu) { fwrite(Uw.data(), sizeof(double), Uw.size(), fu); fclose(fu); }
+  }
+  if (team.world > 1) team.barrier();                                 // nobody unmaps or frees while a peer may still write
   CHECK(lpgpu_finalize(ctx));
+  team.finish();
   return 0;
 }
