@@ -306,6 +306,11 @@ def main():
     s.step(isteps)
     barrier()
     dg_ms, dg_n = g.profile_read()
+    #     ... and around the moment reduction of the per-step diagnostics (computeMass / Momentum / KiE: HBM-bound)
+    g.profile_computeQ(4)
+    for _ in range(10):
+        g.moments_partial()
+    mo_ms, mo_n = g.profile_read()
     g.profile_computeQ(False)
     clocks = sampler.finish((w0, w1))
 
@@ -405,6 +410,14 @@ def main():
                     "algorithmic_bytes_per_launch": adv_bytes_per_launch,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6500 GB/s (B200_PROFILING.md)"}
 
+    roof_mom = None
+    if mo_n > 0:
+        mom_bytes = 40. * s.x_count * NV ** 3          # U0, U2, U3, U4, U5 of every DG cell, read once
+        avg_mo = mo_ms * 1e-3 / mo_n
+        hbm_peak = peaks.get("hbm_gbs") or 6500.
+        roof_mom = {"bound": "hbm", "kernel": "k_moments_cell (computeMass, computeMomentum, computeKiE: per-cell partial sums of five DG coefficients)",
+                    "achieved": mom_bytes / avg_mo / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": mom_bytes / avg_mo / 1e9 / hbm_peak,
+                    "avg_launch_ms": avg_mo * 1e3, "launches": mo_n, "algorithmic_bytes_per_launch": mom_bytes}
     line = None
     if rank == 0:
         ws_mb = (3 * (s.x_count + 2) * 6 * NV ** 3 * 8 + s.x_count * NSPEC ** 3 * 8 * (3 + 2 * 6) + s.x_count * NSPEC * 4 * NV * NV * 16
@@ -417,7 +430,7 @@ def main():
                                          "peer memory: kernels write halo planes and densities into the neighbours' buffers (CUDA IPC), flag-synchronised; no NCCL call in the timestep" if s.exchange == "peer" else
                                          "NCCL all-gather + send/recv per SSP-RK3 stage")),
                 "timesteps_per_s": args.steps / t_dev, "timed_region_s": t_dev, "state_finite_after_timed_region": finite,
-                "roofline": roof, "roofline_advection": roof_adv, "e2e": e2e, "as_reference_loop": as_reference,
+                "roofline": roof, "roofline_advection": roof_adv, "roofline_moments": roof_mom, "e2e": e2e, "as_reference_loop": as_reference,
                 "gpu_launches": int(launches), "clocks": clocks}
     s.close()
 

@@ -167,7 +167,7 @@ int lpgpu_field(lpgpu_ctx *c, double *out);
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
 /* Bracket ComputeQ with CUDA events on the context's stream: enable = 1 around the whole ComputeQ chain of
  * kernels, 2 around its dominant kernel only (the y/x-transform + product kernel of the FFT-convolution
- * pipeline), 3 around the DG stage kernels of the advection instead, 0 off; read returns the summed device time and
+ * pipeline), 3 around the DG stage kernels of the advection instead, 4 around the moment-reduction kernel, 0 off; read returns the summed device time and
  * the number of bracketed launches since enable (synchronises the stream).  While on, the library launches eagerly. */
 int lpgpu_profile_computeQ(lpgpu_ctx *c, int enable);
 int lpgpu_profile_read(lpgpu_ctx *c, double *total_ms, long long *launches);

@@ -172,11 +172,16 @@ struct DgParams {
   int Nv, sv, ncell;
   double dv, dx, dt, scalev, Lv, inv_dxs;
 };
+// Two DG cells (j, j + 1: the same j1, j2) per thread, every access a double2: half the load instructions for the same
+// bytes and twice the bytes in flight per thread -- the kernel is bound by memory latency, not bandwidth (ncu r02s: long
+// scoreboard 62 % of the warp samples at 43 % of the DRAM throughput).  U0 / Uout may be the same buffer in stage 2 (each
+// thread reads its old values before it writes them): they are not declared __restrict__.
+struct DgCell { double tp[6]; };
 template <int STAGE>
-__global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin, const double *__restrict__ U0,
-                                                  double *__restrict__ Uout, const double *__restrict__ fld, DgParams P)
+__global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin, const double *U0,
+                                                  double *Uout, const double *__restrict__ fld, DgParams P)
 {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
   if (t >= (long long)P.ncell * P.sv) return;
   const int sv = P.sv, Nv = P.Nv, NN = Nv * Nv;
   const long long cell = t / sv; const int j = (int)(t % sv), j1 = j / NN;
@@ -188,97 +193,103 @@ __global__ void __launch_bounds__(256) k_dg_stage(const double *__restrict__ Uin
   const double *f4 = fld + 1 + 4 * cell;
   const double E = f4[1], E1 = f4[2], E2 = f4[3];
   const long long own = ((cell + 1) * 6) * (long long)sv + j;
-  double u[6];
+  auto ld2 = [&](const double *base, long long off) { return *reinterpret_cast<const double2 *>(base + off); };
+  double2 u[6], X[6], V[6];
   #pragma unroll
-  for (int c = 0; c < 6; c++) u[c] = Uin[own + (long long)c * sv];
-  double tp[6] = {0., 0., 0., 0., 0., 0.};
-  // I1: only the phi_x test function sees the v1 f volume term
-  tp[1] += dv3 * (c1 * u[0] + dv * u[2] * K12 + u[5] * c1 * 0.25);
-  // I2: E f volume term (Int_fE, FieldCalculations.cpp:126-135)
-  tp[2] -= ((u[0] + u[5] * 0.25) * E + u[1] * E1) * dv2;   // scalev/dv = dv^2
-  tp[5] -= u[2] * dv2 * E * (1. / 6.);
-  // I3: x faces, upwind on the sign of the v1 cell index
-  {
-    double R[6], L[6], ur, ul;
-    if (j1 < Nv / 2) {
-      const long long nb = own + 6LL * sv;    // plane p+1 (right neighbour; halo when p = ncell)
-      #pragma unroll
-      for (int c = 0; c < 6; c++) { R[c] = Uin[nb + (long long)c * sv]; L[c] = u[c]; }
-      ur = -R[1]; ul = -L[1];
-    } else {
-      const long long nb = own - 6LL * sv;    // plane p-1
-      #pragma unroll
-      for (int c = 0; c < 6; c++) { L[c] = Uin[nb + (long long)c * sv]; R[c] = u[c]; }
-      ur = R[1]; ul = L[1];
-    }
-    tp[0] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 + (R[2] - L[2]) * dv * K12 + (R[5] - L[5]) * c1 * 0.25);
-    tp[1] -= 0.5 * dv3 * ((R[0] + 0.5 * ur + L[0] + 0.5 * ul) * c1 + (R[2] + L[2]) * dv * K12 + (R[5] + L[5]) * c1 * 0.25);
-    tp[2] -= dv2 * (((R[0] - L[0]) * dv2 + (ur - ul) * 0.5 * dv2 + (R[2] - L[2]) * dv * c1) * K12 + (R[5] - L[5]) * dv2 * (19. / 720.));
-    tp[3] -= (R[3] - L[3]) * c1 * dv3 * K12;
-    tp[4] -= (R[4] - L[4]) * c1 * dv3 * K12;
-    tp[5] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 * 0.25 + (R[2] - L[2]) * dv * (19. / 720.) + (R[5] - L[5]) * c1 * (19. / 240.));
+  for (int c = 0; c < 6; c++) u[c] = ld2(Uin, own + (long long)c * sv);
+  // x-upwind neighbour: plane p+1 for v1 < 0 (j1 < Nv/2), plane p-1 otherwise (halo planes at the ends)
+  const bool right = j1 < Nv / 2;
+  const long long nbx = right ? own + 6LL * sv : own - 6LL * sv;
+  #pragma unroll
+  for (int c = 0; c < 6; c++) X[c] = ld2(Uin, nbx + (long long)c * sv);
+  // v1-upwind neighbour: j1+1 when the cell-integrated field is positive, j1-1 otherwise; no flux through |v1| = Lv
+  const bool up = E > 0;
+  const bool have_v = up ? (j1 + 1 < Nv) : (j1 > 0);
+  const long long nbv = up ? own + NN : own - NN;
+  #pragma unroll
+  for (int c = 0; c < 6; c++) V[c] = have_v ? ld2(Uin, nbv + (long long)c * sv) : make_double2(0., 0.);
+  double2 old[6];
+  if (STAGE != 0) {
+    #pragma unroll
+    for (int c = 0; c < 6; c++) old[c] = ld2(U0, own + (long long)c * sv);
   }
-  // I5: v1 faces, upwind on the sign of the cell-integrated field; no flux through |v1| = Lv
-  {
-    double R[6], L[6], ur, ul;
-    if (E > 0) {
-      #pragma unroll
-      for (int c = 0; c < 6; c++) L[c] = u[c];
-      ul = -L[2];
-      if (j1 + 1 < Nv) {
+  double2 res[6];
+  #pragma unroll
+  for (int h = 0; h < 2; h++) {
+    double uu[6], xx[6], vv[6];
+    #pragma unroll
+    for (int c = 0; c < 6; c++) { uu[c] = h ? u[c].y : u[c].x; xx[c] = h ? X[c].y : X[c].x; vv[c] = h ? V[c].y : V[c].x; }
+    double tp[6] = {0., 0., 0., 0., 0., 0.};
+    // I1: only the phi_x test function sees the v1 f volume term
+    tp[1] += dv3 * (c1 * uu[0] + dv * uu[2] * K12 + uu[5] * c1 * 0.25);
+    // I2: E f volume term (Int_fE, FieldCalculations.cpp:126-135)
+    tp[2] -= ((uu[0] + uu[5] * 0.25) * E + uu[1] * E1) * dv2;   // scalev/dv = dv^2
+    tp[5] -= uu[2] * dv2 * E * (1. / 6.);
+    // I3: x faces, upwind on the sign of the v1 cell index
+    {
+      double R[6], L[6], ur, ul;
+      if (right) {
         #pragma unroll
-        for (int c = 0; c < 6; c++) R[c] = Uin[own + NN + (long long)c * sv];
-        ur = -R[2];
+        for (int c = 0; c < 6; c++) { R[c] = xx[c]; L[c] = uu[c]; }
+        ur = -R[1]; ul = -L[1];
       } else {
         #pragma unroll
-        for (int c = 0; c < 6; c++) R[c] = 0.;
-        ur = 0.;
+        for (int c = 0; c < 6; c++) { L[c] = xx[c]; R[c] = uu[c]; }
+        ur = R[1]; ul = L[1];
       }
-    } else {
-      #pragma unroll
-      for (int c = 0; c < 6; c++) R[c] = u[c];
-      ur = R[2];
-      if (j1 > 0) {
+      tp[0] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 + (R[2] - L[2]) * dv * K12 + (R[5] - L[5]) * c1 * 0.25);
+      tp[1] -= 0.5 * dv3 * ((R[0] + 0.5 * ur + L[0] + 0.5 * ul) * c1 + (R[2] + L[2]) * dv * K12 + (R[5] + L[5]) * c1 * 0.25);
+      tp[2] -= dv2 * (((R[0] - L[0]) * dv2 + (ur - ul) * 0.5 * dv2 + (R[2] - L[2]) * dv * c1) * K12 + (R[5] - L[5]) * dv2 * (19. / 720.));
+      tp[3] -= (R[3] - L[3]) * c1 * dv3 * K12;
+      tp[4] -= (R[4] - L[4]) * c1 * dv3 * K12;
+      tp[5] -= dv3 * ((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * c1 * 0.25 + (R[2] - L[2]) * dv * (19. / 720.) + (R[5] - L[5]) * c1 * (19. / 240.));
+    }
+    // I5: v1 faces, upwind on the sign of the cell-integrated field
+    {
+      double R[6], L[6], ur, ul;
+      if (up) {
         #pragma unroll
-        for (int c = 0; c < 6; c++) L[c] = Uin[own - NN + (long long)c * sv];
-        ul = L[2];
+        for (int c = 0; c < 6; c++) { L[c] = uu[c]; R[c] = vv[c]; }
+        ul = -L[2]; ur = have_v ? -R[2] : 0.;
       } else {
         #pragma unroll
-        for (int c = 0; c < 6; c++) L[c] = 0.;
-        ul = 0.;
+        for (int c = 0; c < 6; c++) { R[c] = uu[c]; L[c] = vv[c]; }
+        ur = R[2]; ul = have_v ? L[2] : 0.;
       }
+      const double gR = R[0] + 0.5 * ur + R[5] * (5. / 12.), gL = L[0] + 0.5 * ul + L[5] * (5. / 12.);
+      tp[0] += dv2 * (gR - gL) * E + dv2 * (R[1] - L[1]) * E1;
+      tp[1] += dv2 * ((gR - gL) * E1 + (R[1] - L[1]) * E2);
+      tp[2] += 0.5 * (dv2 * (gR + gL) * E + dv2 * (R[1] + L[1]) * E1);
+      tp[3] += (R[3] - L[3]) * E * dv2 * K12;
+      tp[4] += (R[4] - L[4]) * E * dv2 * K12;
+      tp[5] += dv2 * (((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * (5. / 12.) + (R[5] - L[5]) * (133. / 720.)) * E + (R[1] - L[1]) * E1 * (5. / 12.));
     }
-    const double gR = R[0] + 0.5 * ur + R[5] * (5. / 12.), gL = L[0] + 0.5 * ul + L[5] * (5. / 12.);
-    tp[0] += dv2 * (gR - gL) * E + dv2 * (R[1] - L[1]) * E1;
-    tp[1] += dv2 * ((gR - gL) * E1 + (R[1] - L[1]) * E2);
-    tp[2] += 0.5 * (dv2 * (gR + gL) * E + dv2 * (R[1] + L[1]) * E1);
-    tp[3] += (R[3] - L[3]) * E * dv2 * K12;
-    tp[4] += (R[4] - L[4]) * E * dv2 * K12;
-    tp[5] += dv2 * (((R[0] + 0.5 * ur - L[0] - 0.5 * ul) * (5. / 12.) + (R[5] - L[5]) * (133. / 720.)) * E + (R[1] - L[1]) * E1 * (5. / 12.));
+    const double idxs = P.inv_dxs;   // 1/(dx scalev)
+    double H[6];
+    H[0] = (19 * tp[0] * 0.25 - 15 * tp[5]) * idxs;
+    H[5] = (60 * tp[5] - 15 * tp[0]) * idxs;
+    #pragma unroll
+    for (int l = 1; l < 5; l++) H[l] = tp[l] * (12. * idxs);
+    #pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const double o0 = (STAGE != 0) ? (h ? old[c].y : old[c].x) : 0.;
+      double r;
+      if (STAGE == 0) r = uu[c] + P.dt * H[c];
+      else if (STAGE == 1) r = 0.75 * o0 + 0.25 * uu[c] + 0.25 * P.dt * H[c];
+      else r = o0 * (1. / 3.) + uu[c] * (2. / 3.) + P.dt * H[c] * (2. / 3.);
+      if (h) res[c].y = r; else res[c].x = r;
+    }
   }
-  const double idxs = P.inv_dxs;   // 1/(dx scalev)
-  double H[6];
-  H[0] = (19 * tp[0] * 0.25 - 15 * tp[5]) * idxs;
-  H[5] = (60 * tp[5] - 15 * tp[0]) * idxs;
   #pragma unroll
-  for (int l = 1; l < 5; l++) H[l] = tp[l] * (12. * idxs);
-  #pragma unroll
-  for (int c = 0; c < 6; c++) {
-    const long long o = own + (long long)c * sv;
-    double r;
-    if (STAGE == 0) r = u[c] + P.dt * H[c];
-    else if (STAGE == 1) r = 0.75 * U0[o] + 0.25 * u[c] + 0.25 * P.dt * H[c];
-    else r = U0[o] * (1. / 3.) + u[c] * (2. / 3.) + P.dt * H[c] * (2. / 3.);
-    Uout[o] = r;
-  }
+  for (int c = 0; c < 6; c++) *reinterpret_cast<double2 *>(Uout + own + (long long)c * sv) = res[c];
 }
 int lp_launch_dg_stage(lpgpu_ctx *c, int stage)
 {
   DgParams P;
   P.Nv = c->p.Nv; P.sv = c->sv; P.ncell = c->ncell; P.dv = c->tab.dv; P.dx = c->p.Lx / c->p.Nx; P.dt = c->p.dt;
   P.scalev = c->tab.scalev; P.Lv = c->p.Lv; P.inv_dxs = 1. / (P.dx * P.scalev);
-  const long long n = (long long)c->ncell * c->sv;
-  const unsigned grid = (unsigned)((n + 255) / 256);
+  const long long n = (long long)c->ncell * c->sv;      // Nv is even: the two cells of a thread share j1 and j2
+  const unsigned grid = (unsigned)((n / 2 + 255) / 256);
   const bool prof3 = c->prof_on == 3 && c->prof_used + 2 <= c->prof_ev.size();   // bench.py: HBM roofline of the DG stage kernels
   if (prof3) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   // buffers: stage 0 reads U -> writes U1; stage 1 reads U1 (+U) -> U2; stage 2 reads U2 (+U) -> U
@@ -508,16 +519,27 @@ __global__ void __launch_bounds__(256) k_moments_cell(const double *__restrict__
   const long long cell = blockIdx.x;
   const double *u = planes + ((cell + 1) * 6) * (long long)sv;
   double v[5] = {0., 0., 0., 0., 0.};
-  const int per = (sv + gridDim.y - 1) / gridDim.y, jlo = blockIdx.y * per, jhi = min(sv, jlo + per);
-  for (int j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
+  // two DG cells (j, j + 1: Nv is even, so they share j1 and j2) per thread and pass, double2 loads: the reduction is bound
+  // by memory latency (five loads per cell), not by its arithmetic
+  int per = (sv + gridDim.y - 1) / gridDim.y;
+  per += per & 1;
+  const int jlo = blockIdx.y * per, jhi = min(sv, jlo + per);
+  for (int j = jlo + 2 * threadIdx.x; j < jhi; j += 2 * blockDim.x) {
     const int j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
-    const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv, c3 = -Lv + (j3 + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
-    const double U0 = u[j], U2 = u[2LL * sv + j], U3 = u[3LL * sv + j], U4 = u[4LL * sv + j], U5 = u[5LL * sv + j];
-    v[0] += U0 + U5 / 4.;
-    v[1] += c1 * dv * U0 + U2 * dv * dv / 12. + U5 * c1 * dv / 4.;
-    v[2] += c2 * dv * U0 + U3 * dv * dv / 12. + U5 * c2 * dv / 4.;
-    v[3] += c3 * dv * U0 + U4 * dv * dv / 12. + U5 * c3 * dv / 4.;
-    v[4] += U0 * (r2 + dv * dv / 4.) * dv + (c1 * U2 + c2 * U3 + c3 * U4) * dv * dv / 6. + U5 * (dv * dv * dv * 19. / 240. + r2 * dv / 4.);
+    const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv;
+    const double2 A0 = *reinterpret_cast<const double2 *>(u + j), A2 = *reinterpret_cast<const double2 *>(u + 2LL * sv + j),
+                  A3 = *reinterpret_cast<const double2 *>(u + 3LL * sv + j), A4 = *reinterpret_cast<const double2 *>(u + 4LL * sv + j),
+                  A5 = *reinterpret_cast<const double2 *>(u + 5LL * sv + j);
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const double c3 = -Lv + (j3 + h + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
+      const double U0 = h ? A0.y : A0.x, U2 = h ? A2.y : A2.x, U3 = h ? A3.y : A3.x, U4 = h ? A4.y : A4.x, U5 = h ? A5.y : A5.x;
+      v[0] += U0 + U5 / 4.;
+      v[1] += c1 * dv * U0 + U2 * dv * dv / 12. + U5 * c1 * dv / 4.;
+      v[2] += c2 * dv * U0 + U3 * dv * dv / 12. + U5 * c2 * dv / 4.;
+      v[3] += c3 * dv * U0 + U4 * dv * dv / 12. + U5 * c3 * dv / 4.;
+      v[4] += U0 * (r2 + dv * dv / 4.) * dv + (c1 * U2 + c2 * U3 + c3 * U4) * dv * dv / 6. + U5 * (dv * dv * dv * 19. / 240. + r2 * dv / 4.);
+    }
   }
   block_sum<5>(v, red);
   if (threadIdx.x == 0)
@@ -667,9 +689,12 @@ int lp_launch_moments(lpgpu_ctx *c, const double *planes)
 {
   // d_B is free outside the projection: use its head for the per-cell partials
   double *part = c->d_B;
-  const int chunks = c->sv >= 4096 ? 16 : 1;   // blocks per x cell (one block per cell left most of the GPU idle)
+  const int chunks = c->sv >= 4096 ? (c->ncell >= 64 ? 8 : 32) : 1;   // blocks per x cell (one block per cell left most of the GPU idle)
+  const bool prof4 = c->prof_on == 4 && c->prof_used + 2 <= c->prof_ev.size();   // bench.py: achieved HBM GB/s of the moment reduction
+  if (prof4) LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
   k_moments_cell<<<dim3(c->ncell, chunks), 256, 0, c->stream>>>(planes, part, c->p.Nv, c->sv, c->tab.dv, c->p.Lv);
   LP_LAUNCHED(c);
+  if (prof4) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
   const double xs = c->p.homogeneous ? 1. : c->p.Lx / c->p.Nx;
   k_moments_fold<<<1, 32, 0, c->stream>>>(part, c->d_mom, c->ncell * chunks, xs, c->tab.dv, c->tab.scalev);
   LP_LAUNCHED(c);
