@@ -1,6 +1,7 @@
 // extern "C" boundary of liblpgpu.so (declared in include/lpgpu.h).  Host orchestration only:
 // every numerical operation is a kernel in collision.cu / computeq.cu / advection.cu.
 #include "lpgpu_internal.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -107,6 +108,27 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   A_(dev_upload(&c->d_T, t.T));
   A_(dev_upload(&c->d_M, t.M));
   A_(dev_upload(&c->d_S, t.S));
+  // The folded projection (collision.cu, k_project_slab_h) needs table(-k) = conj table(k).  That holds to round-off when
+  // eta[N/2] is exactly 0 (N a power of two); for other N the reference's eta grid leaves eta[N/2] ~ 1e-16, the k = 0 row
+  // of M and S is then round-off noise divided by eta^2 (a reference quirk the tables reproduce, part of the N = 24
+  // blow-up), and the projection has to contract all N slabs as the reference does.
+  c->project_fold = 1;
+  for (int w = 0; w < 3; w++) {
+    const std::vector<double> &x = w == 0 ? t.T : w == 1 ? t.M : t.S;
+    double big = 0., defect = 0.;
+    for (size_t i = 0; i < x.size(); i++) big = std::max(big, std::fabs(x[i]));
+    for (int k = 1; k < p->N; k++)
+      for (int j = 0; j < p->Nv; j++) {
+        const size_t a = 2 * ((size_t)k * p->Nv + j), b = 2 * ((size_t)(p->N - k) * p->Nv + j);
+        defect = std::max(defect, std::max(std::fabs(x[a] - x[b]), std::fabs(x[a + 1] + x[b + 1])));
+      }
+    if (!(defect <= 1e-12 * big)) c->project_fold = 0;
+  }
+  for (int w = 0; w < 3; w++) {               // row N = conj(row 0): the wave number +N/2 of the folded projection
+    std::vector<double> x(w == 0 ? t.T : w == 1 ? t.M : t.S);
+    for (int j = 0; j < p->Nv; j++) { x.push_back(x[2 * j]); x.push_back(-x[2 * j + 1]); }
+    A_(dev_upload(w == 0 ? &c->d_Tx : w == 1 ? &c->d_Mx : &c->d_Sx, x));
+  }
   A_(dev_upload(&c->d_node_xi, t.node_xi));
   A_(dev_upload(&c->d_vc, t.vc));
   A_(dev_upload(&c->d_Etab, t.Etab));
@@ -167,7 +189,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   if (!c) return LPGPU_OK;
   cudaSetDevice(c->p.device);
   cudaDeviceSynchronize();
-  double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_node_xi, c->d_vc,
+  double *ptrs[] = {c->d_eta, c->d_G, c->d_C5, c->d_CCt, c->d_Wfwd, c->d_Winv, c->d_pre_fwd, c->d_pre_inv, c->d_post_fwd, c->d_post_inv, c->d_wt, c->d_T, c->d_M, c->d_S, c->d_Tx, c->d_Mx, c->d_Sx, c->d_node_xi, c->d_vc,
                     c->d_U[0], c->d_U[1], c->d_U[2], c->d_aos, c->d_ms_local, c->d_ms_all, c->d_fld, c->d_mom, c->d_f, c->d_f1,
                     c->d_Qv, c->d_fhat, c->d_tmp, c->d_q[0], c->d_q[1], c->d_q[2], c->d_q[3], c->d_lam, c->d_B, c->d_Etab, c->d_qpart, c->d_ms_part, c->d_fc1, c->d_fc2, c->d_fctw, c->d_Gt, c->d_cpart, c->d_Gl, c->d_ql, c->d_CCt_lin, c->d_dirichlet, c->d_mhat, c->d_GtLin, c->d_ones, c->d_fl_tmp, c->d_fl_g};
   for (double *q : ptrs) if (q) cudaFree(q);

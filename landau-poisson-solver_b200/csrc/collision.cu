@@ -1007,6 +1007,165 @@ __global__ void __launch_bounds__(128) k_project_final_t(const double2 *__restri
   }
 }
 
+// ---- Hermitian-folded projection.  The projection keeps only the real part, and the 1-D factors satisfy
+// T(-k) = conj T(k) (same for M, S), so  Re IntM(-k) X[-k] = Re IntM(k) conj(X[-k]):  the k1 < 0 half of the spectrum is
+// folded onto the k1 > 0 half *before* the contractions,
+//   Y[k1][k2][k3] = X[k1][k2][k3] + conj X[-k1][-k2][-k3]     (k1 > 0),
+// and N/2 + 1 slabs are contracted instead of N (k1 = -N/2 and k1 = 0 have no partner slab and stay as they are).  Exact
+// for any X -- nothing is assumed about X being Hermitian.  The wave numbers run over [-N/2, N/2 - 1], so the partner of
+// an entry with k2 = -N/2 or k3 = -N/2 has the wave number +N/2 that the arrays do not hold: k2 and k3 are therefore
+// contracted over N + 1 entries, entry N standing for +N/2 with the table row conj(row 0) (tTx, tMx, tSx: [N+1][Nv]).
+// slab s of a cell: s = 0 -> index 0 (k1 = -N/2), s = 1 -> index N/2 (k1 = 0), s >= 2 -> index N/2 + s - 1 folded with N - index.
+__device__ __forceinline__ int fold_index(int s, int N) { return s == 0 ? 0 : N / 2 + s - 1; }
+
+__global__ void __launch_bounds__(256, 2) k_project_slab_h(const double2 *__restrict__ q0, const double2 *__restrict__ q1,
+                                                           const double2 *__restrict__ q2, const double2 *__restrict__ q3,
+                                                           double2 *__restrict__ Bbuf, const double2 *__restrict__ tTx,
+                                                           const double2 *__restrict__ tMx, const double2 *__restrict__ tSx,
+                                                           int N, int Nv, double nu)
+{
+  extern __shared__ double2 sm2[];
+  const int K = N + 1, P = K | 1, PV = Nv + 1, NH = N / 2 + 1;
+  double2 *Xs = sm2;                 // [K][P]
+  double2 *As = Xs + K * P;          // [3][K][PV]
+  double2 *Ps = As + 3 * K * PV;     // [N/4][3][Nv]: partial sums of row N of As
+  const long long cell = blockIdx.x / NH;
+  const int s = blockIdx.x % NH, i1 = fold_index(s, N);
+  const bool paired = s >= 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long long base = (cell * N + i1) * N * N, pbase = (cell * N + (N - i1)) * N * N;
+  for (int t = tid; t < K * K; t += nt) {
+    const int i2 = t / K, i3 = t % K;
+    double2 y = make_double2(0., 0.);
+    if (i2 < N && i3 < N) {
+      const long long g = base + i2 * N + i3;
+      const double2 a = q0[g], b = q1[g], c = q2[g], d = q3[g];
+      y = make_double2(nu * (0.5 * a.x + (b.x + c.x + d.x) * (1. / 6.)), nu * (0.5 * a.y + (b.y + c.y + d.y) * (1. / 6.)));
+    }
+    if (paired && i2 > 0 && i3 > 0) {
+      const long long g = pbase + (N - i2) * N + (N - i3);
+      const double2 a = q0[g], b = q1[g], c = q2[g], d = q3[g];
+      y.x += nu * (0.5 * a.x + (b.x + c.x + d.x) * (1. / 6.));
+      y.y -= nu * (0.5 * a.y + (b.y + c.y + d.y) * (1. / 6.));
+    }
+    Xs[i2 * P + i3] = y;
+  }
+  __syncthreads();
+  // contract k3: As[tab][k2][j3], thread = (j3, four consecutive k2 < N); row k2 = N is shared out: the thread of group g
+  // adds up k3 = 4g .. 4g+3 (group 0 also k3 = N) and the partial sums are folded after the barrier
+  for (int it = tid; it < (N / 4) * Nv; it += nt) {
+    const int j3 = it % Nv, g = it / Nv, k20 = 4 * g;
+    double2 aT[4], aM[4], aS[4];
+    #pragma unroll
+    for (int kk = 0; kk < 4; kk++) aT[kk] = aM[kk] = aS[kk] = make_double2(0., 0.);
+    #pragma unroll 2
+    for (int k3 = 0; k3 < K; k3++) {
+      const double2 T3 = tTx[k3 * Nv + j3], M3 = tMx[k3 * Nv + j3], S3 = tSx[k3 * Nv + j3];
+      #pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const double2 x = Xs[(k20 + kk) * P + k3];
+        cfma(aT[kk], T3, x); cfma(aM[kk], M3, x); cfma(aS[kk], S3, x);
+      }
+    }
+    #pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      As[(0 * K + k20 + kk) * PV + j3] = aT[kk]; As[(1 * K + k20 + kk) * PV + j3] = aM[kk]; As[(2 * K + k20 + kk) * PV + j3] = aS[kk];
+    }
+    double2 pT = make_double2(0., 0.), pM = pT, pS = pT;
+    for (int kk = 0; kk < (g == 0 ? 5 : 4); kk++) {
+      const int k3 = kk < 4 ? k20 + kk : N;
+      const double2 x = Xs[N * P + k3];
+      cfma(pT, tTx[k3 * Nv + j3], x); cfma(pM, tMx[k3 * Nv + j3], x); cfma(pS, tSx[k3 * Nv + j3], x);
+    }
+    Ps[(g * 3 + 0) * Nv + j3] = pT; Ps[(g * 3 + 1) * Nv + j3] = pM; Ps[(g * 3 + 2) * Nv + j3] = pS;
+  }
+  __syncthreads();
+  for (int t = tid; t < 3 * Nv; t += nt) {
+    const int w = t / Nv, j3 = t % Nv;
+    double2 a = make_double2(0., 0.);
+    for (int g = 0; g < N / 4; g++) { const double2 x = Ps[(g * 3 + w) * Nv + j3]; a.x += x.x; a.y += x.y; }
+    As[(w * K + N) * PV + j3] = a;
+  }
+  __syncthreads();
+  // contract k2: thread = (j3, four consecutive j2)
+  const int Pq = Nv * Nv;
+  for (int it = tid; it < (Nv / 4) * Nv; it += nt) {
+    const int j3 = it % Nv, j20 = 4 * (it / Nv);
+    double2 bTT[4], bMT[4], bTM[4], bS[4];
+    #pragma unroll
+    for (int jj = 0; jj < 4; jj++) bTT[jj] = bMT[jj] = bTM[jj] = bS[jj] = make_double2(0., 0.);
+    #pragma unroll 2
+    for (int k2 = 0; k2 < K; k2++) {
+      const double2 at = As[(0 * K + k2) * PV + j3], am = As[(1 * K + k2) * PV + j3], as = As[(2 * K + k2) * PV + j3];
+      #pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const double2 T2 = tTx[k2 * Nv + j20 + jj], M2 = tMx[k2 * Nv + j20 + jj], S2 = tSx[k2 * Nv + j20 + jj];
+        cfma(bTT[jj], T2, at); cfma(bMT[jj], M2, at); cfma(bTM[jj], T2, am); cfma(bS[jj], S2, at); cfma(bS[jj], T2, as);
+      }
+    }
+    #pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      double2 *o = Bbuf + (long long)blockIdx.x * 4 * Pq + (j20 + jj) * Nv + j3;
+      o[0] = bTT[jj]; o[Pq] = bMT[jj]; o[2 * Pq] = bTM[jj]; o[3 * Pq] = bS[jj];
+    }
+  }
+}
+// k1 contraction over the N/2 + 1 folded slabs + the DG update; otherwise k_project_final_t.
+__global__ void __launch_bounds__(128) k_project_final_h(const double2 *__restrict__ Bbuf, double *__restrict__ planes,
+                                                         const double2 *__restrict__ tT, const double2 *__restrict__ tM,
+                                                         const double2 *__restrict__ tS, int N, int Nv, int sv, double fac)
+{
+  extern __shared__ double2 Bs[];          // [s][4][32] | T, M, S [s][Nv]
+  const int Pq = Nv * Nv, NH = N / 2 + 1;
+  const long long cell = blockIdx.y; const int p0 = 32 * blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  double2 *sT = Bs + NH * 128, *sM = sT + NH * Nv, *sS = sM + NH * Nv;
+  for (int idx = tid; idx < NH * 4 * 32; idx += blockDim.x) {
+    const int s = idx >> 7, w = (idx >> 5) & 3, pp = idx & 31;
+    fc3::cp16(Bs + idx, Bbuf + ((cell * NH + s) * 4 + w) * Pq + p0 + pp);
+  }
+  for (int idx = tid; idx < NH * Nv; idx += blockDim.x) {
+    const int g = fold_index(idx / Nv, N) * Nv + idx % Nv;
+    fc3::cp16(sT + idx, tT + g); fc3::cp16(sM + idx, tM + g); fc3::cp16(sS + idx, tS + g);
+  }
+  fc3::cp_wait_all();
+  __syncthreads();
+  const int p = p0 + lane;
+  for (int j10 = 8 * warp; j10 < Nv; j10 += 8 * nw) {
+    double tp0[8], tp2[8], tp3[8], tp4[8], tp5[8];
+    #pragma unroll
+    for (int a = 0; a < 8; a++) tp0[a] = tp2[a] = tp3[a] = tp4[a] = tp5[a] = 0.;
+    #pragma unroll 2
+    for (int k1 = 0; k1 < NH; k1++) {
+      const double2 *b = Bs + k1 * 128 + lane;
+      const double2 btt = b[0], bmt = b[32], btm = b[64], bs = b[96];
+      #pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const double2 T1 = sT[k1 * Nv + j10 + a], M1 = sM[k1 * Nv + j10 + a], S1 = sS[k1 * Nv + j10 + a];
+        tp0[a] = fma(T1.x, btt.x, tp0[a]); tp0[a] = fma(-T1.y, btt.y, tp0[a]);
+        tp2[a] = fma(M1.x, btt.x, tp2[a]); tp2[a] = fma(-M1.y, btt.y, tp2[a]);
+        tp3[a] = fma(T1.x, bmt.x, tp3[a]); tp3[a] = fma(-T1.y, bmt.y, tp3[a]);
+        tp4[a] = fma(T1.x, btm.x, tp4[a]); tp4[a] = fma(-T1.y, btm.y, tp4[a]);
+        tp5[a] = fma(S1.x, btt.x, tp5[a]); tp5[a] = fma(-S1.y, btt.y, tp5[a]);
+        tp5[a] = fma(T1.x, bs.x, tp5[a]); tp5[a] = fma(-T1.y, bs.y, tp5[a]);
+      }
+    }
+    #pragma unroll
+    for (int a = 0; a < 8; a++) {
+      double *u = planes + ((cell + 1) * 6) * (long long)sv + (long long)(j10 + a) * Pq + p;
+      const double U0 = u[0], U2 = u[2LL * sv], U3 = u[3LL * sv], U4 = u[4LL * sv], U5 = u[5LL * sv];
+      const double t0 = U0 + U5 * 0.25 + tp0[a] * fac;
+      const double t2 = U2 + tp2[a] * (12. * fac);
+      const double t3 = U3 + tp3[a] * (12. * fac);
+      const double t4 = U4 + tp4[a] * (12. * fac);
+      const double t5 = U0 * 0.25 + U5 * (19. / 240.) + tp5[a] * fac;
+      u[0] = 19 * t0 * 0.25 - 15 * t5;
+      u[5LL * sv] = 60 * t5 - 15 * t0;
+      u[2LL * sv] = t2; u[3LL * sv] = t3; u[4LL * sv] = t4;      // U[6k+1] is not touched by collisions
+    }
+  }
+}
+
 int lp_launch_project(lpgpu_ctx *c, double *planes, int B)
 {
   const int N = c->p.N, Nv = c->p.Nv;
@@ -1017,6 +1176,24 @@ int lp_launch_project(lpgpu_ctx *c, double *planes, int B)
   const double2 *T = reinterpret_cast<const double2 *>(c->d_T), *M = reinterpret_cast<const double2 *>(c->d_M),
                 *S = reinterpret_cast<const double2 *>(c->d_S);
   static const bool simple_only = getenv("LPGPU_PROJECT_SIMPLE") != nullptr;   // developer knob
+  static const bool unfolded = getenv("LPGPU_PROJECT_UNFOLDED") != nullptr;    // developer knob: contract all N slabs
+  if (!simple_only && !unfolded && c->project_fold && N % 4 == 0 && Nv % 8 == 0) {
+    const int K = N + 1, NH = N / 2 + 1;
+    const size_t smemh = ((size_t)K * (K | 1) + (size_t)3 * K * (Nv + 1) + (size_t)(N / 4) * 3 * Nv) * sizeof(double2);
+    LP_CUDA(cudaFuncSetAttribute(k_project_slab_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemh));
+    k_project_slab_h<<<B * NH, 256, smemh, c->stream>>>(
+        reinterpret_cast<const double2 *>(c->d_q[0]), reinterpret_cast<const double2 *>(c->d_q[1]),
+        reinterpret_cast<const double2 *>(c->d_q[2]), reinterpret_cast<const double2 *>(c->d_q[3]),
+        reinterpret_cast<double2 *>(c->d_B), reinterpret_cast<const double2 *>(c->d_Tx), reinterpret_cast<const double2 *>(c->d_Mx),
+        reinterpret_cast<const double2 *>(c->d_Sx), N, Nv, c->p.nu);
+    LP_LAUNCHED(c);
+    const double fac = c->p.dt / c->tab.scalev / c->tab.scaleL / c->tab.scale3;
+    const size_t smemf = ((size_t)NH * 4 * 32 + (size_t)3 * NH * Nv) * sizeof(double2);
+    LP_CUDA(cudaFuncSetAttribute(k_project_final_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf));
+    k_project_final_h<<<dim3(Nv * Nv / 32, B), 128, smemf, c->stream>>>(reinterpret_cast<const double2 *>(c->d_B), planes, T, M, S, N, Nv, c->sv, fac);
+    LP_LAUNCHED(c);
+    return LPGPU_OK;
+  }
   if (!simple_only && N % 4 == 0 && Nv % 8 == 0) {
     LP_CUDA(cudaFuncSetAttribute(k_project_slab_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_project_slab_t<<<B * N, 256, smem, c->stream>>>(

@@ -51,6 +51,8 @@ struct lpgpu_ctx {
   double *d_Etab, *d_qpart;
   size_t cap_part;         // capacity of d_qpart in spectra (cells x l-splits)
   double *d_eta, *d_G, *d_C5, *d_CCt, *d_Wfwd, *d_Winv, *d_pre_fwd, *d_pre_inv, *d_post_fwd, *d_post_inv, *d_wt, *d_T, *d_M, *d_S, *d_node_xi, *d_vc;
+  int project_fold;                        // 1: T, M, S are conjugate-symmetric in k, the projection may fold k1 < 0 onto k1 > 0
+  double *d_Tx, *d_Mx, *d_Sx;              // T, M, S with a row N = conj(row 0) appended (wave number +N/2; folded projection)
   int *d_node_cell;
   // ---- DG state, plane-major: buf[((p*6 + c)*sv + j)], p = 0..ncell+1 (planes 0 and ncell+1 are x halos)
   double *d_U[3];
