@@ -111,7 +111,9 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
   // The folded projection (collision.cu, k_project_slab_h) needs table(-k) = conj table(k).  That holds to round-off when
   // eta[N/2] is exactly 0 (N a power of two); for other N the reference's eta grid leaves eta[N/2] ~ 1e-16, the k = 0 row
   // of M and S is then round-off noise divided by eta^2 (a reference quirk the tables reproduce, part of the N = 24
-  // blow-up), and the projection has to contract all N slabs as the reference does.
+  // blow-up), and the projection has to contract all N slabs as the reference does.  The threshold separates the two
+  // cases by orders of magnitude: the closed forms of M and S cancel (~Nv and ~Nv^2 ulp), so symmetric tables show a
+  // relative defect of 1e-15 (T) to 1e-11 (S at Nv = 64); the noise row gives O(1).
   c->project_fold = 1;
   for (int w = 0; w < 3; w++) {
     const std::vector<double> &x = w == 0 ? t.T : w == 1 ? t.M : t.S;
@@ -122,7 +124,7 @@ int lpgpu_init(const lpgpu_params *p, lpgpu_ctx **out)
         const size_t a = 2 * ((size_t)k * p->Nv + j), b = 2 * ((size_t)(p->N - k) * p->Nv + j);
         defect = std::max(defect, std::max(std::fabs(x[a] - x[b]), std::fabs(x[a + 1] + x[b + 1])));
       }
-    if (!(defect <= 1e-12 * big)) c->project_fold = 0;
+    if (!(defect <= 1e-9 * big)) c->project_fold = 0;
   }
   for (int w = 0; w < 3; w++) {               // row N = conj(row 0): the wave number +N/2 of the folded projection
     std::vector<double> x(w == 0 ? t.T : w == 1 ? t.M : t.S);
