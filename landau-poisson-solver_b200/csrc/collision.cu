@@ -270,12 +270,17 @@ __global__ void __launch_bounds__(N) k_tf_i(const double2 *__restrict__ in, doub
 // forward one, so the stage input f1 never goes to memory (it was 8 B written + 8 B read per node and a launch per stage).
 // in/out: the FS spectrum after its i pass / the forward spectrum before its i pass; the same buffer, slab by slab.
 template <int N, int EPI>
-__global__ void __launch_bounds__(N) k_tf_jk_fs_fft(const double2 *__restrict__ in, double2 *__restrict__ out, PhaseTabs inv, PhaseTabs fwd, FsEpilogue ep)
+__global__ void __launch_bounds__(N, 12) k_tf_jk_fs_fft(const double2 *__restrict__ in, double2 *__restrict__ out, PhaseTabs inv, PhaseTabs fwd, FsEpilogue ep)
 {
   constexpr int P = N + 1;
   __shared__ double2 X[N * P];
   const long long slab = blockIdx.x;                 // cell*N + i
   const int i = (int)(slab % N), t = threadIdx.x;
+  // the epilogue's f and Qv rows: start them towards L2 now, they are needed two transform passes later
+  for (int l = t; l < N * N / 16; l += N) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(ep.f + slab * N * N + l * 16));
+    if (EPI != 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(ep.Qv + slab * N * N + l * 16));
+  }
   #pragma unroll 16
   for (int j = 0; j < N; j++) X[j * P + t] = __ldg(in + slab * N * N + j * N + t);
   __syncthreads();
@@ -289,21 +294,39 @@ __global__ void __launch_bounds__(N) k_tf_jk_fs_fft(const double2 *__restrict__ 
   #pragma unroll
   for (int j = 0; j < N; j++) v[j] = X[j * P + t];          // column k = t
   fc3::fftN<N, +1, N>(v);
-  __syncthreads();                                          // every column is in registers: X may be refilled
+  // Column t of X is this thread's alone from the load above to the barrier below.  The column is parked there so that
+  // the registers can hold the epilogue's operands (post-phase, f, Qv) for N/2 rows at a time: two memory round trips
+  // per slab; fetched row by row next to the 2N live transform registers, every row waited for its own loads.
   #pragma unroll
-  for (int j = 0; j < N; j++) {
-    const long long g = slab * N * N + j * N + t;
-    const double2 acc = phase_mul(__ldg(inv.post + (i * N + j) * N + t), v[j]);
-    const double Q = acc.x * ep.inv;
-    double f1;
-    if (EPI == 1) { ep.Qv[g] = Q; f1 = __ldg(ep.f + g) + ep.dt * Q * ep.nu; }
-    else if (EPI == 2) f1 = __ldg(ep.f + g) + 0.5 * ep.dt * __ldg(ep.Qv + g) * ep.nu + 0.5 * ep.dt * Q * ep.nu;
-    else f1 = __ldg(ep.f + g) + 0.5 * __ldg(ep.Qv + g) * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
-    // fft3D's pre-phase and quadrature weights on the new stage input, exactly as k_tf_jk<fwd> applies them
-    double2 x = phase_mul(__ldg(fwd.pre + i + j + t), make_double2(f1, 0.));
-    const double fac = fwd.c3 * fwd.wt[i] * fwd.wt[j] * fwd.wt[t];
-    x.x = __dmul_rn(fac, x.x); x.y = __dmul_rn(fac, x.y);
-    X[j * P + t] = x;
+  for (int j = 0; j < N; j++) X[j * P + t] = v[j];
+  constexpr int H = N / 2;
+  #pragma unroll
+  for (int j0 = 0; j0 < N; j0 += H) {
+    double2 pz[H]; double ff[H], qq[H];
+    #pragma unroll
+    for (int jj = 0; jj < H; jj++) {
+      const int j = j0 + jj;
+      const long long g = slab * N * N + j * N + t;
+      pz[jj] = __ldg(inv.post + (i * N + j) * N + t);
+      ff[jj] = __ldg(ep.f + g);
+      qq[jj] = EPI == 1 ? 0. : __ldg(ep.Qv + g);
+    }
+    #pragma unroll
+    for (int jj = 0; jj < H; jj++) {
+      const int j = j0 + jj;
+      const long long g = slab * N * N + j * N + t;
+      const double2 acc = phase_mul(pz[jj], X[j * P + t]);
+      const double Q = acc.x * ep.inv;
+      double f1;
+      if (EPI == 1) { ep.Qv[g] = Q; f1 = ff[jj] + ep.dt * Q * ep.nu; }
+      else if (EPI == 2) f1 = ff[jj] + 0.5 * ep.dt * qq[jj] * ep.nu + 0.5 * ep.dt * Q * ep.nu;
+      else f1 = ff[jj] + 0.5 * qq[jj] * ep.nu + 0.5 * Q * ep.nu;   // no dt: reference quirk (:940, :1122)
+      // fft3D's pre-phase and quadrature weights on the new stage input, exactly as k_tf_jk<fwd> applies them
+      double2 x = phase_mul(__ldg(fwd.pre + i + j + t), make_double2(f1, 0.));
+      const double fac = fwd.c3 * fwd.wt[i] * fwd.wt[j] * fwd.wt[t];
+      x.x = __dmul_rn(fac, x.x); x.y = __dmul_rn(fac, x.y);
+      X[j * P + t] = x;
+    }
   }
   __syncthreads();
   #pragma unroll
@@ -793,7 +816,9 @@ int lp_launch_fs_conserving(lpgpu_ctx *c, double *q, const double *part, int mod
   if (next_fwd && !unfused && mode >= 1 && mode <= 3) {
     PhaseTabs inv = {nullptr, reinterpret_cast<const double2 *>(c->d_post_inv), nullptr, 0.};
     PhaseTabs fwd = {reinterpret_cast<const double2 *>(c->d_pre_fwd), nullptr, c->d_wt, c->tab.c3_fwd};
-#define LP_FSFFT(NN, EE) k_tf_jk_fs_fft<NN, EE><<<B * NN, NN, 0, c->stream>>>(o2, o2, inv, fwd, ep)
+    // (twelve one-warp CTAs per SM need the whole shared-memory carve-out)
+#define LP_FSFFT(NN, EE) do { cudaFuncSetAttribute(k_tf_jk_fs_fft<NN, EE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+                              k_tf_jk_fs_fft<NN, EE><<<B * NN, NN, 0, c->stream>>>(o2, o2, inv, fwd, ep); } while (0)
 #define LP_FSFFT_N(NN) do { if (mode == 1) LP_FSFFT(NN, 1); else if (mode == 2) LP_FSFFT(NN, 2); else LP_FSFFT(NN, 3); } while (0)
     if (N == 32) LP_FSFFT_N(32); else if (N == 24) LP_FSFFT_N(24); else if (N == 16) LP_FSFFT_N(16); else LP_FSFFT_N(8);
 #undef LP_FSFFT_N

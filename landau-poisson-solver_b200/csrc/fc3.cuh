@@ -491,15 +491,22 @@ struct F3 {
     const double sc = 1.0 / ((double)M * M * M);
     constexpr int N3 = N * N * N;
     double2 *o = q + (long long)cell * N3 + (long long)xo * N * N;
-    for (int idx = tid; idx < N * N; idx += NT) {
-      const int yo = idx / N, zo = idx % N, l = zo % L, sh = zo / L + 1;
-      const double2 v = inv_combine(T3[l * PN + yo], T3[(L + l) * PN + yo], T3[(2 * L + l) * PN + yo], sh);
-      const double2 w = make_double2(v.x * sc, v.y * sc);
-      o[idx] = w;
-      if (C5) {
-        const int g = xo * N * N + idx;
-        s[0] += w.x * C5[g]; s[1] += w.y * C5[N3 + g]; s[2] += w.y * C5[2 * N3 + g];
-        s[3] += w.y * C5[3 * N3 + g]; s[4] += w.x * C5[4 * N3 + g];
+    // unrolled with the bound as a predicate: the loads of the conservation rows of all the iterations go out together
+    // (the runtime-bound loop fetched them one iteration at a time, eleven L2 round trips per CTA)
+    constexpr int IT = (N * N + NT - 1) / NT;
+    #pragma unroll
+    for (int it = 0; it < IT; it++) {
+      const int idx = tid + it * NT;
+      if (idx < N * N) {
+        const int yo = idx / N, zo = idx % N, l = zo % L, sh = zo / L + 1;
+        const double2 v = inv_combine(T3[l * PN + yo], T3[(L + l) * PN + yo], T3[(2 * L + l) * PN + yo], sh);
+        const double2 w = make_double2(v.x * sc, v.y * sc);
+        o[idx] = w;
+        if (C5) {
+          const int g = xo * N * N + idx;
+          s[0] += w.x * C5[g]; s[1] += w.y * C5[N3 + g]; s[2] += w.y * C5[2 * N3 + g];
+          s[3] += w.y * C5[3 * N3 + g]; s[4] += w.x * C5[4 * N3 + g];
+        }
       }
     }
   }
