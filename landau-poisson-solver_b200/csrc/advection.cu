@@ -545,12 +545,25 @@ __global__ void __launch_bounds__(256) k_moments_cell(const double *__restrict__
   if (threadIdx.x == 0)
     for (int m = 0; m < 5; m++) part[5 * (cell * gridDim.y + blockIdx.y) + m] = v[m];
 }
-__global__ void k_moments_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double xs, double dv, double scalev)
+// fold of n partial rows of NV values: thread t adds rows t, t + 256, ... in that order, block_sum adds the 256 threads in
+// a fixed tree -- the same bits run to run, and not the 0.8 ms (moments, 512 cells) / 3.5 ms (diagnostics) that one
+// thread walking all the rows took
+template <int NV>
+__device__ __forceinline__ void fold_rows(const double *__restrict__ part, int n, double (&v)[NV], double *red)
 {
+  #pragma unroll
+  for (int m = 0; m < NV; m++) v[m] = 0.;
+  for (int c = threadIdx.x; c < n; c += blockDim.x)
+    #pragma unroll
+    for (int m = 0; m < NV; m++) v[m] += part[NV * c + m];
+  block_sum<NV>(v, red);
+}
+__global__ void __launch_bounds__(256) k_moments_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double xs, double dv, double scalev)
+{
+  __shared__ double red[5 * 32];
+  double v[5];
+  fold_rows<5>(part, ncell, v, red);
   if (threadIdx.x != 0) return;
-  double v[5] = {0., 0., 0., 0., 0.};
-  for (int c = 0; c < ncell; c++)
-    for (int m = 0; m < 5; m++) v[m] += part[5 * c + m];
   out[0] = v[0] * xs * scalev;
   out[1] = v[1] * xs * dv * dv; out[2] = v[2] * xs * dv * dv; out[3] = v[3] * xs * dv * dv;
   out[4] = 0.5 * v[4] * xs * dv * dv;
@@ -564,33 +577,39 @@ __global__ void k_moments_fold(const double *__restrict__ part, double *__restri
 // number of negative cells.
 __constant__ double c_gw[5] = {0.5688888888888889, 0.4786286704993665, 0.4786286704993665, 0.2369268850561891, 0.2369268850561891};
 __constant__ double c_gt[5] = {0., -0.5384693101056831, 0.5384693101056831, -0.9061798459386640, 0.9061798459386640};
-// log of a positive double for the entropy integrand: 64-interval table on the mantissa (c_i = 1 + (i + 1/2)/64, the
-// table holds rc_i = fl(1/c_i) and -log(rc_i)), d = m rc_i - 1 by one FMA (|d| <= 1/128), log1p(d) to degree 7
-// (truncation 2e-18).  |error| <= 2e-16 (1 + |log x|): the same bound as libm's to within a factor of two, at a fifth of
+// log of a positive double for the entropy integrand: 128-interval table on the mantissa (c_i = 1 + (i + 1/2)/128, the
+// table holds rc_i = fl(1/c_i) and -log(rc_i)), d = m rc_i - 1 by one FMA (|d| <= 1/256), log1p(d) to degree 6
+// (truncation d^7/7 <= 2e-18).  |error| <= 2e-16 (1 + |log x|): the same bound as libm's to within a factor of two, at a fifth of
 // its FP64 instructions -- the entropy (5^4 logarithms per DG cell per step) is bound by exactly those.
-// x is a normal number here (the caller clamps at 1e-300): no special cases, no branches.
-__device__ __forceinline__ double log_pos(double x, const double2 *__restrict__ tab)
+// x is a positive normal number or +inf where the result is used; anything else gives a finite or NaN value the caller
+// discards.  No special cases, no branches.  The 5^4-point rule executes this 10^10 times per step at Nx = 512, so the
+// instruction count matters as much as the FP64 count: the coefficients are constant-bank operands (as immediates the
+// compiler rebuilt each of them in uniform registers for every call), and the table is read with ld.shared from a
+// 32-bit address made once per thread (through a pointer the shared window base was recomputed per call).
+__constant__ double c_lp[4] = {-1. / 6., 0.2, 1. / 3., 0.693147180559945309417};
+__device__ __forceinline__ double log_pos(double x, unsigned tab_s)
 {
-  const long long bits = __double_as_longlong(x);
-  const int hi = (int)(bits >> 32), ex = (hi >> 20) & 0x7ff;
-  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);   // [1, 2)
-  const double2 t = tab[(hi >> 14) & 63];
-  const double d = fma(m, t.x, -1.0);
-  double q = fma(d, 1. / 7., -1. / 6.);
-  q = fma(d, q, 0.2); q = fma(d, q, -0.25); q = fma(d, q, 1. / 3.); q = fma(d, q, -0.5);
+  const int hi = __double2hiint(x);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+  double rc, lrc;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(tab_s + ((hi >> 9) & 0x7f0)));
+  const double d = fma(m, rc, -1.0);
+  double q = fma(d, c_lp[0], c_lp[1]);
+  q = fma(d, q, -0.25); q = fma(d, q, c_lp[2]); q = fma(d, q, -0.5);
   const double p = fma(d * d, q, d);
-  return fma((double)(ex - 1023), 0.693147180559945309417, t.y + p);
+  return fma((double)((hi >> 20) - 1023), c_lp[3], lrc + p);
 }
 __global__ void __launch_bounds__(128, 4) k_diag_cell(const double *__restrict__ planes, double *__restrict__ part, int Nv, int sv,
                                                    double dv, double Lv, int homogeneous)
 {
   __shared__ double red[4 * 32];
-  __shared__ double2 ltab[64];
-  if (threadIdx.x < 64) {
-    const double rc = 1.0 / (1.0 + (threadIdx.x + 0.5) / 64.);
+  __shared__ double2 ltab[128];
+  {
+    const double rc = 1.0 / (1.0 + (threadIdx.x + 0.5) / 128.);   // 128 threads: one entry each
     ltab[threadIdx.x] = make_double2(rc, -log(rc));
   }
   __syncthreads();
+  const unsigned tab_s = (unsigned)__cvta_generic_to_shared(ltab);
   const long long cell = blockIdx.x;
   const double *u = planes + ((cell + 1) * 6) * (long long)sv;
   double v[4] = {0., 0., 0., 0.};
@@ -603,20 +622,26 @@ __global__ void __launch_bounds__(128, 4) k_diag_cell(const double *__restrict__
       for (int b = 0; b < 5; b++)
         #pragma unroll
         for (int cc = 0; cc < 5; cc++) {
-          // same expressions, same association as the one-line form: only what does not depend on d is computed once
+          // the point values f are formed exactly as in the reference's one-line expression; the weights are applied
+          // innermost-first (w_d inside, w_a w_b w_c once per line of five points)
           const double xs = homogeneous ? 0. : 0.5 * c_gt[a], x1 = 0.5 * c_gt[b], x2 = 0.5 * c_gt[cc];
           const double head = U0 + (homogeneous ? 0. : U1 * xs) + U2 * x1 + U3 * x2;
           const double wabc = (homogeneous ? 1. : c_gw[a]) * c_gw[b] * c_gw[cc], q12 = x1 * x1 + x2 * x2;
+          double ein = 0., ain = 0.;
           #pragma unroll
           for (int d = 0; d < 5; d++) {
             const double x3 = 0.5 * c_gt[d];
             const double f = head + U4 * x3 + U5 * (q12 + x3 * x3);
-            const double w = wabc * c_gw[d];
-            // below 1e-300 the integrand is below 1e-297: the clamp keeps log_pos on normal numbers and changes nothing
-            const double lf = log_pos(fmax(f, 1e-300), ltab);
-            e = f > 0 ? fma(w * f, lf, e) : e;
-            avg += w * f;
+            const double lf = log_pos(f, tab_s);
+            // f > 0 (EntropyCalculations.cpp:71 adds f log f only there), as an integer test on the high word:
+            // positive normal numbers and +inf pass; zero, negatives, NaN and denormals below 2^-1042 (whose f log f is
+            // below 1e-310) do not
+            const bool pos = (unsigned)(__double2hiint(f) - 1) < 0x7ff00000u;
+            ein = pos ? fma(c_gw[d], f * lf, ein) : ein;
+            ain = fma(c_gw[d], f, ain);
           }
+          e = fma(wabc, ein, e);
+          avg = fma(wabc, ain, avg);
         }
     const int j3 = j % Nv, j2 = (j / Nv) % Nv, j1 = j / (Nv * Nv);
     const double c1 = -Lv + (j1 + 0.5) * dv, c2 = -Lv + (j2 + 0.5) * dv, c3 = -Lv + (j3 + 0.5) * dv, r2 = c1 * c1 + c2 * c2 + c3 * c3;
@@ -628,12 +653,12 @@ __global__ void __launch_bounds__(128, 4) k_diag_cell(const double *__restrict__
   if (threadIdx.x == 0)
     for (int m = 0; m < 4; m++) part[4 * (cell * gridDim.y + blockIdx.y) + m] = v[m];
 }
-__global__ void k_diag_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double scale)
+__global__ void __launch_bounds__(256) k_diag_fold(const double *__restrict__ part, double *__restrict__ out, int ncell, double scale)
 {
+  __shared__ double red[4 * 32];
+  double v[4];
+  fold_rows<4>(part, ncell, v, red);
   if (threadIdx.x != 0) return;
-  double v[4] = {0., 0., 0., 0.};
-  for (int c = 0; c < ncell; c++)
-    for (int m = 0; m < 4; m++) v[m] += part[4 * c + m];
   out[0] = v[0] * scale; out[1] = v[1]; out[2] = v[2]; out[3] = v[3];
 }
 int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev)
@@ -647,7 +672,7 @@ int lp_launch_diagnostics(lpgpu_ctx *c, const double *planes, double *out4_dev)
   LP_LAUNCHED(c);
   const double dv = c->tab.dv, dx = c->p.Lx / c->p.Nx;
   const double scale = 0.5 * dv * 0.5 * dv * 0.5 * dv * (c->p.homogeneous ? 1. : 0.5 * dx);
-  k_diag_fold<<<1, 32, 0, c->stream>>>(part, out4_dev, c->ncell * chunks, scale);
+  k_diag_fold<<<1, 256, 0, c->stream>>>(part, out4_dev, c->ncell * chunks, scale);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
@@ -696,7 +721,7 @@ int lp_launch_moments(lpgpu_ctx *c, const double *planes)
   LP_LAUNCHED(c);
   if (prof4) { LP_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream)); c->prof_used += 2; }
   const double xs = c->p.homogeneous ? 1. : c->p.Lx / c->p.Nx;
-  k_moments_fold<<<1, 32, 0, c->stream>>>(part, c->d_mom, c->ncell * chunks, xs, c->tab.dv, c->tab.scalev);
+  k_moments_fold<<<1, 256, 0, c->stream>>>(part, c->d_mom, c->ncell * chunks, xs, c->tab.dv, c->tab.scalev);
   LP_LAUNCHED(c);
   return LPGPU_OK;
 }
