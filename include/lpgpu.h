@@ -104,6 +104,13 @@ int lpgpu_collide_step_async(lpgpu_ctx *c);
 int lpgpu_step(lpgpu_ctx *c, int nsteps);
 /* Same, enqueued only (lpgpu_synchronize before reading results). */
 int lpgpu_step_async(lpgpu_ctx *c, int nsteps);
+/* One pass of the while(t<nT) body (LP_ompi.cpp:662-813) on a state that stays in HOST memory, as the reference's U does:
+ * U_in (this context's shard, the reference's layout U[6k+l]) -> RK3 -> collision step -> U_out.  Equivalent to
+ * lpgpu_upload_U(U_in); lpgpu_step(1); lpgpu_download_U(U_out), but pipelined over chunks of x cells: a chunk's layout
+ * kernel runs while the next chunk is still being copied, and the collided chunks travel back to U_out (the other PCIe
+ * direction) while the following chunks are collided.  Pass page-locked buffers for the copies to be asynchronous;
+ * U_out may be U_in.  Synchronous: the result is in U_out on return. */
+int lpgpu_step_host(lpgpu_ctx *c, const double *U_in, double *U_out);
 
 /* ---- sharded advection: one exchange per SSP-RK3 stage (stage = 0,1,2) ------------------- */
 /* Device addresses (in this context's memory) for the exchange of stage `stage`:

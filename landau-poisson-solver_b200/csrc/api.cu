@@ -215,6 +215,13 @@ int lpgpu_finalize(lpgpu_ctx *c)
   for (cudaStream_t st : c->group_streams) if (st) cudaStreamDestroy(st);
   for (cudaEvent_t ev : c->group_done) if (ev) cudaEventDestroy(ev);
   if (c->group_fork) cudaEventDestroy(c->group_fork);
+  for (lpgpu_ctx *v : c->hchunks) delete v;
+  for (cudaEvent_t ev : c->h_up) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : c->h_down) if (ev) cudaEventDestroy(ev);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  if (c->h_fork) cudaEventDestroy(c->h_fork);
+  if (c->h_join) cudaEventDestroy(c->h_join);
   delete c;
   return LPGPU_OK;
 }
@@ -507,26 +514,35 @@ static void drop_host_tables(lpgpu_ctx *v)
   for (std::vector<double> *x : {&t.G, &t.Gl, &t.C5, &t.Wfwd, &t.Winv, &t.pre_fwd, &t.pre_inv, &t.post_fwd, &t.post_inv, &t.T, &t.M, &t.S, &t.dirichlet, &t.Etab})
     std::vector<double>().swap(*x);
 }
+// a view of cells [b0, b1) of the context: the parent's device arrays offset to the first cell, its own launch counter
+static lpgpu_ctx *make_view(lpgpu_ctx *c, size_t b0, size_t b1)
+{
+  const int N = c->p.N, M = 3 * N / 2, Nv = c->p.Nv;
+  lpgpu_ctx *v = new (std::nothrow) lpgpu_ctx(*c);
+  if (!v) return nullptr;
+  drop_host_tables(v);
+  v->is_view = true; v->ncell = (int)(b1 - b0); v->cap_cells = b1 - b0; v->launches = 0;
+  v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->graph_failed[0] = v->graph_failed[1] = true; v->prof_on = 0; v->prof_ev.clear();
+  v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
+  v->hchunks.clear(); v->hchunk_begin.clear(); v->h_up.clear(); v->h_down.clear();
+  const size_t n3 = (size_t)c->N3 * b0;
+  v->d_U[0] += (size_t)6 * c->sv * b0;
+  v->d_f += n3; v->d_f1 += n3; v->d_Qv += n3; v->d_fhat += 2 * n3; v->d_tmp += 2 * n3;
+  for (int s = 0; s < 4; s++) v->d_q[s] += 2 * n3;
+  if (v->d_mhat) v->d_mhat += 2 * n3;
+  v->d_lam += (size_t)5 * 8 * b0; v->d_cpart += (size_t)5 * N * b0; v->d_B += (size_t)2 * b0 * N * 4 * Nv * Nv;
+  v->d_fc1 += (size_t)20 * N * N * M * b0; v->d_fc2 += (size_t)4 * N * M * M * b0;
+  return v;
+}
 static int make_groups(lpgpu_ctx *c, int G)
 {
-  const int B = c->ncell, N = c->p.N, M = 3 * N / 2, Nv = c->p.Nv;
+  const int B = c->ncell;
   LP_CUDA(cudaEventCreateWithFlags(&c->group_fork, cudaEventDisableTiming));
   for (int g = 0; g < G; g++) {
     const size_t b0 = (size_t)((long long)B * g / G), b1 = (size_t)((long long)B * (g + 1) / G);
-    lpgpu_ctx *v = new (std::nothrow) lpgpu_ctx(*c);
+    lpgpu_ctx *v = make_view(c, b0, b1);
     if (!v) return LPGPU_ENOMEM;
     c->groups.push_back(v);
-    drop_host_tables(v);
-    v->is_view = true; v->ncell = (int)(b1 - b0); v->cap_cells = b1 - b0; v->launches = 0;
-    v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->graph_failed[0] = v->graph_failed[1] = true; v->prof_on = 0; v->prof_ev.clear();
-    v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
-    const size_t n3 = (size_t)c->N3 * b0;
-    v->d_U[0] += (size_t)6 * c->sv * b0;
-    v->d_f += n3; v->d_f1 += n3; v->d_Qv += n3; v->d_fhat += 2 * n3; v->d_tmp += 2 * n3;
-    for (int s = 0; s < 4; s++) v->d_q[s] += 2 * n3;
-    if (v->d_mhat) v->d_mhat += 2 * n3;
-    v->d_lam += (size_t)5 * 8 * b0; v->d_cpart += (size_t)5 * N * b0; v->d_B += (size_t)2 * b0 * N * 4 * Nv * Nv;
-    v->d_fc1 += (size_t)20 * N * N * M * b0; v->d_fc2 += (size_t)4 * N * M * M * b0;
     cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
     if (g > 0) {
       LP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -635,6 +651,92 @@ int lpgpu_step_async(lpgpu_ctx *c, int nsteps)
 {
   LP_ENTER(c);
   return step_enqueue(c, nsteps);
+}
+
+// One timestep on a state that lives in HOST memory, as U does in the reference's time loop (LP_ompi.cpp:662-813): upload,
+// RK3 advection, collision step, download -- pipelined over chunks of x cells instead of three whole-shard phases.
+//   * the chunks of U_in are copied on a copy stream; the layout kernel of a chunk runs as soon as its copy has landed;
+//   * the advection needs the whole shard (the Poisson solve is global), so it starts after the last chunk;
+//   * the collision step of a cell depends on no other cell: the chunks are collided one after the other and chunk k is
+//     on its way back to U_out (second copy stream, the other PCIe direction) while chunk k+1 is collided.
+// At Nx = 512, Nv = 32 a step moves 805 MB each way (~14.6 ms each at 55 GB/s) around 19.4 ms of kernels; the download is
+// hidden but for its last chunk.  U_out may be U_in (no download starts before the last upload has been consumed).
+static int ensure_host_chunks(lpgpu_ctx *c)
+{
+  if (!c->hchunks.empty()) return LPGPU_OK;
+  // Chunk sizes shrink geometrically (each a quarter of what is left; 512 cells: 128, 96, 72, 54, 40, 32, 32, 32, 26).
+  // A chunk's download (28 us per cell at 55 GB/s) must finish within the next chunk's collisions (38 us per cell) or the
+  // copies queue up behind each other -- so a chunk is at least 3/4 of its predecessor -- and what stays exposed at the
+  // end is the download of the LAST chunk, so that one is small; most cells are still collided in large batches (full
+  // waves).  Below ~32 cells a chunk's kernels no longer fill the GPU.
+  static const int knob = getenv("LPGPU_HOST_CHUNK") ? atoi(getenv("LPGPU_HOST_CHUNK")) : 0;   // developer knobs: smallest chunk,
+  static const int div = getenv("LPGPU_HOST_DIV") ? atoi(getenv("LPGPU_HOST_DIV")) : 4;        // fraction of the rest per chunk (0: uniform)
+  const int B = c->ncell, least = knob > 0 ? knob : (B >= 64 ? 32 : 1);
+  std::vector<int> cut(1, 0);
+  for (int rem = B; rem > 0;) {
+    int take = div > 0 ? rem / div : least;
+    if (take < least) take = least;
+    if (2 * rem <= 3 * least) take = rem;
+    if (take > rem) take = rem;
+    cut.push_back(cut.back() + take); rem -= take;
+  }
+  const int n = (int)cut.size() - 1;
+  // the work arrays of the FFT-convolution pipeline are allocated on first use: before the views copy the pointers.  The
+  // chunks run one after the other on one stream, so they all use the parent's arrays from the start (not a slice each:
+  // when memory is short the arrays hold fewer than ncell cells, fc_chunk < ncell)
+  if (c->p.nu > 0.) (void)lp_fc_prepare(c);
+  LP_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  LP_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  LP_CUDA(cudaEventCreateWithFlags(&c->h_fork, cudaEventDisableTiming));
+  LP_CUDA(cudaEventCreateWithFlags(&c->h_join, cudaEventDisableTiming));
+  for (int k = 0; k < n; k++) {
+    lpgpu_ctx *v = make_view(c, (size_t)cut[k], (size_t)cut[k + 1]);
+    if (!v) return LPGPU_ENOMEM;
+    v->d_fc1 = c->d_fc1; v->d_fc2 = c->d_fc2;
+    c->hchunks.push_back(v); c->hchunk_begin.push_back(cut[k]);
+    cudaEvent_t a = nullptr, b = nullptr;
+    LP_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    LP_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    c->h_up.push_back(a); c->h_down.push_back(b);
+  }
+  return LPGPU_OK;
+}
+int lpgpu_step_host(lpgpu_ctx *c, const double *U_in, double *U_out)
+{
+  LP_ENTER(c);
+  if (!U_in || !U_out) { lp_set_error("lpgpu_step_host: null U"); return LPGPU_EINVAL; }
+  LP_TRY(ensure_host_chunks(c));
+  const size_t plane = (size_t)6 * c->sv;
+  const int n = (int)c->hchunks.size();
+  // the copy stream starts behind whatever the context's stream still has to do with the staging buffer
+  LP_CUDA(cudaEventRecord(c->h_fork, c->stream));
+  LP_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->h_fork, 0));
+  LP_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->h_fork, 0));
+  for (int k = 0; k < n; k++) {
+    lpgpu_ctx *v = c->hchunks[k];
+    const size_t b0 = (size_t)c->hchunk_begin[k];
+    v->stream = c->stream; v->have_mhat = c->have_mhat;
+    LP_CUDA(cudaMemcpyAsync(c->d_aos + plane * b0, U_in + plane * b0, plane * v->ncell * sizeof(double), cudaMemcpyHostToDevice, c->h2d_stream));
+    LP_CUDA(cudaEventRecord(c->h_up[k], c->h2d_stream));
+    LP_CUDA(cudaStreamWaitEvent(c->stream, c->h_up[k], 0));
+    LP_TRY(lp_launch_aos_to_planes(v, c->d_aos + plane * b0, v->d_U[0]));
+    c->launches += v->launches; v->launches = 0;
+  }
+  if (!c->p.homogeneous) LP_TRY(advect_rk3_async(c));
+  for (int k = 0; k < n; k++) {
+    lpgpu_ctx *v = c->hchunks[k];
+    const size_t b0 = (size_t)c->hchunk_begin[k];
+    if (c->p.nu > 0.) LP_TRY(collide_cells(v));
+    LP_TRY(lp_launch_planes_to_aos(v, v->d_U[0], c->d_aos + plane * b0));
+    c->launches += v->launches; v->launches = 0;
+    LP_CUDA(cudaEventRecord(c->h_down[k], c->stream));
+    LP_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->h_down[k], 0));
+    LP_CUDA(cudaMemcpyAsync(U_out + plane * b0, c->d_aos + plane * b0, plane * v->ncell * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
+  }
+  LP_CUDA(cudaEventRecord(c->h_join, c->d2h_stream));
+  LP_CUDA(cudaStreamWaitEvent(c->stream, c->h_join, 0));
+  LP_CUDA(cudaStreamSynchronize(c->stream));
+  return peer_check(c);
 }
 
 int lpgpu_set_maxwellian(lpgpu_ctx *c)
@@ -823,6 +925,7 @@ int lpgpu_diagnostics_begin(lpgpu_ctx *c)
     if (!v) return LPGPU_ENOMEM;
     drop_host_tables(v);
     v->is_view = true; v->stream = c->diag_stream; v->launches = 0; v->groups.clear(); v->group_streams.clear(); v->group_done.clear();
+    v->hchunks.clear(); v->hchunk_begin.clear(); v->h_up.clear(); v->h_down.clear();
     v->gexec[0] = v->gexec[1] = nullptr; v->gstream = nullptr; v->prof_on = 0; v->prof_ev.clear(); v->diag_view = nullptr;
     double *q = c->d_diag_scratch;
     v->d_mom = q; q += 8; v->d_lam = q; q += 8;

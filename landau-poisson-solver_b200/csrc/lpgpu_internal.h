@@ -93,6 +93,12 @@ struct lpgpu_ctx {
   std::vector<cudaStream_t> group_streams;
   std::vector<cudaEvent_t> group_done;
   cudaEvent_t group_fork;
+  // lpgpu_step_host: chunks of cells (views), the two copy streams, per-chunk "upload landed" / "ready to download" events
+  std::vector<lpgpu_ctx *> hchunks;
+  std::vector<int> hchunk_begin;
+  cudaStream_t h2d_stream, d2h_stream;
+  cudaEvent_t h_fork, h_join;
+  std::vector<cudaEvent_t> h_up, h_down;
   bool is_view;
   // ---- peer-memory exchange of the sharded advection (one process per GPU on one node, CUDA IPC): every rank writes
   //      its densities into all ranks' mailboxes and its boundary planes into its neighbours' halo planes, then raises a

@@ -40,7 +40,7 @@ class Exchange(C.Structure):
 EXPORTS = [
     "lpgpu_last_error", "lpgpu_device_count", "lpgpu_init", "lpgpu_finalize", "lpgpu_set_stream",
     "lpgpu_synchronize", "lpgpu_launch_count", "lpgpu_upload_U", "lpgpu_download_U",
-    "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_step_async", "lpgpu_set_maxwellian",
+    "lpgpu_upload_U_async", "lpgpu_download_U_async", "lpgpu_step_async", "lpgpu_step_host", "lpgpu_set_maxwellian",
     "lpgpu_advect_rk3", "lpgpu_collide_step", "lpgpu_collide_step_async", "lpgpu_step", "lpgpu_advect_exchange_info",
     "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_setInit_spectral", "lpgpu_fft3D", "lpgpu_FS",
     "lpgpu_ComputeQ", "lpgpu_conserveMoments", "lpgpu_sample_device", "lpgpu_eval_device",
@@ -75,6 +75,7 @@ def load_library():
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
     for name in ("lpgpu_step", "lpgpu_step_async", "lpgpu_advect_reduce", "lpgpu_advect_apply", "lpgpu_eval_device"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+    L.lpgpu_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.lpgpu_advect_exchange_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(Exchange)]
     for name in ("lpgpu_fft3D", "lpgpu_FS", "lpgpu_ComputeQ"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -187,6 +188,18 @@ class LPGpu:
 
     def step(self, nsteps=1, wait=True):
         self._check((self.L.lpgpu_step if wait else self.L.lpgpu_step_async)(self.h, int(nsteps)))
+
+    def step_host(self, U_in, U_out=None):
+        """One timestep on a host-resident state (the reference's time loop keeps U on the host): upload, RK3, collision
+        step and download pipelined over chunks of cells.  U_out defaults to a new array; it may be U_in.  Page-locked
+        buffers make the copies asynchronous."""
+        assert isinstance(U_in, np.ndarray) and U_in.dtype == np.float64 and U_in.flags.c_contiguous, "U_in: contiguous float64 array"
+        assert U_in.size == self.ncell * self.sv * 6, "U must hold this shard: x_count*Nv^3*6 doubles"
+        if U_out is None:
+            U_out = np.empty(self.ncell * self.sv * 6)
+        assert isinstance(U_out, np.ndarray) and U_out.dtype == np.float64 and U_out.flags.c_contiguous and U_out.size == U_in.size
+        self._check(self.L.lpgpu_step_host(self.h, _ptr(U_in), _ptr(U_out)))
+        return U_out
 
     def exchange_info(self, stage):
         ex = Exchange()

@@ -401,6 +401,15 @@ class ShardedSolver:
             main.wait_stream(self.halo_stream)
             self.g.advect_apply(stage)
 
+    def step_host(self, U_in, U_out=None):
+        """One timestep on this rank's shard held in host memory (upload, RK3, collisions, download pipelined over chunks
+        of cells inside the library).  NCCL-exchange runs fall back to the three calls: their advection is driven from here."""
+        if self.world == 1 or self.homogeneous or self.exchange == "peer":
+            return self.g.step_host(U_in, U_out)
+        self.upload(U_in)
+        self.step(1)
+        return self.download(U_out)
+
     def step(self, nsteps=1, wait=True):
         """nsteps passes of the while(t<nT) body (LP_ompi.cpp:662-813) without diagnostics.  wait=False only
         enqueues (pipelined callers: synchronize() before touching host buffers)."""

@@ -240,6 +240,35 @@ def test_pipelined_contexts_match_synchronous_calls(pkg):
         ctx[k].close()
 
 
+@pytest.mark.parametrize("cfg", [SMALL, dict(SMALL, Nx=5), dict(Nx=1, Nv=8, N=8, Lv=5.25, Lx=4 * np.pi, nu=0.05, dt=0.01, homogeneous=True)])
+def test_step_on_host_state_matches_upload_step_download(pkg, cfg):
+    """lpgpu_step_host (one call per timestep, state in host memory, chunks of cells pipelined through upload / RK3 /
+    collisions / download) against the three whole-shard calls and against the oracle; pageable and page-locked buffers,
+    out of place and in place, several steps in a row (each step's input is the previous step's output)."""
+    import torch
+    ora = PortOracle(**cfg)
+    U = ora.SetInit_4H_Homo() if cfg.get("homogeneous") else _perturbed(ora, seed=3)
+    g = pkg.LPGpu(**cfg)
+    g.upload_U(U)
+    want = [U]
+    for _ in range(3):
+        g.step(1)
+        want.append(g.download_U())
+    assert relerr(want[1] - U, ora.step(U) - U) < TOL_DU
+    # pageable buffers, out of place
+    got = g.step_host(U.copy())
+    assert relerr(got - U, want[1] - U) < 1e-12
+    # page-locked buffers, in place, three steps
+    h = torch.from_numpy(U.copy()).pin_memory()
+    for k in range(3):
+        out = g.step_host(h.numpy(), h.numpy())
+        assert out is not None
+        assert relerr(h.numpy() - want[k], want[k + 1] - want[k]) < 1e-11
+    # the state left on the device is the one returned
+    assert np.array_equal(g.download_U(), h.numpy())
+    g.close()
+
+
 def test_entropy_and_negativity_diagnostics(small, pkg):
     """computeEntropy / FindNegVals / computeKiEratio (LP_ompi.cpp:819,829,846) on the GPU."""
     ora, g = small

@@ -40,7 +40,7 @@ def _peer_worker(rank, world, port, q):
     s.upload(U0[rank * n:(rank + 1) * n])
     s.step(2)                                   # eager, captured
     s.step(2)                                   # replays
-    mine = s.download()
+    mine = s.step_host(s.download())            # a fifth step on the host-resident shard (lpgpu_step_host: peers inside)
     s.close()                                   # raises if a wait for the peer ever timed out
     q.put((rank, mine))
     dist.barrier()
@@ -73,7 +73,7 @@ def test_peer_exchange_between_two_processes_on_one_gpu():
     U0 = solver.set_init_ld(cfg["Nx"], cfg["Nv"], cfg["Lv"], cfg["Lx"], 0.5, np.pi / 2, True)
     one = solver.ShardedSolver(device=0, **cfg)
     one.upload(U0)
-    one.step(4)
+    one.step(5)
     want = one.download()
     one.close()
     got = np.concatenate([res[0], res[1]])
