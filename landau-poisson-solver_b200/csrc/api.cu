@@ -222,6 +222,7 @@ int lpgpu_finalize(lpgpu_ctx *c)
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->h_fork) cudaEventDestroy(c->h_fork);
   if (c->h_join) cudaEventDestroy(c->h_join);
+  if (c->h_trace0) cudaEventDestroy(c->h_trace0);
   delete c;
   return LPGPU_OK;
 }
@@ -710,6 +711,7 @@ int lpgpu_step_host(lpgpu_ctx *c, const double *U_in, double *U_out)
   const int n = (int)c->hchunks.size();
   // the copy stream starts behind whatever the context's stream still has to do with the staging buffer
   LP_CUDA(cudaEventRecord(c->h_fork, c->stream));
+  if (getenv("LPGPU_HOST_TRACE")) { if (!c->h_trace0) LP_CUDA(cudaEventCreate(&c->h_trace0)); LP_CUDA(cudaEventRecord(c->h_trace0, c->stream)); }
   LP_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->h_fork, 0));
   LP_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->h_fork, 0));
   for (int k = 0; k < n; k++) {
@@ -722,7 +724,12 @@ int lpgpu_step_host(lpgpu_ctx *c, const double *U_in, double *U_out)
     LP_TRY(lp_launch_aos_to_planes(v, c->d_aos + plane * b0, v->d_U[0]));
     c->launches += v->launches; v->launches = 0;
   }
+  static const bool trace = getenv("LPGPU_HOST_TRACE") != nullptr;   // developer knob: print where the time of a call goes
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  mark(c->stream);                                     // [1] last chunk re-laid (tev[0] is recorded below, at the fork)
   if (!c->p.homogeneous) LP_TRY(advect_rk3_async(c));
+  mark(c->stream);                                     // [2] advection done
   for (int k = 0; k < n; k++) {
     lpgpu_ctx *v = c->hchunks[k];
     const size_t b0 = (size_t)c->hchunk_begin[k];
@@ -733,9 +740,18 @@ int lpgpu_step_host(lpgpu_ctx *c, const double *U_in, double *U_out)
     LP_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->h_down[k], 0));
     LP_CUDA(cudaMemcpyAsync(U_out + plane * b0, c->d_aos + plane * b0, plane * v->ncell * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
   }
+  mark(c->stream);                                     // [3] last chunk collided and re-laid
   LP_CUDA(cudaEventRecord(c->h_join, c->d2h_stream));
   LP_CUDA(cudaStreamWaitEvent(c->stream, c->h_join, 0));
+  mark(c->stream);                                     // [4] last download done
   LP_CUDA(cudaStreamSynchronize(c->stream));
+  if (trace) {
+    float a = 0, b = 0, d = 0, e = 0;
+    cudaEventElapsedTime(&a, c->h_trace0, tev[0]); cudaEventElapsedTime(&b, tev[0], tev[1]);
+    cudaEventElapsedTime(&d, tev[1], tev[2]); cudaEventElapsedTime(&e, tev[2], tev[3]);
+    fprintf(stderr, "lpgpu_step_host: upload + layout %.2f ms, advection %.2f ms, collisions (%d chunks) %.2f ms, download tail %.2f ms\n", a, b, n, d, e);
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+  }
   return peer_check(c);
 }
 

@@ -97,7 +97,7 @@ struct lpgpu_ctx {
   std::vector<lpgpu_ctx *> hchunks;
   std::vector<int> hchunk_begin;
   cudaStream_t h2d_stream, d2h_stream;
-  cudaEvent_t h_fork, h_join;
+  cudaEvent_t h_fork, h_join, h_trace0;
   std::vector<cudaEvent_t> h_up, h_down;
   bool is_view;
   // ---- peer-memory exchange of the sharded advection (one process per GPU on one node, CUDA IPC): every rank writes
