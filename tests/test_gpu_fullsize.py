@@ -189,9 +189,16 @@ def test_many_cells_chunked_ComputeQ_equals_small_context(pkg, monkeypatch):
     g.collide_step()                                           # eager
     g.collide_step()                                           # captured into a graph
     got = g.download_U()
-    g.close()
     for k in range(5):
         assert np.array_equal(got[k * want.size:(k + 1) * want.size], want), k
+    # the host-resident timestep on the same memory-limited context: its chunks of cells share the one set of work arrays
+    U40 = np.tile(U8, 5)
+    g.upload_U(U40)
+    g.step(1)
+    ref = g.download_U()
+    out = g.step_host(U40.copy())
+    g.close()
+    assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref - U40))
 
 
 def test_full_size_many_cells_equal_the_32_cell_shard(pkg):
