@@ -239,6 +239,43 @@ LP_HD double2 inv_combine(double2 t0, double2 t1, double2 t2, int s)
   return make_double2(m.x - c * D.y, m.y + c * D.x);
 }
 
+// ---- line halves: two threads per M-point line, H = M/2 = 3L/2 outputs each (F2Q: the x stage of a three-warp CTA is then
+// exactly N x 3 / ... = 2M tasks, and a line's 2L inputs are read twice instead of three times)
+// forward: y[q] = X[2q + h], q < H, from the 2L non-zero inputs:  b[n] = (x[n] + (-1)^h x[n + H]) w_M^(h n)  (x[n + H] exists
+// for n < L/2), X[2q + h] = sum_{n < H} b[n] exp(-2 pi i n q / H)
+template <int L>
+LP_HD void fwd_half(const double2 (&a0)[L], const double2 (&a1)[L], int h, double2 (&y)[3 * L / 2])
+{
+  constexpr int M = 3 * L, H = M / 2, P = L / 2;      // pairs: n < P  (n + H = L + (n + P))
+  if (h == 0) {
+    #pragma unroll
+    for (int n = 0; n < P; n++) y[n] = cadd(a0[n], a1[n + P]);
+    #pragma unroll
+    for (int n = P; n < L; n++) y[n] = a0[n];
+    #pragma unroll
+    for (int n = L; n < H; n++) y[n] = a1[n - L];
+  } else {
+    #pragma unroll
+    for (int n = 0; n < P; n++) y[n] = mul_tw<M, -1>(csub(a0[n], a1[n + P]), n);
+    #pragma unroll
+    for (int n = P; n < L; n++) y[n] = mul_tw<M, -1>(a0[n], n);
+    #pragma unroll
+    for (int n = L; n < H; n++) y[n] = mul_tw<M, -1>(a1[n - L], n);
+  }
+  fftN<H, -1, M>(y);
+}
+// inverse, in place: z[q] = Z[2q + h]  ->  t_h[n] = conj(w_M^(h n)) IFFT_H(z)[n];  x[n] = t_0[n] + t_1[n], x[n + H] = t_0[n] - t_1[n]
+template <int L>
+LP_HD void inv_half(double2 (&z)[3 * L / 2], int h)
+{
+  constexpr int M = 3 * L, H = M / 2;
+  fftN<H, +1, M>(z);
+  if (h == 1) {
+    #pragma unroll
+    for (int n = 0; n < H; n++) z[n] = mul_tw<M, +1>(z[n], n);
+  }
+}
+
 // 16-byte asynchronous global -> shared copy (plain copy under the emulator)
 LP_HD void cp16(double2 *dst_smem, const double2 *src)
 {
@@ -445,6 +482,94 @@ struct F2 {
       const int kp = ry * L + q;
       c[q] = inv_combine(T[l * PY + kp], T[(L + l) * PY + kp], T[(2 * L + l) * PY + kp], s);
     }
+    inv_third<L>(c, ry);
+    #pragma unroll
+    for (int lp = 0; lp < L; lp++) T2[(ry * L + lp) * PN + xo] = c[lp];
+  }
+  static LP_HD void store(int tid, int cell, int kz, const double2 *T2, double2 *C)
+  {
+    double2 *o = C + ((long long)cell * M + kz) * (N * N);
+    for (int idx = tid; idx < N * N; idx += NT) {
+      const int xo = idx / N, yo = idx % N, lp = yo % L, s = yo / L + 1;
+      o[idx] = inv_combine(T2[lp * PN + xo], T2[(L + lp) * PN + xo], T2[(2 * L + lp) * PN + xo], s);
+    }
+  }
+};
+
+// =========================================================================================================
+// F2Q: the same plane as F2 on a CTA of 3N threads (three warps at L = 16), four CTAs per SM.  One array at a time: y stage
+// of u_p (thirds, thread = (r, x)), x stage of u_p (halves, thread = (h, pos): the transform stays in registers), y stage
+// of v_p, x stage of v_p, multiply-accumulate.  shared: IN[N][N] (one plane) | Y[N][PY] (one array); T and T2 alias both.
+//   Y[x][r L + q] holds y' = 3q + r (as in F2); pos = r L + q is the x stage's line index
+template <int L>
+struct F2Q {
+  static constexpr int N = 2 * L, M = 3 * L, H = M / 2, PY = M + 1, PN = N + 1, NT = 3 * N;
+  static constexpr int IN_C2 = N * N, Y_C2 = N * PY;
+  static_assert(2 * M == NT, "x-stage tasks (two halves of M lines) = threads");
+  static_assert(2 * H * PY <= IN_C2 + Y_C2, "T (inverse-x halves) must fit the two buffers");
+  static_assert(3 * L * PN <= IN_C2 + Y_C2, "T2 must fit the two buffers");
+  static LP_HD const double2 *plane(const double2 *Z, int cell, int p, int arr, int kz)
+  {
+    return Z + (((long long)cell * 10 + (arr ? 7 + zpow_of(p) : p)) * M + kz) * (N * N);
+  }
+  // y stage of one array (arr = 0: u_p, 1: the v source of p, weighted by E(y)^yp before and -E(x)^xp after the transform)
+  static LP_HD void ystage1(int tid, int p, int arr, const double2 *IN, const double *sE, double2 *Y)
+  {
+    const int x = tid % N, r = tid / N;
+    const double2 *src = IN + x;
+    double2 a0[L], a1[L], yv[L];
+    #pragma unroll
+    for (int l = 0; l < L; l++) { a0[l] = src[l * N]; a1[l] = src[(l + L) * N]; }
+    const int yp = ypow_of(p);
+    if (arr == 1 && yp) {
+      #pragma unroll
+      for (int l = 0; l < L; l++) {
+        const double e0 = ipow(sE[l], yp), e1 = ipow(sE[l + L], yp);
+        a0[l].x *= e0; a0[l].y *= e0; a1[l].x *= e1; a1[l].y *= e1;
+      }
+    }
+    fwd_third<L>(a0, a1, r, yv);
+    if (arr == 1 && p > 0) {
+      const double sx = -ipow(sE[x], xpow_of(p));
+      #pragma unroll
+      for (int q = 0; q < L; q++) { yv[q].x *= sx; yv[q].y *= sx; }
+    }
+    double2 *dst = Y + x * PY + r * L;
+    #pragma unroll
+    for (int q = 0; q < L; q++) dst[q] = yv[q];
+  }
+  // x stage of the array in Y: out[q] = transform at x' = 2q + h of line pos
+  static LP_HD void xhalf(int tid, const double2 *Y, double2 (&out)[H])
+  {
+    const int h = tid / M, pos = tid % M;
+    double2 a0[L], a1[L];
+    #pragma unroll
+    for (int l = 0; l < L; l++) { a0[l] = Y[l * PY + pos]; a1[l] = Y[(l + L) * PY + pos]; }
+    fwd_half<L>(a0, a1, h, out);
+  }
+  // inverse x of the accumulated products: T[(h H + n)][pos]  (T aliases IN | Y: call after a barrier)
+  static LP_HD void xinverse(int tid, double2 (&acc)[H], double2 *T)
+  {
+    const int h = tid / M, pos = tid % M;
+    inv_half<L>(acc, h);
+    #pragma unroll
+    for (int n = 0; n < H; n++) T[(h * H + n) * PY + pos] = acc[n];
+  }
+  // inverse y of the N kept x rows (x index xo + L of M): thread = (ry, xo).  The two halves are combined on the way in;
+  // the results go to T2, which aliases T: every thread loads, barrier, every thread stores
+  static LP_HD void yinverse_load(int tid, const double2 *T, double2 (&c)[L])
+  {
+    const int xo = tid % N, ry = tid / N, n = xo + L, np = n < H ? n : n - H;
+    #pragma unroll
+    for (int q = 0; q < L; q++) {
+      const int kp = ry * L + q;
+      const double2 t0 = T[np * PY + kp], t1 = T[(H + np) * PY + kp];
+      c[q] = n < H ? cadd(t0, t1) : csub(t0, t1);
+    }
+  }
+  static LP_HD void yinverse_store(int tid, double2 (&c)[L], double2 *T2)
+  {
+    const int xo = tid % N, ry = tid / N;
     inv_third<L>(c, ry);
     #pragma unroll
     for (int lp = 0; lp < L; lp++) T2[(ry * L + lp) * PN + xo] = c[lp];

@@ -521,6 +521,120 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
   __syncthreads();
   K::store(tid, cell, kz, IN, C);
 }
+// ---------------------------------------------------------------------------------------------------------
+// k_fc3_f2q: the same plane on THREE warps, four CTAs per SM (fc3::F2Q).  Inside one CTA the warps load together and
+// compute together, so a CTA keeps the FP64 pipe busy 36 % and the shared-memory pipe 38 % of its time and two co-resident
+// CTAs overlap those only as two independent streams do (profiles/r02_f2_kernels.md); four streams overlap more.  What
+// makes four fit: one array at a time (41 KB of shared memory: one input plane + one Y array; the next plane is fetched
+// into the input buffer while the x stage runs out of Y), the x stage as two halves per line (96 tasks = 96 threads, a
+// line's inputs read twice instead of three times), the u transform kept in registers across the v array's y stage
+// instead of parked, and the 48 x 48 accumulators in 96 of the CTA's 128 TMEM columns (4 x 128 = all 512).
+__global__ void __launch_bounds__(96, 4) k_fc3_f2q(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
+{
+  constexpr int L = 16;
+  typedef fc3::F2Q<L> K;
+  extern __shared__ double2 smf[];
+  __shared__ unsigned s_tmem;
+  __shared__ __align__(8) unsigned long long s_bar;
+  double2 *IN = smf, *Y = IN + K::IN_C2;
+  double *sE = reinterpret_cast<double *>(Y + K::Y_C2);
+  const int kz = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tmem);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(dst), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  constexpr unsigned PLANE_BYTES = K::N * K::N * sizeof(double2);
+  auto issue_plane = [&](int p, int arr) {
+    mbar_expect_tx(&s_bar, PLANE_BYTES);
+    bulk_load(IN, K::plane(Z, cell, p, arr, kz), PLANE_BYTES, &s_bar);
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    issue_plane(0, 0);
+  }
+  for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const unsigned tbase = s_tmem;
+  const unsigned tacc = tbase + ((unsigned)(warp * 32) << 16);
+  // fourteen array passes, k = 2p + arr (u_p, then the v source of p): ONE copy of the y- and x-stage code (the two-copy
+  // version was 4096 instructions and lost 10 % of its issue slots to instruction fetch with four CTAs in different phases)
+  // the u transform waits for the v transform in registers, except its last eight values: those go to the 32 TMEM columns
+  // the accumulators leave free (with all 24 in registers the v array's y stage spilled most of them to local memory)
+  // ... and eight more to a strip of shared memory of their own (12 KB: four CTAs still fit an SM)
+  constexpr int UR = K::H - 16;
+  double2 uh[UR];
+  double2 *upark = reinterpret_cast<double2 *>(sE + K::N) + tid;       // [8][NT]
+  #pragma unroll 1
+  for (int k = 0; k < 14; k++) {
+    const int p = k >> 1, arr = k & 1;
+    mbar_wait(&s_bar, (unsigned)k & 1u);    // plane k landed
+    K::ystage1(tid, p, arr, IN, sE, Y);
+    __syncthreads();                        // Y complete, IN consumed
+    if (k + 1 < 14 && tid == 0) { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); issue_plane((k + 1) >> 1, (k + 1) & 1); }   // arrives while the x stage runs
+    double2 t[K::H];
+    K::xhalf(tid, Y, t);
+    __syncwarp();                           // the warp holding both h diverged in the pre-stage; tcgen05.* is warp-wide
+    if (arr == 0) {
+      #pragma unroll
+      for (int q = 0; q < UR; q++) uh[q] = t[q];
+      #pragma unroll
+      for (int q = 0; q < 8; q++) upark[q * K::NT] = t[UR + q];
+      { double2 t4[4] = {t[UR + 8], t[UR + 9], t[UR + 10], t[UR + 11]}; tmem_st4c(tacc + 96, t4); }
+      { double2 t4[4] = {t[UR + 12], t[UR + 13], t[UR + 14], t[UR + 15]}; tmem_st4c(tacc + 112, t4); }
+      tmem_wait_st();
+    } else {
+      #pragma unroll
+      for (int c4 = 0; c4 < K::H / 4; c4++) {
+        double2 a[4];
+        if (p > 0) tmem_ld4c(tacc + 16 * c4, a);
+        else { a[0] = a[1] = a[2] = a[3] = make_double2(0., 0.); }
+        double2 u4[4];
+        if (4 * c4 >= UR + 8) tmem_ld4c(tacc + 96 + 4 * (4 * c4 - UR - 8), u4);
+        else if (4 * c4 >= UR) {
+          #pragma unroll
+          for (int i = 0; i < 4; i++) u4[i] = upark[(4 * c4 - UR + i) * K::NT];
+        }
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int q = 4 * c4 + i;
+          const double2 uu = 4 * c4 >= UR ? u4[i] : uh[q < UR ? q : 0];
+          a[i].x += uu.x * t[q].x - uu.y * t[q].y;
+          a[i].y += uu.x * t[q].y + uu.y * t[q].x;
+        }
+        tmem_st4c(tacc + 16 * c4, a);
+      }
+      tmem_wait_st();
+    }
+    __syncthreads();                        // every read of Y is done before the next y stage writes it
+  }
+  {
+    double2 acc[K::H];
+    #pragma unroll
+    for (int c4 = 0; c4 < K::H / 4; c4++) {
+      double2 a[4];
+      tmem_ld4c(tacc + 16 * c4, a);
+      #pragma unroll
+      for (int i = 0; i < 4; i++) acc[4 * c4 + i] = a[i];
+    }
+    K::xinverse(tid, acc, smf);             // T aliases IN | Y: no copy is in flight, every reader passed the barrier above
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"(128u) : "memory");
+  {
+    double2 c[L];
+    K::yinverse_load(tid, smf, c);
+    __syncthreads();                        // T2 aliases T
+    K::yinverse_store(tid, c, smf);
+  }
+  __syncthreads();
+  K::store(tid, cell, kz, smf, C);
+}
 // part (nullable): per (cell, xo) partial dot products of the conservation rows with the stored spectrum,
 // [cell][xo][5]; folded in a fixed order by the kernels that apply the correction (collision.cu)
 template <int L, int NSPLIT>
@@ -582,7 +696,16 @@ int launch_fc3(lpgpu_ctx *c, const double2 *fh, double2 *Z, double2 *C, double2 
   const int nsplit = (nb * M * 2 <= 148) ? 3 : 1;
   const long long split_stride = (long long)nb * M * N * N;
   const dim3 g2(M, nb, nsplit);
-  if (L == 16 && !no_tmem && nsplit == 3) k_fc3_f2_tmem<true, 3><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
+  static const bool quarter = getenv("LPGPU_F2_SIX_WARPS") == nullptr;   // developer knob: LPGPU_F2_SIX_WARPS=1 runs the round-1 kernel (six warps, two CTAs per SM)
+  if (L == 16 && !no_tmem && nsplit == 1 && quarter) {
+    typedef fc3::F2Q<16> KQ;
+    static const int padq = getenv("LPGPU_F2Q_PAD_KB") ? atoi(getenv("LPGPU_F2Q_PAD_KB")) : 0;   // experiment: fewer CTAs per SM
+    const size_t smemq = (size_t)(KQ::IN_C2 + KQ::Y_C2 + 8 * KQ::NT) * sizeof(double2) + KQ::N * sizeof(double) + (size_t)padq * 1024;
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f2q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemq));
+    LP_CUDA(cudaFuncSetAttribute(k_fc3_f2q, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    k_fc3_f2q<<<dim3(M, nb), KQ::NT, smemq, c->stream>>>(Z, E, C);
+  }
+  else if (L == 16 && !no_tmem && nsplit == 3) k_fc3_f2_tmem<true, 3><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else if (L == 16 && !no_tmem && park_uh) k_fc3_f2_tmem<true, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else if (L == 16 && !no_tmem) k_fc3_f2_tmem<false, 1><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);
   else k_fc3_f2<L><<<g2, K2::NT, smem2, c->stream>>>(Z, E, C, split_stride);

@@ -9,7 +9,7 @@
 
 // mhat (nullable): the linear operator Q(f, M) -- the u arrays come from the stored Maxwellian transform
 template <int L>
-static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr)
+static void emulate(int B, const double2 *fhat, const double *G7, const double *E, double2 *q, int nsplit, const double2 *mhat = nullptr, bool quarter = false)
 {
   using namespace fc3;
   constexpr int N = 2 * L, M = 3 * L;
@@ -32,7 +32,39 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
         for (int t = 0; t < K::NT; t++) K::lines(t, cell, y, Gs.data(), N * N, FS.data(), sE.data(), Z.data(), 0, 5, mhat ? FM.data() : nullptr);
       }
   }
-  {
+  if (quarter) {
+    // F2Q (k_fc3_f2q): one array at a time on 3N threads; IN | Y are one contiguous region that T and T2 alias
+    typedef F2Q<L> K;
+    std::vector<double2> buf(K::IN_C2 + K::Y_C2);
+    double2 *IN = buf.data(), *Y = IN + K::IN_C2;
+    std::vector<double> sE(E, E + N);
+    struct Half { double2 a[K::H]; };
+    struct Line { double2 a[L]; };
+    std::vector<Half> acc(K::NT), uh(K::NT), vh(K::NT);
+    std::vector<Line> cl(K::NT);
+    for (int cell = 0; cell < B; cell++)
+      for (int kz = 0; kz < M; kz++) {
+        std::memset(acc.data(), 0, sizeof(Half) * acc.size());
+        for (int p = 0; p < 7; p++) {
+          std::memcpy(IN, K::plane(Z.data(), cell, p, 0, kz), sizeof(double2) * N * N);       // the bulk copy of u_p
+          for (int t = 0; t < K::NT; t++) K::ystage1(t, p, 0, IN, sE.data(), Y);
+          std::memcpy(IN, K::plane(Z.data(), cell, p, 1, kz), sizeof(double2) * N * N);       // ... of the v source, issued here
+          for (int t = 0; t < K::NT; t++) K::xhalf(t, Y, uh[t].a);
+          for (int t = 0; t < K::NT; t++) K::ystage1(t, p, 1, IN, sE.data(), Y);
+          for (int t = 0; t < K::NT; t++) {
+            K::xhalf(t, Y, vh[t].a);
+            for (int k = 0; k < K::H; k++) {
+              acc[t].a[k].x += uh[t].a[k].x * vh[t].a[k].x - uh[t].a[k].y * vh[t].a[k].y;
+              acc[t].a[k].y += uh[t].a[k].x * vh[t].a[k].y + uh[t].a[k].y * vh[t].a[k].x;
+            }
+          }
+        }
+        for (int t = 0; t < K::NT; t++) K::xinverse(t, acc[t].a, buf.data());
+        for (int t = 0; t < K::NT; t++) K::yinverse_load(t, buf.data(), cl[t].a);
+        for (int t = 0; t < K::NT; t++) K::yinverse_store(t, cl[t].a, buf.data());
+        for (int t = 0; t < K::NT; t++) K::store(t, cell, kz, buf.data(), C.data());
+      }
+  } else {
     typedef F2<L> K;
     std::vector<double2> IN(K::IN_C2), Y(K::Y_C2);
     std::vector<double> sE(E, E + N);
@@ -99,6 +131,19 @@ extern "C" int fc3_emulate_linear(int N, int B, const double *fhat, const double
 extern "C" int fc3_emulate(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
 {
   return fc3_emulate_split(N, B, fhat, G7, E, q, 1);
+}
+// the four-CTAs-per-SM variant of the y/x stage (F2Q): halves along x, one array at a time
+extern "C" int fc3_emulate_quarter(int N, int B, const double *fhat, const double *G7, const double *E, double *q)
+{
+  const double2 *f = reinterpret_cast<const double2 *>(fhat);
+  double2 *o = reinterpret_cast<double2 *>(q);
+  switch (N) {
+    case 8: emulate<4>(B, f, G7, E, o, 1, nullptr, true); return 0;
+    case 16: emulate<8>(B, f, G7, E, o, 1, nullptr, true); return 0;
+    case 24: emulate<12>(B, f, G7, E, o, 1, nullptr, true); return 0;
+    case 32: emulate<16>(B, f, G7, E, o, 1, nullptr, true); return 0;
+  }
+  return 1;
 }
 
 static int direct_sum(int N, int B, const double *fhat, const double *mhat, const double *G7, const double *E, double *q);

@@ -37,6 +37,20 @@ def test_pipeline_matches_direct_sum(emul, N, B):
     assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("N,B", [(8, 2), (16, 1), (24, 1), (32, 1)])
+def test_quarter_variant_matches_direct_sum(emul, N, B):
+    """F2Q (k_fc3_f2q): the y/x stage on three-warp CTAs -- one array at a time, the x stage as two halves per line
+    (M/2-point transforms), the inverse x combined from the halves on the way into the inverse y."""
+    rng = np.random.default_rng(50 + N)
+    fh = rng.standard_normal((B, N ** 3, 2))
+    G = rng.standard_normal((N ** 3, 7))
+    E = (np.arange(N) - N / 2) * 0.37
+    got, want = np.zeros_like(fh), np.zeros_like(fh)
+    assert emul.fc3_emulate_quarter(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), got.ctypes.data_as(P)) == 0
+    assert emul.fc3_direct(N, B, fh.ctypes.data_as(P), G.ctypes.data_as(P), E.ctypes.data_as(P), want.ctypes.data_as(P)) == 0
+    assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
+
+
 def test_product_split_over_three_ctas(emul):
     """F2 may split its seven products over three CTAs per (cell, kz) when few cells are in flight; F3 sums the parts."""
     N, B = 16, 1
