@@ -538,6 +538,15 @@ struct F2Q {
     #pragma unroll
     for (int q = 0; q < L; q++) dst[q] = yv[q];
   }
+  // v_1 = -E(x)^2 fhat from the y transform of v_0 = fhat that is in Y: every thread rescales the third it wrote
+  static LP_HD void rescale_v1(int tid, const double *sE, double2 *Y)
+  {
+    const int x = tid % N, r = tid / N;
+    const double sx = -ipow(sE[x], 2);
+    double2 *dst = Y + x * PY + r * L;
+    #pragma unroll
+    for (int q = 0; q < L; q++) { const double2 v = dst[q]; dst[q] = make_double2(v.x * sx, v.y * sx); }
+  }
   // x stage of the array in Y: out[q] = transform at x' = 2q + h of line pos
   static LP_HD void xhalf(int tid, const double2 *Y, double2 (&out)[H])
   {

@@ -545,15 +545,23 @@ __global__ void __launch_bounds__(96, 4) k_fc3_f2q(const double2 *__restrict__ Z
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   constexpr unsigned PLANE_BYTES = K::N * K::N * sizeof(double2);
-  auto issue_plane = [&](int p, int arr) {
+  // The thirteen planes a CTA reads, in order: u_0, v-source of 0, u_1, then (u_p, v-source of p) for p = 2..6.  Product 1 has
+  // no plane of its own for v: v_1 = -E(x)^2 fhat has the y transform of v_0 = fhat, which is still in Y after product 0 --
+  // it is rescaled in place and transformed along x FIRST (so v_1's transform is the parked factor of product 1).
+  auto plane_of = [&](int i) {
+    const int p = i < 2 ? 0 : i == 2 ? 1 : 2 + (i - 3) / 2, arr = i < 2 ? i : i == 2 ? 0 : (i - 3) & 1;
+    return K::plane(Z, cell, p, arr, kz);
+  };
+  auto issue_plane = [&](int i) {      // one thread: plane i into IN through the TMA unit, plane i + 1 on its way to L2
     mbar_expect_tx(&s_bar, PLANE_BYTES);
-    bulk_load(IN, K::plane(Z, cell, p, arr, kz), PLANE_BYTES, &s_bar);
+    bulk_load(IN, plane_of(i), PLANE_BYTES, &s_bar);
+    if (i + 1 < 13) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(plane_of(i + 1)), "r"(PLANE_BYTES) : "memory");
   };
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    issue_plane(0, 0);
+    issue_plane(0);
   }
   for (int i = tid; i < K::N; i += K::NT) sE[i] = E[i];
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -561,25 +569,35 @@ __global__ void __launch_bounds__(96, 4) k_fc3_f2q(const double2 *__restrict__ Z
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const unsigned tbase = s_tmem;
   const unsigned tacc = tbase + ((unsigned)(warp * 32) << 16);
-  // fourteen array passes, k = 2p + arr (u_p, then the v source of p): ONE copy of the y- and x-stage code (the two-copy
-  // version was 4096 instructions and lost 10 % of its issue slots to instruction fetch with four CTAs in different phases)
-  // the u transform waits for the v transform in registers, except its last eight values: those go to the 32 TMEM columns
-  // the accumulators leave free (with all 24 in registers the v array's y stage spilled most of them to local memory)
-  // ... and eight more to a strip of shared memory of their own (12 KB: four CTAs still fit an SM)
+  // fourteen array passes with ONE copy of the y- and x-stage code (two copies were 4096 instructions and lost 10 % of the
+  // issue slots to instruction fetch with four CTAs in different phases).  The first transform of a product waits for the
+  // second in registers, except its last sixteen values: eight go to the 32 TMEM columns the accumulators leave free, eight
+  // to a strip of shared memory of their own (12 KB: four CTAs still fit an SM) -- with all 24 in registers the next y
+  // stage spilled most of them to local memory, and the four CTAs then ran no faster than two of the six-warp kernel.
   constexpr int UR = K::H - 16;
   double2 uh[UR];
   double2 *upark = reinterpret_cast<double2 *>(sE + K::N) + tid;       // [8][NT]
+  int issued = 1, waited = 0;
   #pragma unroll 1
   for (int k = 0; k < 14; k++) {
-    const int p = k >> 1, arr = k & 1;
-    mbar_wait(&s_bar, (unsigned)k & 1u);    // plane k landed
-    K::ystage1(tid, p, arr, IN, sE, Y);
+    const int p = k < 2 ? 0 : k < 4 ? 1 : 2 + (k - 4) / 2;
+    const bool rescale = k == 2, first = k == 0 || k == 2 || (k >= 4 && !((k - 4) & 1));
+    const int arr = k == 3 ? 0 : k < 2 ? k : (k - 4) & 1;
+    if (rescale) {
+      K::rescale_v1(tid, sE, Y);
+    } else {
+      mbar_wait(&s_bar, (unsigned)(waited++) & 1u);    // the plane landed
+      K::ystage1(tid, p, arr, IN, sE, Y);
+    }
     __syncthreads();                        // Y complete, IN consumed
-    if (k + 1 < 14 && tid == 0) { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); issue_plane((k + 1) >> 1, (k + 1) & 1); }   // arrives while the x stage runs
+    if (!rescale && issued < 13) {
+      if (tid == 0) { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); issue_plane(issued); }   // arrives while the x stage runs
+      issued++;
+    }
     double2 t[K::H];
     K::xhalf(tid, Y, t);
     __syncwarp();                           // the warp holding both h diverged in the pre-stage; tcgen05.* is warp-wide
-    if (arr == 0) {
+    if (first) {
       #pragma unroll
       for (int q = 0; q < UR; q++) uh[q] = t[q];
       #pragma unroll
@@ -610,7 +628,7 @@ __global__ void __launch_bounds__(96, 4) k_fc3_f2q(const double2 *__restrict__ Z
       }
       tmem_wait_st();
     }
-    __syncthreads();                        // every read of Y is done before the next y stage writes it
+    __syncthreads();                        // every read of Y is done before the next pass writes it
   }
   {
     double2 acc[K::H];

@@ -45,17 +45,24 @@ static void emulate(int B, const double2 *fhat, const double *G7, const double *
     for (int cell = 0; cell < B; cell++)
       for (int kz = 0; kz < M; kz++) {
         std::memset(acc.data(), 0, sizeof(Half) * acc.size());
-        for (int p = 0; p < 7; p++) {
-          std::memcpy(IN, K::plane(Z.data(), cell, p, 0, kz), sizeof(double2) * N * N);       // the bulk copy of u_p
-          for (int t = 0; t < K::NT; t++) K::ystage1(t, p, 0, IN, sE.data(), Y);
-          std::memcpy(IN, K::plane(Z.data(), cell, p, 1, kz), sizeof(double2) * N * N);       // ... of the v source, issued here
-          for (int t = 0; t < K::NT; t++) K::xhalf(t, Y, uh[t].a);
-          for (int t = 0; t < K::NT; t++) K::ystage1(t, p, 1, IN, sE.data(), Y);
+        // fourteen array passes as in the kernel: product 1 takes its v factor from product 0's Y (rescaled in place) and
+        // transforms it FIRST; every other product transforms u first
+        for (int k = 0; k < 14; k++) {
+          const int p = k < 2 ? 0 : k < 4 ? 1 : 2 + (k - 4) / 2;
+          const bool rescale = k == 2, first = k == 0 || k == 2 || (k >= 4 && !((k - 4) & 1));
+          const int arr = k == 3 ? 0 : k < 2 ? k : (k - 4) & 1;
+          if (rescale) {
+            for (int t = 0; t < K::NT; t++) K::rescale_v1(t, sE.data(), Y);
+          } else {
+            std::memcpy(IN, K::plane(Z.data(), cell, p, arr, kz), sizeof(double2) * N * N);     // the bulk copy
+            for (int t = 0; t < K::NT; t++) K::ystage1(t, p, arr, IN, sE.data(), Y);
+          }
           for (int t = 0; t < K::NT; t++) {
+            if (first) { K::xhalf(t, Y, uh[t].a); continue; }
             K::xhalf(t, Y, vh[t].a);
-            for (int k = 0; k < K::H; k++) {
-              acc[t].a[k].x += uh[t].a[k].x * vh[t].a[k].x - uh[t].a[k].y * vh[t].a[k].y;
-              acc[t].a[k].y += uh[t].a[k].x * vh[t].a[k].y + uh[t].a[k].y * vh[t].a[k].x;
+            for (int q = 0; q < K::H; q++) {
+              acc[t].a[q].x += uh[t].a[q].x * vh[t].a[q].x - uh[t].a[q].y * vh[t].a[q].y;
+              acc[t].a[q].y += uh[t].a[q].x * vh[t].a[q].y + uh[t].a[q].y * vh[t].a[q].x;
             }
           }
         }
