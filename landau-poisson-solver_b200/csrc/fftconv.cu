@@ -527,8 +527,9 @@ __global__ void __launch_bounds__(192, 2) k_fc3_f2_tmem(const double2 *__restric
 // CTAs overlap those only as two independent streams do (profiles/r02_f2_kernels.md); four streams overlap more.  What
 // makes four fit: one array at a time (41 KB of shared memory: one input plane + one Y array; the next plane is fetched
 // into the input buffer while the x stage runs out of Y), the x stage as two halves per line (96 tasks = 96 threads, a
-// line's inputs read twice instead of three times), the u transform kept in registers across the v array's y stage
-// instead of parked, and the 48 x 48 accumulators in 96 of the CTA's 128 TMEM columns (4 x 128 = all 512).
+// line's inputs read twice instead of three times), the first transform of a product kept across the second array's y
+// stage in registers, 32 spare TMEM columns and a 12 KB strip of shared memory (see below), and the 48 x 48 accumulators in
+// 96 of the CTA's 128 TMEM columns (4 x 128 = all 512).
 __global__ void __launch_bounds__(96, 4) k_fc3_f2q(const double2 *__restrict__ Z, const double *__restrict__ E, double2 *__restrict__ C)
 {
   constexpr int L = 16;
