@@ -213,3 +213,32 @@ extern "C" int fc3_fftN(int N, int sign, const double *in, double *out)
   }
   return 1;
 }
+
+// the line halves of F2Q at L = 16: in = 32 complex inputs (the non-zero two thirds of a 48-point line);
+// fwd: out[h*24 + q] = X[2q + h];  inv: in = 48 complex X (same layout), out[n] = sum_k X[k] exp(+2 pi i n k / 48), n < 48,
+// rebuilt from the two inverse halves as the kernel does (t_0 + t_1, t_0 - t_1)
+extern "C" int fc3_half_lines(int inverse, const double *in, double *out)
+{
+  using namespace fc3;
+  constexpr int L = 16, H = 24;
+  if (!inverse) {
+    double2 a0[L], a1[L];
+    for (int l = 0; l < L; l++) { a0[l] = make_double2(in[2 * l], in[2 * l + 1]); a1[l] = make_double2(in[2 * (l + L)], in[2 * (l + L) + 1]); }
+    for (int h = 0; h < 2; h++) {
+      double2 y[H];
+      fwd_half<L>(a0, a1, h, y);
+      for (int q = 0; q < H; q++) { out[2 * (h * H + q)] = y[q].x; out[2 * (h * H + q) + 1] = y[q].y; }
+    }
+    return 0;
+  }
+  double2 t[2][H];
+  for (int h = 0; h < 2; h++) {
+    for (int q = 0; q < H; q++) t[h][q] = make_double2(in[2 * (h * H + q)], in[2 * (h * H + q) + 1]);
+    inv_half<L>(t[h], h);
+  }
+  for (int n = 0; n < H; n++) {
+    const double2 p = cadd(t[0][n], t[1][n]), m = csub(t[0][n], t[1][n]);
+    out[2 * n] = p.x; out[2 * n + 1] = p.y; out[2 * (n + H)] = m.x; out[2 * (n + H) + 1] = m.y;
+  }
+  return 0;
+}

@@ -97,3 +97,24 @@ def test_register_fft_matches_definition(emul, N, sign):
     k = np.arange(N)
     want = np.exp(sign * 2j * np.pi * np.outer(k, k) / N) @ x
     assert np.abs(out[:, 0] + 1j * out[:, 1] - want).max() < 1e-14 * np.abs(want).max() * N
+
+
+def test_line_halves_match_definition(emul):
+    """fwd_half / inv_half (the x stage of k_fc3_f2q): X[2q + h] of a 48-point line whose last 16 inputs are zero, and the
+    full inverse rebuilt from the two 24-point inverses."""
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    xin = np.ascontiguousarray(np.stack([x.real, x.imag], axis=1))
+    out = np.zeros((48, 2))
+    assert emul.fc3_half_lines(0, xin.ctypes.data_as(P), out.ctypes.data_as(P)) == 0
+    X = np.exp(-2j * np.pi * np.outer(np.arange(48), np.arange(32)) / 48) @ x
+    got = out[:, 0] + 1j * out[:, 1]
+    for h in range(2):
+        assert np.abs(got[h * 24:(h + 1) * 24] - X[h::2]).max() < 1e-13 * np.abs(X).max()
+    Z = rng.standard_normal(48) + 1j * rng.standard_normal(48)
+    zin = np.zeros((48, 2))
+    for h in range(2):
+        zin[h * 24:(h + 1) * 24, 0], zin[h * 24:(h + 1) * 24, 1] = Z[h::2].real, Z[h::2].imag
+    assert emul.fc3_half_lines(1, zin.ctypes.data_as(P), out.ctypes.data_as(P)) == 0
+    want = np.exp(2j * np.pi * np.outer(np.arange(48), np.arange(48)) / 48) @ Z
+    assert np.abs(out[:, 0] + 1j * out[:, 1] - want).max() < 1e-13 * np.abs(want).max()
