@@ -237,8 +237,6 @@ __global__ void __launch_bounds__(256) k_fc_inv_yz(const double2 *__restrict__ C
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
 { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(b)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
-{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(b)) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
 { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
